@@ -1,0 +1,134 @@
+/*
+ * ipoke_b200 -- C ABI of the B200-native iPOKE sampling hot path (libipoke_b200.so).
+ *
+ * Plain pointers and sizes only; no torch types.  Every entry point returns 0 on success or a negative
+ * ipk_status; the message of the last failure on the calling thread is available from ipk_last_error().
+ * All device pointers are CUDA device pointers on the current device; `stream` is a cudaStream_t passed
+ * as void* (NULL = legacy default stream).  Calls are asynchronous on `stream` unless stated otherwise.
+ *
+ * Tensor layouts at this boundary are the reference's own (fp32, NCHW / N-T-C-H-W); the library keeps
+ * NHWC / NDHWC and packed operand planes internally.
+ *
+ * Reference interfaces replaced (paths relative to the CompVis/ipoke checkout):
+ *   ipk_flow_*   <- SupervisedMacowTransformer.forward/reverse     models/modules/INN/INN.py:469-481
+ *                   (MultiScaleInternal.forward                    models/modules/INN/macow2.py:873-920)
+ *   ipk_fs_*     <- PokeMotionModel.decode_first_stage             models/second_stage_video.py:361-382
+ *                   (ConvGRU.forward                               models/modules/motion_models/rnn.py:104-133,
+ *                    SpadeCondConvDecoder.forward                  models/modules/autoencoders/fully_conv_models.py:166-177)
+ *   ipk_sample_* <- PokeMotionModel.forward_sample loop body       models/second_stage_video.py:333-341
+ *   ipk_*_set_tensor takes the reference's state-dict key names unchanged.
+ */
+#ifndef IPOKE_B200_H_
+#define IPOKE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IPK_VERSION 100 /* 0.1.0 */
+
+typedef enum ipk_status {
+  IPK_OK = 0,
+  IPK_ERR_INVALID = -1,   /* bad argument / config                          */
+  IPK_ERR_MISSING = -2,   /* a required state-dict tensor was not provided  */
+  IPK_ERR_SHAPE = -3,     /* tensor numel / dtype mismatch                  */
+  IPK_ERR_CUDA = -4,      /* CUDA runtime / driver failure                  */
+  IPK_ERR_STATE = -5,     /* call order violated (e.g. run before finalize) */
+  IPK_ERR_UNSUPPORTED = -6
+} ipk_status;
+
+/* Arithmetic of the GEMM/conv contractions.  State, norms, affine transforms and log-det are fp32 always. */
+typedef enum ipk_precision {
+  IPK_PREC_FP32_SIMT = 0,   /* fp32 FFMA kernels everywhere (validation engine, small layers)              */
+  IPK_PREC_FP32_SPLIT = 1,  /* tcgen05 bf16x3 error-compensated MMA (a_hi*b_hi + a_lo*b_hi + a_hi*b_lo)      */
+  IPK_PREC_BF16 = 2         /* tcgen05 bf16 operands, fp32 accumulate                                       */
+} ipk_precision;
+
+typedef enum ipk_dtype { IPK_F32 = 0, IPK_I64 = 1, IPK_U8 = 2 } ipk_dtype;
+
+#define IPK_MAX_LEVELS 32
+#define IPK_MAX_DEC 8
+
+/* Mirrors the keys SupervisedMacowTransformer reads from config['architecture'] (INN.py:448-467). */
+typedef struct ipk_flow_config {
+  int32_t flow_in_channels;           /* C0                                   */
+  int32_t flow_mid_channels;          /* hidden width of the NICE couplings   */
+  int32_t h_channels;                 /* conditioning channels                */
+  int32_t n_levels;                   /* len(num_steps)                       */
+  int32_t num_steps[IPK_MAX_LEVELS];
+  int32_t factor;
+  int32_t kernel_h, kernel_w;         /* kernel_size (2,3)                    */
+  int32_t precision;                  /* ipk_precision                        */
+  int32_t max_batch;                  /* workspace is sized for this batch    */
+} ipk_flow_config;
+
+/* Mirrors config['architecture'] of the first stage (config/first_stage.yaml:50-63). */
+typedef struct ipk_fs_config {
+  int32_t z_dim;
+  int32_t spatial;                    /* output H = W (64 or 128)             */
+  int32_t n_gru_layers;
+  int32_t n_dec;                      /* len(dec_channels)                    */
+  int32_t dec_channels[IPK_MAX_DEC];
+  int32_t precision;                  /* ipk_precision                        */
+  int32_t max_batch;
+  int32_t max_frames;                 /* max T per decode call                */
+  int32_t chunk_videos;               /* videos decoded per pass (0 = auto)   */
+} ipk_fs_config;
+
+typedef struct ipk_flow ipk_flow;
+typedef struct ipk_fs ipk_fs;
+
+int ipk_version(void);
+const char* ipk_last_error(void);
+/* number of kernels this library has launched on the calling thread since the last reset */
+int64_t ipk_launch_count(void);
+void ipk_launch_count_reset(void);
+
+/* ---- conditional MaCow flow ---- */
+int ipk_flow_create(const ipk_flow_config* cfg, ipk_flow** out);
+/* name: state-dict key without the module prefix, e.g. "flow.layers.0.0.actnorm1.log_scale". The data is
+ * read during ipk_flow_finalize and must stay valid until then. */
+int ipk_flow_set_tensor(ipk_flow* f, const char* name, const void* dev_ptr, int64_t numel, int dtype);
+/* folds weight-norm, packs operands for the selected precision; synchronises `stream`. */
+int ipk_flow_finalize(ipk_flow* f, void* stream);
+/* sampling direction: z[B,C0,8,8], cond[B,h,8,8] -> out[B,C0,8,8] */
+int ipk_flow_reverse(ipk_flow* f, const float* z, const float* cond, float* out, int32_t B, void* stream);
+/* density direction: x -> z[B,C0,8,8], logdet[B] */
+int ipk_flow_forward(ipk_flow* f, const float* x, const float* cond, float* z, float* logdet, int32_t B, void* stream);
+int ipk_flow_destroy(ipk_flow* f);
+
+/* ---- first-stage decoder: latent ConvGRU + SPADE decoder ---- */
+int ipk_fs_create(const ipk_fs_config* cfg, ipk_fs** out);
+int ipk_fs_set_tensor(ipk_fs* d, const char* name, const void* dev_ptr, int64_t numel, int dtype);
+int ipk_fs_finalize(ipk_fs* d, void* stream);
+/* motion[B,z,8,8], x0[B,3,S,S] -> frames[B,T,3,S,S] */
+int ipk_fs_decode(ipk_fs* d, const float* motion, const float* x0, float* frames, int32_t B, int32_t T, void* stream);
+/* one ConvGRU step (ConvGRU.forward): x[B,z,8,8], hidden[L][B,z,8,8] -> new_hidden[L][B,z,8,8] */
+int ipk_fs_gru_step(ipk_fs* d, const float* x, const float* hidden, float* new_hidden, int32_t B, void* stream);
+/* one decoder pass (SpadeCondConvDecoder.forward): h[B,z,8,8], x0[B,3,S,S] -> frame[B,3,S,S] */
+int ipk_fs_gen(ipk_fs* d, const float* h, const float* x0, float* frame, int32_t B, void* stream);
+int ipk_fs_destroy(ipk_fs* d);
+
+/* ---- whole sampling step with DEVICE buffers: flow inverse -> GRU + decoder ---- */
+int ipk_sample(ipk_flow* f, ipk_fs* d, const float* z, const float* cond, const float* x0, float* frames,
+               int32_t B, int32_t T, void* stream);
+/* ---- same with HOST buffers (pinned or pageable): H2D, compute, D2H, stream-synchronised on return ---- */
+int ipk_sample_host(ipk_flow* f, ipk_fs* d, const float* z_host, const float* cond_host, const float* x0_host,
+                    float* frames_host, int32_t B, int32_t T, void* stream);
+
+/* ---- kernel-level test hooks (used by tests/ to check single kernels against the oracle) ---- */
+/* out[M,N] = A[M,K] * W[N,K]^T through the engine selected by `precision` */
+int ipk_test_gemm(const float* A, const float* W, float* out, int32_t M, int32_t N, int32_t K, int32_t precision, void* stream);
+/* 3x3 stride-1 pad-1 conv, NHWC in[F,H,W,Cin], OIHW weights w[Cout,Cin,3,3] -> NHWC out[F,H,W,Cout] */
+int ipk_test_conv3x3(const float* in, const float* w, const float* bias, float* out, int32_t F, int32_t H, int32_t W,
+                     int32_t Cin, int32_t Cout, int32_t precision, void* stream);
+/* ConvTranspose2d(3, stride 2, pad 1, output_pad 1), NHWC in[F,H,W,Cin], IOHW weights -> NHWC out[F,2H,2W,Cout] */
+int ipk_test_convT3x3(const float* in, const float* w, const float* bias, float* out, int32_t F, int32_t H, int32_t W,
+                      int32_t Cin, int32_t Cout, int32_t precision, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IPOKE_B200_H_ */

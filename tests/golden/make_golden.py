@@ -1,0 +1,127 @@
+"""Generate the golden fixtures in tests/golden/*.pt by running the UNMODIFIED reference modules.
+
+Run in the build container only (needs /root/reference):   python tests/golden/make_golden.py [--full]
+
+For every case the synthetic state-dict from oracle/ipoke_oracle.py is loaded into the reference's own
+modules with load_state_dict(strict=True) (so key names / shapes are proven identical to the reference
+checkpoint layout), the reference is run on seeded inputs, and its outputs are stored.  The oracle is
+compared against the reference in the same run and the max-abs differences are stored beside the outputs.
+Inputs and weights are NOT stored: they regenerate from the seeds recorded in each fixture.
+"""
+import argparse
+import os
+import sys
+import time
+import warnings
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+warnings.filterwarnings("ignore")
+
+import ref_import  # noqa: E402
+from oracle import ipoke_oracle as O  # noqa: E402
+
+FLOW_CASES = {
+    # name: (cfg kwargs, B, weight seed, input seed)
+    "flow_tiny_even": (dict(flow_in_channels=16, flow_mid_channels=64, h_channels=16, num_steps=[2, 1, 1], factor=4), 3, 1, 11),
+    "flow_tiny_odd": (dict(flow_in_channels=16, flow_mid_channels=48, h_channels=8, num_steps=[1, 1], factor=3), 2, 2, 12),
+    "flow_c32_hd128": (dict(flow_in_channels=32, flow_mid_channels=128, h_channels=128), 2, 3, 13),
+    "flow_c64_hd128": (dict(flow_in_channels=64, flow_mid_channels=128, h_channels=128, num_steps=[1] * 15), 2, 4, 14),
+}
+FULL_FLOW_CASES = {
+    "flow_full_c32": (dict(flow_in_channels=32, flow_mid_channels=2048, h_channels=128), 2, 5, 42),
+}
+FS_CASES = {
+    # name: (cfg kwargs, B, T, weight seed, input seed)
+    "fs_64": (dict(z_dim=32, spatial=64), 2, 3, 21, 31),
+    "fs_128": (dict(z_dim=32, spatial=128), 1, 2, 22, 32),
+    "fs_64_z64": (dict(z_dim=64, spatial=64), 1, 2, 23, 33),
+}
+
+
+def ref_flow(cfg, sd):
+    Flow = ref_import.flow_cls()
+    m = Flow(dict(cfg))
+    m.load_state_dict(sd, strict=True)
+    return m.eval()
+
+
+def run_flow_case(name, spec, out_dir):
+    kw, B, wseed, iseed = spec
+    cfg = O.flow_config(**kw)
+    t0 = time.time()
+    sd = O.synth_flow_state_dict(cfg, seed=wseed)
+    z, cond, _ = O.synth_inputs(B, cfg["flow_in_channels"], cfg["h_channels"], 8, seed=iseed)
+    m = ref_flow(cfg, sd)
+    with torch.no_grad():
+        x_ref = m(z, cond, reverse=True)                 # sampling direction
+        z2_ref, ld_ref = m(x_ref, cond, reverse=False)   # density direction on the sampled latent
+        x_or = O.flow_reverse(sd, cfg, z, cond)
+        z2_or, ld_or = O.flow_forward(sd, cfg, x_ref, cond)
+        x64 = O.flow_reverse(sd, cfg, z.double(), cond.double())
+    fix = dict(kind="flow", cfg_kwargs=kw, B=B, wseed=wseed, iseed=iseed,
+               x_rev=x_ref.clone(), z_fwd=z2_ref.clone(), logdet=ld_ref.clone(),
+               oracle_vs_ref=dict(rev=(x_or - x_ref).abs().max().item(), fwd=(z2_or - z2_ref).abs().max().item(),
+                                  logdet=(ld_or - ld_ref).abs().max().item()),
+               ref_fp32_vs_oracle_fp64=(x64.float() - x_ref).abs().max().item(),
+               roundtrip=(z2_ref - z).abs().max().item(),
+               x_std=x_ref.std().item(), torch_version=torch.__version__)
+    torch.save(fix, os.path.join(out_dir, name + ".pt"))
+    print(f"{name}: {time.time() - t0:.1f}s  oracle-vs-ref {fix['oracle_vs_ref']}  fp64 {fix['ref_fp32_vs_oracle_fp64']:.2e} "
+          f"roundtrip {fix['roundtrip']:.2e}  x std {fix['x_std']:.3f}  logdet {ld_ref.tolist()}")
+
+
+def run_fs_case(name, spec, out_dir):
+    kw, B, T, wseed, iseed = spec
+    cfg = O.first_stage_config(**kw)
+    sd = O.synth_first_stage_state_dict(cfg, seed=wseed)
+    ConvGRU, Dec = ref_import.first_stage_parts()
+    rnn = ConvGRU(input_size=cfg["z_dim"], hidden_sizes=cfg["z_dim"], n_layers=cfg["n_gru_layers"], kernel_sizes=3,
+                  upsampling=[False] * cfg["n_gru_layers"])
+    gen = Dec(dict(cfg))
+    rnn.load_state_dict({k[len("rnn."):]: v for k, v in sd.items() if k.startswith("rnn.")}, strict=True)
+    gen.load_state_dict({k[len("gen."):]: v for k, v in sd.items() if k.startswith("gen.")}, strict=True)
+    rnn.eval(); gen.eval()
+    g = torch.Generator().manual_seed(iseed)
+    motion = torch.randn((B, cfg["z_dim"], 8, 8), generator=g) * 1.3
+    x0 = torch.rand((B, 3, cfg["spatial"], cfg["spatial"]), generator=g) * 2 - 1
+    with torch.no_grad():
+        # decode_first_stage, second_stage_video.py:361-382
+        hidden = [motion] * cfg["n_gru_layers"]
+        in_rnn = torch.cat([sd["motion_bias"]] * B, dim=0)
+        frames, hid_last = [], None
+        for _ in range(T):
+            hidden = rnn(in_rnn, hidden)
+            frames.append(gen([hidden[-1]], x0, del_shape=True))
+        ref = torch.stack(frames, dim=1)
+        orc = O.decode_first_stage(sd, cfg, motion, x0, T)
+        orc64 = O.decode_first_stage(sd, cfg, motion.double(), x0.double(), T)
+    fix = dict(kind="first_stage", cfg_kwargs=kw, B=B, T=T, wseed=wseed, iseed=iseed, frames=ref.clone(),
+               hidden_last=hidden[-1].clone(),
+               oracle_vs_ref=(orc - ref).abs().max().item(),
+               ref_fp32_vs_oracle_fp64=(orc64.float() - ref).abs().max().item(), torch_version=torch.__version__)
+    torch.save(fix, os.path.join(out_dir, name + ".pt"))
+    print(f"{name}: oracle-vs-ref {fix['oracle_vs_ref']:.2e}  fp64 {fix['ref_fp32_vs_oracle_fp64']:.2e} "
+          f"frames std {ref.std().item():.3f} range [{ref.min().item():.3f},{ref.max().item():.3f}]")
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--full", action="store_true", help="also run the full-size (1.05 B parameter) flow case")
+    ap.add_argument("--only", default=None)
+    a = ap.parse_args()
+    torch.manual_seed(0)
+    for n, s in FLOW_CASES.items():
+        if a.only in (None, n):
+            run_flow_case(n, s, HERE)
+    for n, s in FS_CASES.items():
+        if a.only in (None, n):
+            run_fs_case(n, s, HERE)
+    if a.full:
+        for n, s in FULL_FLOW_CASES.items():
+            if a.only in (None, n):
+                run_flow_case(n, s, HERE)

@@ -1,0 +1,76 @@
+"""The CPU oracle (oracle/ipoke_oracle.py) against the golden fixtures produced by the UNMODIFIED reference
+modules (tests/golden/make_golden.py).  Pins the oracle; runs anywhere (no GPU, no /root/reference)."""
+import pytest
+import torch
+
+from conftest import golden
+from oracle import ipoke_oracle as O
+
+FLOW = ["flow_tiny_even", "flow_tiny_odd", "flow_c32_hd128", "flow_c64_hd128"]
+FS = ["fs_64", "fs_128", "fs_64_z64"]
+TOL = 2e-4  # fp32 re-association noise of a 1000-layer flow; fixtures record ref-fp32 vs oracle-fp64 of the same size
+
+
+@pytest.mark.parametrize("name", FLOW)
+def test_flow_oracle_matches_reference(name):
+    fx = golden(name)
+    cfg = O.flow_config(**fx["cfg_kwargs"])
+    sd = O.synth_flow_state_dict(cfg, seed=fx["wseed"])
+    z, cond, _ = O.synth_inputs(fx["B"], cfg["flow_in_channels"], cfg["h_channels"], 8, seed=fx["iseed"])
+    with torch.no_grad():
+        x = O.flow_reverse(sd, cfg, z, cond)
+        z2, ld = O.flow_forward(sd, cfg, fx["x_rev"], cond)
+    assert (x - fx["x_rev"]).abs().max().item() < TOL
+    assert (z2 - fx["z_fwd"]).abs().max().item() < TOL
+    assert (ld - fx["logdet"]).abs().max().item() < 1e-3 * max(1.0, fx["logdet"].abs().max().item())
+    # invertibility (SURVEY.md section 8c known-answer property i)
+    assert (z2 - z).abs().max().item() < 1e-3
+
+
+@pytest.mark.parametrize("name", FS)
+def test_first_stage_oracle_matches_reference(name):
+    fx = golden(name)
+    cfg = O.first_stage_config(**fx["cfg_kwargs"])
+    sd = O.synth_first_stage_state_dict(cfg, seed=fx["wseed"])
+    g = torch.Generator().manual_seed(fx["iseed"])
+    motion = torch.randn((fx["B"], cfg["z_dim"], 8, 8), generator=g) * 1.3
+    x0 = torch.rand((fx["B"], 3, cfg["spatial"], cfg["spatial"]), generator=g) * 2 - 1
+    with torch.no_grad():
+        frames = O.decode_first_stage(sd, cfg, motion, x0, fx["T"])
+    assert frames.shape == fx["frames"].shape
+    assert (frames - fx["frames"]).abs().max().item() < 5e-5
+
+
+def test_shuffle_roundtrip_exact():
+    cfg = O.flow_config(flow_in_channels=16, flow_mid_channels=16, h_channels=4, num_steps=[1], factor=2)
+    sd = O.synth_flow_state_dict(cfg, seed=9)
+    x = torch.randn(2, 16, 8, 8)
+    p = "flow.layers.0.0.conv1x1."
+    assert torch.equal(O.shuffle_bwd(sd, p, O.shuffle_fwd(sd, p, x)), x)
+
+
+def test_identity_init_logdet_is_actnorm_sum():
+    """Known-answer property ii: with weight_g = 0 and zero biases every coupling is the identity and
+    logdet = H*W*sum(ActNorm log_scale), identical for all samples."""
+    cfg = O.flow_config(flow_in_channels=16, flow_mid_channels=16, h_channels=4, num_steps=[1, 1], factor=4)
+    sd = O.synth_flow_state_dict(cfg, seed=3)
+    tot = 0.0
+    for k in sd:
+        if k.endswith("weight_g") or k.endswith("conv.bias"):
+            sd[k] = torch.zeros_like(sd[k])
+        if k.endswith("log_scale"):
+            tot += 64.0 * sd[k].sum().item()
+    z, cond, _ = O.synth_inputs(3, 16, 4, 8, seed=1)
+    _, ld = O.flow_forward(sd, cfg, z, cond)
+    assert torch.allclose(ld, torch.full((3,), tot), atol=1e-4)
+
+
+@pytest.mark.slow
+def test_full_size_flow_oracle_matches_reference():
+    fx = golden("flow_full_c32")
+    cfg = O.flow_config(**fx["cfg_kwargs"])
+    sd = O.synth_flow_state_dict(cfg, seed=fx["wseed"])
+    z, cond, _ = O.synth_inputs(fx["B"], 32, 128, 8, seed=fx["iseed"])
+    with torch.no_grad():
+        x = O.flow_reverse(sd, cfg, z, cond)
+    assert (x - fx["x_rev"]).abs().max().item() < 5e-4
