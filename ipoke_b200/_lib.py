@@ -1,0 +1,114 @@
+"""ctypes binding of libipoke_b200.so (the C ABI declared in include/ipoke_b200.h).
+
+There is no CPU fallback: importing this module without the built library raises, and every entry point raises
+RuntimeError with the library's message when the native call fails.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libipoke_b200.so")
+
+IPK_MAX_LEVELS = 32
+IPK_MAX_DEC = 8
+PREC = {"fp32_simt": 0, "fp32": 1, "fp32_split": 1, "bf16": 2}
+DT_F32, DT_I64, DT_U8 = 0, 1, 2
+
+
+class FlowConfig(ctypes.Structure):
+    _fields_ = [("flow_in_channels", ctypes.c_int32), ("flow_mid_channels", ctypes.c_int32), ("h_channels", ctypes.c_int32),
+                ("n_levels", ctypes.c_int32), ("num_steps", ctypes.c_int32 * IPK_MAX_LEVELS), ("factor", ctypes.c_int32),
+                ("kernel_h", ctypes.c_int32), ("kernel_w", ctypes.c_int32), ("precision", ctypes.c_int32),
+                ("max_batch", ctypes.c_int32)]
+
+
+class FsConfig(ctypes.Structure):
+    _fields_ = [("z_dim", ctypes.c_int32), ("spatial", ctypes.c_int32), ("n_gru_layers", ctypes.c_int32),
+                ("n_dec", ctypes.c_int32), ("dec_channels", ctypes.c_int32 * IPK_MAX_DEC), ("precision", ctypes.c_int32),
+                ("max_batch", ctypes.c_int32), ("max_frames", ctypes.c_int32), ("chunk_videos", ctypes.c_int32)]
+
+
+EXPORTS = [
+    "ipk_version", "ipk_last_error", "ipk_launch_count", "ipk_launch_count_reset",
+    "ipk_flow_create", "ipk_flow_set_tensor", "ipk_flow_finalize", "ipk_flow_reverse", "ipk_flow_forward", "ipk_flow_destroy",
+    "ipk_fs_create", "ipk_fs_set_tensor", "ipk_fs_finalize", "ipk_fs_decode", "ipk_fs_gru_step", "ipk_fs_gen", "ipk_fs_destroy",
+    "ipk_sample", "ipk_sample_host", "ipk_test_gemm", "ipk_test_conv3x3", "ipk_test_convT3x3",
+]
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"ipoke_b200: native library not built ({LIB_PATH}); run `make` or __graft_entry__.build(). "
+                           "There is no CPU fallback.")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64, cp = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_char_p
+    L.ipk_version.restype = ctypes.c_int
+    L.ipk_last_error.restype = cp
+    L.ipk_launch_count.restype = i64
+    L.ipk_launch_count_reset.restype = None
+    L.ipk_flow_create.argtypes = [ctypes.POINTER(FlowConfig), ctypes.POINTER(vp)]
+    L.ipk_flow_set_tensor.argtypes = [vp, cp, vp, i64, ctypes.c_int]
+    L.ipk_flow_finalize.argtypes = [vp, vp]
+    L.ipk_flow_reverse.argtypes = [vp, vp, vp, vp, i32, vp]
+    L.ipk_flow_forward.argtypes = [vp, vp, vp, vp, vp, i32, vp]
+    L.ipk_flow_destroy.argtypes = [vp]
+    L.ipk_fs_create.argtypes = [ctypes.POINTER(FsConfig), ctypes.POINTER(vp)]
+    L.ipk_fs_set_tensor.argtypes = [vp, cp, vp, i64, ctypes.c_int]
+    L.ipk_fs_finalize.argtypes = [vp, vp]
+    L.ipk_fs_decode.argtypes = [vp, vp, vp, vp, i32, i32, vp]
+    L.ipk_fs_gru_step.argtypes = [vp, vp, vp, vp, i32, vp]
+    L.ipk_fs_gen.argtypes = [vp, vp, vp, vp, i32, vp]
+    L.ipk_fs_destroy.argtypes = [vp]
+    L.ipk_sample.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp]
+    L.ipk_sample_host.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp]
+    L.ipk_test_gemm.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
+    L.ipk_test_conv3x3.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
+    L.ipk_test_convT3x3.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
+    for name in EXPORTS:
+        fn = getattr(L, name)
+        if name.startswith(("ipk_flow_", "ipk_fs_", "ipk_sample", "ipk_test_")):
+            fn.restype = ctypes.c_int
+    _lib = L
+    return L
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"ipoke_b200: {what} failed (status {rc}): {lib().ipk_last_error().decode()}")
+
+
+def precision_code(p):
+    if isinstance(p, int):
+        return p
+    if p not in PREC:
+        raise ValueError(f"unknown precision {p!r}; use one of {sorted(PREC)}")
+    return PREC[p]
+
+
+def current_stream_ptr():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def dtype_code(t):
+    import torch
+    if t.dtype == torch.float32:
+        return DT_F32
+    if t.dtype == torch.int64:
+        return DT_I64
+    if t.dtype == torch.uint8:
+        return DT_U8
+    raise TypeError(f"unsupported tensor dtype {t.dtype}")
+
+
+def launch_count():
+    return int(lib().ipk_launch_count())
+
+
+def launch_count_reset():
+    lib().ipk_launch_count_reset()

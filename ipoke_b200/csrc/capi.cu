@@ -1,0 +1,222 @@
+// C ABI glue: error state, launch counter, whole-step entry points and kernel-level test hooks.
+#include <cstdarg>
+#include <mutex>
+#include <map>
+#include "conv.cuh"
+#include "elementwise.cuh"
+
+namespace ipk {
+
+thread_local std::string g_last_error;
+thread_local int64_t g_launches = 0;
+
+void set_last_error(const std::string& m) { g_last_error = m; }
+
+[[noreturn]] void fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  throw Error(code, buf);
+}
+
+// ---- profiler
+namespace {
+struct ProfRec { std::string tag; cudaEvent_t e0, e1; };
+std::vector<ProfRec> g_prof;
+std::vector<size_t> g_prof_open;
+bool g_prof_on = false;
+}
+bool& Prof::enabled() { return g_prof_on; }
+void Prof::begin(const char* tag, cudaStream_t st) {
+  ProfRec r;
+  r.tag = tag;
+  cudaEventCreate(&r.e0);
+  cudaEventCreate(&r.e1);
+  cudaEventRecord(r.e0, st);
+  g_prof.push_back(r);
+  g_prof_open.push_back(g_prof.size() - 1);
+}
+void Prof::end(cudaStream_t st) {
+  if (g_prof_open.empty()) return;
+  cudaEventRecord(g_prof[g_prof_open.back()].e1, st);
+  g_prof_open.pop_back();
+}
+
+}  // namespace ipk
+
+using namespace ipk;
+
+extern "C" void ipk_prof_enable(int on) {
+  for (auto& r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  g_prof.clear();
+  g_prof_open.clear();
+  g_prof_on = on != 0;
+}
+// writes "tag count total_ms\n" lines into buf; returns the number of bytes needed
+extern "C" int ipk_prof_report(char* buf, int cap) {
+  cudaDeviceSynchronize();
+  std::map<std::string, std::pair<int, double>> acc;
+  std::vector<std::string> order;
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) { cudaGetLastError(); continue; }
+    if (!acc.count(r.tag)) order.push_back(r.tag);
+    acc[r.tag].first += 1;
+    acc[r.tag].second += ms;
+  }
+  std::string out;
+  char line[256];
+  for (auto& t : order) {
+    snprintf(line, sizeof(line), "%s %d %.6f\n", t.c_str(), acc[t].first, acc[t].second);
+    out += line;
+  }
+  if (buf && cap > 0) { snprintf(buf, cap, "%s", out.c_str()); }
+  return (int)out.size() + 1;
+}
+
+// defined in flow.cu / decoder.cu
+struct ipk_flow;
+struct ipk_fs;
+int ipk_fs_decode_nhwc(ipk_fs* d, const float* motion_nhwc, const float* x0, float* frames, int B, int T, cudaStream_t st);
+int ipk_flow_reverse_nhwc(ipk_flow* f, const float* z, const float* cond, const float** state_nhwc, int B, cudaStream_t st);
+
+extern "C" int ipk_version(void) { return IPK_VERSION; }
+extern "C" const char* ipk_last_error(void) { return g_last_error.c_str(); }
+extern "C" int64_t ipk_launch_count(void) { return g_launches; }
+extern "C" void ipk_launch_count_reset(void) { g_launches = 0; }
+
+extern "C" int ipk_sample(ipk_flow* f, ipk_fs* d, const float* z, const float* cond, const float* x0, float* frames,
+                          int32_t B, int32_t T, void* stream) {
+  IPK_TRY
+  IPK_CHECK(f && d && z && cond && x0 && frames, IPK_ERR_INVALID, "ipk_sample: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const float* motion = nullptr;   // flow state stays NHWC on device and feeds the GRU directly
+  int rc = ipk_flow_reverse_nhwc(f, z, cond, &motion, B, st);
+  if (rc != 0) return rc;
+  ipk_fs_decode_nhwc(d, motion, x0, frames, B, T, st);
+  IPK_CATCH
+}
+
+namespace {
+struct HostStage {
+  float *z = nullptr, *cond = nullptr, *x0 = nullptr, *frames = nullptr;
+  size_t nz = 0, nc = 0, nx = 0, nf = 0;
+  void ensure(float** p, size_t* cap, size_t n) {
+    if (*cap >= n) return;
+    if (*p) cudaFree(*p);
+    IPK_CUDA(cudaMalloc((void**)p, n * sizeof(float)));
+    *cap = n;
+  }
+};
+HostStage g_stage;
+std::mutex g_stage_mu;
+}  // namespace
+
+struct FlowDims { int C0, hch; };
+FlowDims ipk_flow_dims(ipk_flow* f);
+int ipk_fs_spatial(ipk_fs* d);
+
+extern "C" int ipk_sample_host(ipk_flow* f, ipk_fs* d, const float* z_host, const float* cond_host, const float* x0_host,
+                               float* frames_host, int32_t B, int32_t T, void* stream) {
+  IPK_TRY
+  IPK_CHECK(f && d && z_host && cond_host && x0_host && frames_host, IPK_ERR_INVALID, "ipk_sample_host: null argument");
+  std::lock_guard<std::mutex> lk(g_stage_mu);
+  cudaStream_t st = (cudaStream_t)stream;
+  FlowDims fd = ipk_flow_dims(f);
+  const int S = ipk_fs_spatial(d);
+  const size_t nz = (size_t)B * fd.C0 * 64, nc = (size_t)B * fd.hch * 64, nx = (size_t)B * 3 * S * S, nf = (size_t)B * T * 3 * S * S;
+  g_stage.ensure(&g_stage.z, &g_stage.nz, nz);
+  g_stage.ensure(&g_stage.cond, &g_stage.nc, nc);
+  g_stage.ensure(&g_stage.x0, &g_stage.nx, nx);
+  g_stage.ensure(&g_stage.frames, &g_stage.nf, nf);
+  IPK_CUDA(cudaMemcpyAsync(g_stage.z, z_host, nz * 4, cudaMemcpyHostToDevice, st));
+  IPK_CUDA(cudaMemcpyAsync(g_stage.cond, cond_host, nc * 4, cudaMemcpyHostToDevice, st));
+  IPK_CUDA(cudaMemcpyAsync(g_stage.x0, x0_host, nx * 4, cudaMemcpyHostToDevice, st));
+  const float* motion = nullptr;
+  int rc = ipk_flow_reverse_nhwc(f, g_stage.z, g_stage.cond, &motion, B, st);
+  if (rc != 0) return rc;
+  ipk_fs_decode_nhwc(d, motion, g_stage.x0, g_stage.frames, B, T, st);
+  IPK_CUDA(cudaMemcpyAsync(frames_host, g_stage.frames, nf * 4, cudaMemcpyDeviceToHost, st));
+  IPK_CUDA(cudaStreamSynchronize(st));
+  IPK_CATCH
+}
+
+// ------------------------------------------------------------------------------------------ test hooks
+namespace {
+struct Tmp {
+  std::vector<void*> v;
+  template <typename T> T* alloc(size_t n) { void* p; IPK_CUDA(cudaMalloc(&p, std::max<size_t>(n * sizeof(T), 16))); v.push_back(p); return (T*)p; }
+  ~Tmp() { for (void* p : v) cudaFree(p); }
+};
+
+// fp32 NHWC tensor -> operand of `engine` (returns hi pointer; lo through *lo)
+void* make_operand(Tmp& tmp, const float* x, long long rows, int C, int engine, void** lo, cudaStream_t st) {
+  *lo = nullptr;
+  if (engine == IPK_PREC_FP32_SIMT) return (void*)x;
+  __nv_bfloat16* hi = tmp.alloc<__nv_bfloat16>((size_t)rows * C);
+  NormApply n; n.x = x; n.F = 1; n.P = rows; n.C = C; n.out_hi = hi;
+  if (engine == IPK_PREC_FP32_SPLIT) { n.out_lo = tmp.alloc<__nv_bfloat16>((size_t)rows * C); *lo = n.out_lo; }
+  norm_apply(n, st);
+  return hi;
+}
+}  // namespace
+
+extern "C" int ipk_test_gemm(const float* A, const float* W, float* out, int32_t M, int32_t N, int32_t K, int32_t precision, void* stream) {
+  IPK_TRY
+  cudaStream_t st = (cudaStream_t)stream;
+  IPK_CHECK(K % 4 == 0, IPK_ERR_UNSUPPORTED, "ipk_test_gemm: K must be a multiple of 4");
+  if (precision != IPK_PREC_FP32_SIMT) IPK_CHECK(K % 8 == 0, IPK_ERR_UNSUPPORTED, "ipk_test_gemm: tensor-core engine needs K %% 8 == 0");
+  DevPool pool;
+  Tmp tmp;
+  ConvW w = conv_alloc(pool, precision, 1, K, N, false);
+  PackSrc s; s.w = W; s.N = N; s.Ksrc = K;
+  conv_pack_into(w, 0, s, {0}, st);
+  ConvIn in; in.cstride = K; in.F = M; in.H = 1; in.W = 1;
+  in.p = make_operand(tmp, A, M, K, precision, (void**)&in.p_lo, st);
+  ConvOut o; o.p = out; o.cstride = N; o.Ho = 1; o.Wo = 1;
+  conv_run(w, in, o, taps_1x1(), 1, st);
+  IPK_CUDA(cudaStreamSynchronize(st));
+  pool.release();
+  IPK_CATCH
+}
+
+static int test_conv_impl(const float* in_, const float* w_, const float* bias, float* out, int F, int H, int W, int Cin, int Cout,
+                          int precision, bool transposed, cudaStream_t st) {
+  IPK_TRY
+  IPK_CHECK(Cin % 4 == 0, IPK_ERR_UNSUPPORTED, "test conv: Cin must be a multiple of 4");
+  if (precision != IPK_PREC_FP32_SIMT) IPK_CHECK(Cin % 8 == 0, IPK_ERR_UNSUPPORTED, "test conv: tensor-core engine needs Cin %% 8 == 0");
+  DevPool pool;
+  Tmp tmp;
+  ConvW w = conv_alloc(pool, precision, 9, Cin, Cout, bias != nullptr);
+  PackSrc s; s.w = w_; s.N = Cout; s.Ksrc = Cin; s.kh = 3; s.kw = 3; s.transposed = transposed;
+  conv_pack_into(w, 0, s, {0, 1, 2, 3, 4, 5, 6, 7, 8}, st);
+  if (bias) conv_pack_bias(w, 0, bias, Cout, 0.f, st);
+  ConvIn in; in.cstride = Cin; in.F = F; in.H = H; in.W = W;
+  in.p = make_operand(tmp, in_, (long long)F * H * W, Cin, precision, (void**)&in.p_lo, st);
+  ConvOut o; o.p = out; o.cstride = Cout; o.bias = w.bias;
+  if (!transposed) {
+    o.Ho = H; o.Wo = W;
+    conv_run(w, in, o, taps_3x3(), 1, st);
+  } else {
+    o.Ho = 2 * H; o.Wo = 2 * W; o.ymul = 2; o.xmul = 2;
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) {
+        o.yadd = a; o.xadd = b;
+        conv_run(w, in, o, taps_convT(a, b), 1, st);
+      }
+  }
+  IPK_CUDA(cudaStreamSynchronize(st));
+  pool.release();
+  IPK_CATCH
+}
+
+extern "C" int ipk_test_conv3x3(const float* in, const float* w, const float* bias, float* out, int32_t F, int32_t H, int32_t W,
+                                int32_t Cin, int32_t Cout, int32_t precision, void* stream) {
+  return test_conv_impl(in, w, bias, out, F, H, W, Cin, Cout, precision, false, (cudaStream_t)stream);
+}
+extern "C" int ipk_test_convT3x3(const float* in, const float* w, const float* bias, float* out, int32_t F, int32_t H, int32_t W,
+                                 int32_t Cin, int32_t Cout, int32_t precision, void* stream) {
+  return test_conv_impl(in, w, bias, out, F, H, W, Cin, Cout, precision, true, (cudaStream_t)stream);
+}

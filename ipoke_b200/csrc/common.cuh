@@ -1,0 +1,167 @@
+// Shared helpers for the ipoke_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <stdexcept>
+#include <vector>
+#include <algorithm>
+
+#include "../../include/ipoke_b200.h"
+
+namespace ipk {
+
+// ---------------------------------------------------------------- errors
+struct Error : public std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+void set_last_error(const std::string& m);
+[[noreturn]] void fail(int code, const char* fmt, ...);
+
+#define IPK_CUDA(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess)                                                                          \
+      ::ipk::fail(IPK_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define IPK_CHECK(cond, code, ...)                  \
+  do {                                              \
+    if (!(cond)) ::ipk::fail((code), __VA_ARGS__);  \
+  } while (0)
+
+// launch bookkeeping (gpu_launches in bench.py)
+extern thread_local int64_t g_launches;
+inline void count_launch(int n = 1) { g_launches += n; }
+#define IPK_LAUNCH_CHECK()                \
+  do {                                    \
+    ::ipk::count_launch();                \
+    IPK_CUDA(cudaGetLastError());         \
+  } while (0)
+
+// ---------------------------------------------------------------- optional per-phase device timing
+// When enabled (ipk_prof_enable), every ProfScope brackets the launches issued inside it with CUDA events on the launch
+// stream; ipk_prof_report() sums the elapsed time per tag.  Disabled: zero cost besides one branch.
+struct Prof {
+  static bool& enabled();
+  static void begin(const char* tag, cudaStream_t st);
+  static void end(cudaStream_t st);
+};
+struct ProfScope {
+  cudaStream_t st;
+  bool on;
+  ProfScope(const char* tag, cudaStream_t s) : st(s), on(Prof::enabled()) { if (on) Prof::begin(tag, st); }
+  ~ProfScope() { if (on) Prof::end(st); }
+};
+
+// ---------------------------------------------------------------- activations
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_ELU = 2, ACT_LRELU02 = 3, ACT_TANH = 4, ACT_SIGMOID = 5 };
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+  switch (act) {
+    case ACT_RELU: return fmaxf(v, 0.f);
+    case ACT_ELU: return v > 0.f ? v : expm1f(v);
+    case ACT_LRELU02: return v > 0.f ? v : 0.2f * v;
+    case ACT_TANH: return tanhf(v);
+    case ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+    default: return v;
+  }
+}
+
+// Activation-operand storage modes (what a producing kernel writes for the next contraction)
+enum OutMode : int {
+  OUT_F32_NHWC = 0,     // fp32 [pixels][cstride]
+  OUT_F32_NCHW = 1,     // fp32 [frame][C][Ho][Wo]   (frames at the ABI edge)
+  OUT_BF16_SPLIT = 2,   // two bf16 planes (hi, lo) [pixels][cstride]; lo plane at +plane_stride elements
+  OUT_BF16 = 3          // one bf16 plane
+};
+
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+inline int64_t round_up64(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------- device arena (bump allocator)
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, off = 0;
+  void init(size_t bytes) {
+    release();
+    IPK_CUDA(cudaMalloc((void**)&base, bytes));
+    cap = bytes;
+    off = 0;
+  }
+  void release() {
+    if (base) cudaFree(base);
+    base = nullptr;
+    cap = off = 0;
+  }
+  template <typename T>
+  T* alloc(size_t n) {
+    size_t bytes = (n * sizeof(T) + 255) / 256 * 256;
+    IPK_CHECK(off + bytes <= cap, IPK_ERR_INVALID, "arena overflow: need %zu more bytes (cap %zu)", bytes, cap);
+    T* p = (T*)(base + off);
+    off += bytes;
+    return p;
+  }
+};
+
+// owned device allocations (packed weights): chunked bump allocator, 256-byte aligned
+struct DevPool {
+  std::vector<void*> chunks;
+  char* cur = nullptr;
+  size_t cur_cap = 0, cur_off = 0;
+  size_t total = 0;
+  static constexpr size_t kChunk = 256ull << 20;
+  template <typename T>
+  T* alloc(size_t n, bool zero = false) {
+    size_t bytes = (std::max<size_t>(n * sizeof(T), 16) + 255) / 256 * 256;
+    char* p;
+    if (bytes > kChunk / 4) {
+      void* q = nullptr;
+      IPK_CUDA(cudaMalloc(&q, bytes));
+      chunks.push_back(q);
+      p = (char*)q;
+    } else {
+      if (cur == nullptr || cur_off + bytes > cur_cap) {
+        void* q = nullptr;
+        IPK_CUDA(cudaMalloc(&q, kChunk));
+        chunks.push_back(q);
+        cur = (char*)q;
+        cur_cap = kChunk;
+        cur_off = 0;
+      }
+      p = cur + cur_off;
+      cur_off += bytes;
+    }
+    total += bytes;
+    if (zero) {
+      IPK_CUDA(cudaMemset(p, 0, bytes));
+      IPK_CUDA(cudaDeviceSynchronize());   // plan-build time only: order the memset before packing kernels on any stream
+    }
+    return (T*)p;
+  }
+  void release() {
+    for (void* p : chunks) cudaFree(p);
+    chunks.clear();
+    cur = nullptr;
+    cur_cap = cur_off = total = 0;
+  }
+};
+
+#define IPK_TRY try {
+#define IPK_CATCH                                                                                \
+  }                                                                                              \
+  catch (const ::ipk::Error& e) { ::ipk::set_last_error(e.what()); return e.code; }              \
+  catch (const std::exception& e) { ::ipk::set_last_error(e.what()); return IPK_ERR_INVALID; }   \
+  return IPK_OK;
+
+}  // namespace ipk

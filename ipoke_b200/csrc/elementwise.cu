@@ -1,0 +1,362 @@
+// Elementwise / reduction kernels: layout conversion at the ABI edge, Instance/GroupNorm statistics, the fused
+// normalise + affine + activation + residual + SPADE pass, ConvGRU gate math, bilinear resize, parameter folding.
+#include "elementwise.cuh"
+
+namespace ipk {
+
+static inline int grid_for(long long n, int threads = 256, int max_blocks = 148 * 32) {
+  long long b = (n + threads - 1) / threads;
+  return (int)std::max<long long>(1, std::min<long long>(b, max_blocks));
+}
+
+// ------------------------------------------------------------------ layout
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int C, int P, int cs) {
+  long long total = (long long)B * C * P;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(e % C);
+    long long bp = e / C;
+    int p = (int)(bp % P);
+    int b = (int)(bp / P);
+    out[((size_t)b * P + p) * cs + c] = in[((size_t)b * C + c) * P + p];
+  }
+}
+void nchw_to_nhwc(const float* in, float* out, int B, int C, int P, int cstride, cudaStream_t st) {
+  nchw_to_nhwc_kernel<<<grid_for((long long)B * C * P), 256, 0, st>>>(in, out, B, C, P, cstride);
+  IPK_LAUNCH_CHECK();
+}
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int C, int P, int cs) {
+  long long total = (long long)B * C * P;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    int p = (int)(e % P);
+    long long bc = e / P;
+    int c = (int)(bc % C);
+    int b = (int)(bc / C);
+    out[e] = in[((size_t)b * P + p) * cs + c];
+  }
+}
+void nhwc_to_nchw(const float* in, float* out, int B, int C, int P, int cstride, cudaStream_t st) {
+  nhwc_to_nchw_kernel<<<grid_for((long long)B * C * P), 256, 0, st>>>(in, out, B, C, P, cstride);
+  IPK_LAUNCH_CHECK();
+}
+__global__ void broadcast_chw_kernel(const float* __restrict__ src, float* __restrict__ out, int B, int C, int P, int cs, int coff) {
+  long long total = (long long)B * C * P;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(e % C);
+    long long bp = e / C;
+    int p = (int)(bp % P);
+    out[(size_t)bp * cs + coff + c] = src[(size_t)c * P + p];
+  }
+}
+void broadcast_chw_to_nhwc(const float* src, float* out, int B, int C, int P, int cstride, int coff, cudaStream_t st) {
+  broadcast_chw_kernel<<<grid_for((long long)B * C * P), 256, 0, st>>>(src, out, B, C, P, cstride, coff);
+  IPK_LAUNCH_CHECK();
+}
+__global__ void copy_channels_kernel(const float* __restrict__ src, int scs, int scoff, float* __restrict__ dst, int dcs, int dcoff,
+                                     long long M, int C) {
+  long long total = M * C;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(e % C);
+    long long m = e / C;
+    dst[m * dcs + dcoff + c] = src[m * scs + scoff + c];
+  }
+}
+void copy_channels(const float* src, int scs, int scoff, float* dst, int dcs, int dcoff, long long M, int C, cudaStream_t st) {
+  copy_channels_kernel<<<grid_for(M * C), 256, 0, st>>>(src, scs, scoff, dst, dcs, dcoff, M, C);
+  IPK_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------ norm statistics
+// grid (chunks, F); each block reduces `ppb` pixels of one frame for all channels.
+__global__ void __launch_bounds__(256) channel_stats_kernel(const float* __restrict__ x, long long P, int C, int ppb, double* __restrict__ sums) {
+  const int f = blockIdx.y;
+  const long long p0 = (long long)blockIdx.x * ppb;
+  const long long p1 = min(P, p0 + ppb);
+  const float* xf = x + (size_t)f * P * C;
+  const int lanes = C < 256 ? 256 / C : 1;          // pixel lanes when C < 256
+  const int lane = C < 256 ? threadIdx.x / C : 0;
+  if (lane >= lanes) return;
+  const int cstep = C < 256 ? C : 256;
+  for (int c = threadIdx.x % C; c < C; c += cstep) {
+    float s = 0.f, q = 0.f;
+    for (long long p = p0 + lane; p < p1; p += lanes) {
+      float v = xf[p * C + c];
+      s += v;
+      q = fmaf(v, v, q);
+    }
+    atomicAdd(&sums[((size_t)f * C + c) * 2 + 0], (double)s);
+    atomicAdd(&sums[((size_t)f * C + c) * 2 + 1], (double)q);
+  }
+}
+void channel_stats(const float* x, int F, long long P, int C, double* sums, cudaStream_t st) {
+  int lanes = std::max(1, 256 / C);
+  int ppb = 128 * lanes;                              // <= 128 fp32 accumulations per thread
+  dim3 g((unsigned)((P + ppb - 1) / ppb), F);
+  channel_stats_kernel<<<g, 256, 0, st>>>(x, P, C, ppb, sums);
+  IPK_LAUNCH_CHECK();
+}
+__global__ void finalize_stats_kernel(const double* __restrict__ sums, float* __restrict__ mr, int F, long long P, int C, int groups, float eps) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= F * C) return;
+  int f = i / C, c = i % C;
+  double s = 0, q = 0, n;
+  if (groups == 0) {
+    s = sums[(size_t)i * 2];
+    q = sums[(size_t)i * 2 + 1];
+    n = (double)P;
+  } else {
+    int cpg = C / groups;
+    int g0 = (c / cpg) * cpg;
+    for (int k = 0; k < cpg; ++k) {
+      s += sums[((size_t)f * C + g0 + k) * 2];
+      q += sums[((size_t)f * C + g0 + k) * 2 + 1];
+    }
+    n = (double)P * cpg;
+  }
+  double mean = s / n;
+  double var = q / n - mean * mean;
+  if (var < 0) var = 0;
+  mr[(size_t)i * 2] = (float)mean;
+  mr[(size_t)i * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+void finalize_stats(const double* sums, float* mr, int F, long long P, int C, int groups, float eps, cudaStream_t st) {
+  finalize_stats_kernel<<<cdiv(F * C, 256), 256, 0, st>>>(sums, mr, F, P, C, groups, eps);
+  IPK_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------ fused normalise/affine/act/residual/SPADE
+struct NormApplyK {
+  const float* x; int F, C; long long P;
+  const float* mr; const float* w; const float* b; int act; const float* add; const float* spade; int T;
+  float* out_f32; __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
+};
+__global__ void __launch_bounds__(256) norm_apply_kernel(const NormApplyK a) {
+  const int C4 = a.C / 4;
+  const long long total = (long long)a.F * a.P * C4;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    int c4 = (int)(e % C4);
+    long long fp = e / C4;
+    int f = (int)(fp / a.P);
+    long long p = fp % a.P;
+    float4 v4 = ((const float4*)a.x)[e];
+    float v[4] = {v4.x, v4.y, v4.z, v4.w};
+    float ad[4] = {0.f, 0.f, 0.f, 0.f};
+    if (a.add) {
+      float4 t = ((const float4*)a.add)[e];
+      ad[0] = t.x; ad[1] = t.y; ad[2] = t.z; ad[3] = t.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int c = c4 * 4 + i;
+      float t = v[i];
+      if (a.mr) {
+        float mean = a.mr[((size_t)f * a.C + c) * 2], rstd = a.mr[((size_t)f * a.C + c) * 2 + 1];
+        t = (t - mean) * rstd;
+      }
+      if (a.w) t = t * a.w[c] + a.b[c];
+      t = act_apply(t, a.act);
+      t += ad[i];
+      if (a.spade) {
+        size_t sp = ((size_t)(f / a.T) * a.P + p) * (2 * a.C);
+        t = t * a.spade[sp + c] + a.spade[sp + a.C + c];
+      }
+      v[i] = t;
+    }
+    if (a.out_f32) ((float4*)a.out_f32)[e] = make_float4(v[0], v[1], v[2], v[3]);
+    if (a.out_hi) {
+      __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) split_bf16(v[i], hi[i], lo[i]);
+      __nv_bfloat162* oh = (__nv_bfloat162*)(a.out_hi + e * 4);
+      oh[0] = __nv_bfloat162(hi[0], hi[1]);
+      oh[1] = __nv_bfloat162(hi[2], hi[3]);
+      if (a.out_lo) {
+        __nv_bfloat162* ol = (__nv_bfloat162*)(a.out_lo + e * 4);
+        ol[0] = __nv_bfloat162(lo[0], lo[1]);
+        ol[1] = __nv_bfloat162(lo[2], lo[3]);
+      }
+    }
+  }
+}
+void norm_apply(const NormApply& n, cudaStream_t st) {
+  IPK_CHECK(n.C % 4 == 0, IPK_ERR_UNSUPPORTED, "norm_apply: C must be a multiple of 4");
+  NormApplyK a{n.x, n.F, n.C, n.P, n.mr, n.w, n.b, n.act, n.add, n.spade, n.T, n.out_f32, n.out_hi, n.out_lo};
+  long long total = (long long)n.F * n.P * (n.C / 4);
+  if (total == 0) return;
+  norm_apply_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, st>>>(a);
+  IPK_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------ ConvGRU gates
+__global__ void gru_gate1_kernel(const float* __restrict__ raw, const float* __restrict__ xh, float* __restrict__ U,
+                                 float* __restrict__ xrh, long long M, int z) {
+  long long total = M * z;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(e % z);
+    long long m = e / z;
+    float u = 1.f / (1.f + expf(-raw[m * 2 * z + c]));
+    float r = 1.f / (1.f + expf(-raw[m * 2 * z + z + c]));
+    float h = xh[m * 2 * z + z + c];
+    U[e] = u;
+    xrh[m * 2 * z + z + c] = h * r;
+  }
+}
+void gru_gate1(const float* raw, const float* xh, float* U, float* xrh, long long M, int z, cudaStream_t st) {
+  gru_gate1_kernel<<<grid_for(M * z), 256, 0, st>>>(raw, xh, U, xrh, M, z);
+  IPK_LAUNCH_CHECK();
+}
+struct GruDst4 { GruDst d[4]; int n; };
+__global__ void gru_gate2_kernel(const float* __restrict__ raw, const float* __restrict__ U, const float* __restrict__ xh,
+                                 long long M, int z, GruDst4 dst, float* __restrict__ seq_out, int T, int t) {
+  long long total = M * z;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(e % z);
+    long long m = e / z;
+    float o = tanhf(raw[e]);
+    float u = U[e];
+    float h = xh[m * 2 * z + z + c];
+    float hn = h * (1.f - u) + o * u;
+    for (int i = 0; i < dst.n; ++i) dst.d[i].p[m * dst.d[i].cstride + dst.d[i].coff + c] = hn;
+    if (seq_out) {
+      long long b = m / 64, p = m % 64;      // 8x8 latent grid
+      seq_out[((b * T + t) * 64 + p) * z + c] = hn;
+    }
+  }
+}
+void gru_gate2(const float* raw, const float* U, const float* xh, long long M, int z, const GruDst* dst, int ndst,
+               float* seq_out, int T, int t, cudaStream_t st) {
+  GruDst4 d;
+  d.n = ndst;
+  for (int i = 0; i < ndst && i < 4; ++i) d.d[i] = dst[i];
+  gru_gate2_kernel<<<grid_for(M * z), 256, 0, st>>>(raw, U, xh, M, z, d, seq_out, T, t);
+  IPK_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------ bilinear resize (align_corners=True)
+__global__ void bilinear_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int C, int S, int s) {
+  long long total = (long long)B * s * s * C;
+  const float scale = s > 1 ? (float)(S - 1) / (float)(s - 1) : 0.f;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(e % C);
+    long long r = e / C;
+    int ox = (int)(r % s);
+    r /= s;
+    int oy = (int)(r % s);
+    int b = (int)(r / s);
+    float fy = scale * oy, fx = scale * ox;
+    int y0 = (int)fy, x0 = (int)fx;
+    int y1 = y0 + (y0 < S - 1 ? 1 : 0), x1 = x0 + (x0 < S - 1 ? 1 : 0);
+    float ly = fy - y0, lx = fx - x0;
+    const float* ip = in + ((size_t)b * C + c) * S * S;
+    float v = (1.f - ly) * ((1.f - lx) * ip[y0 * S + x0] + lx * ip[y0 * S + x1]) + ly * ((1.f - lx) * ip[y1 * S + x0] + lx * ip[y1 * S + x1]);
+    out[e] = v;
+  }
+}
+void bilinear_nchw_to_nhwc(const float* in, float* out, int B, int C, int S, int s, cudaStream_t st) {
+  bilinear_kernel<<<grid_for((long long)B * s * s * C), 256, 0, st>>>(in, out, B, C, S, s);
+  IPK_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------ parameter folding
+__global__ void weight_norm_scale_kernel(const float* __restrict__ v, const float* __restrict__ g, float* __restrict__ os, int N, int row) {
+  int n = blockIdx.x;
+  __shared__ double red[32];
+  double s = 0;
+  for (int i = threadIdx.x; i < row; i += blockDim.x) {
+    double t = v[(size_t)n * row + i];
+    s += t * t;
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int i = 0; i < (blockDim.x + 31) / 32; ++i) t += red[i];
+    os[n] = (float)((double)g[n] / sqrt(t));
+  }
+}
+void weight_norm_scale(const float* v, const float* g, float* oscale, int N, int row, cudaStream_t st) {
+  weight_norm_scale_kernel<<<N, 256, 0, st>>>(v, g, oscale, N, row);
+  IPK_LAUNCH_CHECK();
+}
+
+// sigma = sum_r u[r] * sum_c Wm[r][c] v[c].  dim0: Wm[r][c] = w[r*cols + c].  dim1 (ConvTranspose): w is [d0][d1][rest],
+// rows = d1, cols = d0*rest, Wm[r][(i0, j)] = w[(i0*d1 + r)*rest + j].
+__global__ void spectral_sigma_kernel(const float* __restrict__ w, const float* __restrict__ u, const float* __restrict__ v,
+                                      float* __restrict__ sigma, int d0, int d1, int rest, int dim1) {
+  __shared__ double red[32];
+  long long total = (long long)d0 * d1 * rest;
+  double s = 0;
+  for (long long e = threadIdx.x; e < total; e += blockDim.x) {
+    int j = (int)(e % rest);
+    int i1 = (int)((e / rest) % d1);
+    int i0 = (int)(e / ((long long)rest * d1));
+    int r, c;
+    if (dim1) { r = i1; c = i0 * rest + j; } else { r = i0; c = i1 * rest + j; }
+    s += (double)u[r] * (double)w[e] * (double)v[c];
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int i = 0; i < (blockDim.x + 31) / 32; ++i) t += red[i];
+    sigma[0] = (float)t;
+  }
+}
+void spectral_sigma(const float* w, const float* u, const float* v, float* sigma, int d0, int d1, int rest, bool dim1, cudaStream_t st) {
+  spectral_sigma_kernel<<<1, 1024, 0, st>>>(w, u, v, sigma, d0, d1, rest, dim1 ? 1 : 0);
+  IPK_LAUNCH_CHECK();
+}
+
+// MCF shifted-conv weights w[hid][C][kh][kw] -> canonical line layout dst[t = du_idx*3 + dv_idx][Cp/4][hid][4]
+// (du in {-2,-1} along the sequential axis, dv in {-1,0,1} along the line); see flow_segment.cu.
+__global__ void pack_mcf_shift_kernel(const float* __restrict__ w, float* __restrict__ dst, int hid, int C, int Cp, int kh, int kw, int order) {
+  int total = 6 * Cp * hid;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    int ci = e % 4;
+    int n = (e / 4) % hid;
+    int c4 = (e / (4 * hid)) % (Cp / 4);
+    int t = e / (4 * hid * (Cp / 4));
+    int c = c4 * 4 + ci;
+    int du_idx = t / 3, dv_idx = t % 3;
+    int ky, kx;
+    switch (order) {
+      case 0: ky = du_idx; kx = dv_idx; break;          // A (2x3)
+      case 1: ky = 1 - du_idx; kx = dv_idx; break;      // B (2x3)
+      case 2: kx = du_idx; ky = dv_idx; break;          // C (3x2)
+      default: kx = 1 - du_idx; ky = dv_idx; break;     // D (3x2)
+    }
+    float v = 0.f;
+    if (c < C) v = w[(((size_t)n * C + c) * kh + ky) * kw + kx];
+    dst[e] = v;
+  }
+}
+void pack_mcf_shift(const float* w, float* dst, int hid, int C, int Cp, int kh, int kw, int order, cudaStream_t st) {
+  pack_mcf_shift_kernel<<<grid_for(6LL * Cp * hid), 256, 0, st>>>(w, dst, hid, C, Cp, kh, kw, order);
+  IPK_LAUNCH_CHECK();
+}
+__global__ void pack_rows4_kernel(const float* __restrict__ w, const float* __restrict__ os, float* __restrict__ dst, int O, int row, int k_off, int K) {
+  int total = K * O;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    int ki = e % 4;
+    int o = (e / 4) % O;
+    int k4 = e / (4 * O);
+    int k = k4 * 4 + ki;
+    dst[e] = w[(size_t)o * row + k_off + k] * (os ? os[o] : 1.f);
+  }
+}
+void pack_rows4(const float* w, const float* oscale, float* dst, int O, int row, int k_off, int K, cudaStream_t st) {
+  IPK_CHECK(K % 4 == 0, IPK_ERR_UNSUPPORTED, "pack_rows4: K must be a multiple of 4 (got %d)", K);
+  pack_rows4_kernel<<<grid_for((long long)K * O), 256, 0, st>>>(w, oscale, dst, O, row, k_off, K);
+  IPK_LAUNCH_CHECK();
+}
+__global__ void i64_to_i32_kernel(const long long* __restrict__ s, int* __restrict__ d, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) d[i] = (int)s[i];
+}
+void i64_to_i32(const long long* src, int* dst, int n, cudaStream_t st) {
+  i64_to_i32_kernel<<<cdiv(n, 128), 128, 0, st>>>(src, dst, n);
+  IPK_LAUNCH_CHECK();
+}
+
+}  // namespace ipk
