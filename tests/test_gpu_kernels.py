@@ -7,7 +7,7 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
-PRECS = [(0, "simt", 2e-6), (1, "split", 2e-5), (2, "bf16", 1.5e-2)]
+PRECS = [(0, "simt", 1e-5), (1, "split", 1e-4), (2, "bf16", 1.5e-2)]  # relative to max|ref|; K up to 18432
 
 
 def _lib():
