@@ -85,6 +85,10 @@ const char* ipk_last_error(void);
 /* number of kernels this library has launched on the calling thread since the last reset */
 int64_t ipk_launch_count(void);
 void ipk_launch_count_reset(void);
+/* optional per-phase device timing: when enabled every phase of a plan run is bracketed by CUDA events on the launch
+ * stream; ipk_prof_report synchronises the device and writes "tag count total_ms\n" lines into buf (returns bytes needed) */
+void ipk_prof_enable(int on);
+int ipk_prof_report(char* buf, int cap);
 
 /* ---- conditional MaCow flow ---- */
 int ipk_flow_create(const ipk_flow_config* cfg, ipk_flow** out);

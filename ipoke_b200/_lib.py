@@ -29,7 +29,7 @@ class FsConfig(ctypes.Structure):
 
 
 EXPORTS = [
-    "ipk_version", "ipk_last_error", "ipk_launch_count", "ipk_launch_count_reset",
+    "ipk_version", "ipk_last_error", "ipk_launch_count", "ipk_launch_count_reset", "ipk_prof_enable", "ipk_prof_report",
     "ipk_flow_create", "ipk_flow_set_tensor", "ipk_flow_finalize", "ipk_flow_reverse", "ipk_flow_forward", "ipk_flow_destroy",
     "ipk_fs_create", "ipk_fs_set_tensor", "ipk_fs_finalize", "ipk_fs_decode", "ipk_fs_gru_step", "ipk_fs_gen", "ipk_fs_destroy",
     "ipk_sample", "ipk_sample_host", "ipk_test_gemm", "ipk_test_conv3x3", "ipk_test_convT3x3",
@@ -51,6 +51,10 @@ def lib():
     L.ipk_last_error.restype = cp
     L.ipk_launch_count.restype = i64
     L.ipk_launch_count_reset.restype = None
+    L.ipk_prof_enable.argtypes = [ctypes.c_int]
+    L.ipk_prof_enable.restype = None
+    L.ipk_prof_report.argtypes = [ctypes.c_char_p, ctypes.c_int]
+    L.ipk_prof_report.restype = ctypes.c_int
     L.ipk_flow_create.argtypes = [ctypes.POINTER(FlowConfig), ctypes.POINTER(vp)]
     L.ipk_flow_set_tensor.argtypes = [vp, cp, vp, i64, ctypes.c_int]
     L.ipk_flow_finalize.argtypes = [vp, vp]
@@ -112,3 +116,20 @@ def launch_count():
 
 def launch_count_reset():
     lib().ipk_launch_count_reset()
+
+
+def prof_enable(on=True):
+    lib().ipk_prof_enable(1 if on else 0)
+
+
+def prof_report():
+    """{tag: (count, total_ms)} of the phases recorded since prof_enable(True); synchronises the device."""
+    L = lib()
+    n = L.ipk_prof_report(None, 0)
+    buf = ctypes.create_string_buffer(n + 16)
+    L.ipk_prof_report(buf, n + 16)
+    out = {}
+    for line in buf.value.decode().splitlines():
+        tag, cnt, ms = line.split()
+        out[tag] = (int(cnt), float(ms))
+    return out

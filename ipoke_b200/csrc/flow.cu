@@ -378,8 +378,10 @@ static void run_nice_net(ipk_flow* f, const NiceLayer& n, int B, cudaStream_t st
 static void run_program(ipk_flow* f, std::vector<Stage>& stages, bool fwd, int B, cudaStream_t st) {
   for (Stage& s : stages) {
     SegmentLaunch sl{s.d_ops, (int)s.host_ops.size(), s.C, s.has_mcf};
-    ProfScope ps(s.has_mcf ? "flow.segment.mcf" : "flow.segment.light", st);
-    flow_segment_run(sl, fwd, f->state, f->C0, f->cond, f->hch, f->logdet_ws, B, st);
+    {
+      ProfScope ps(s.has_mcf ? "flow.segment.mcf" : "flow.segment.light", st);
+      flow_segment_run(sl, fwd, f->state, f->C0, f->cond, f->hch, f->logdet_ws, B, st);
+    }
     if (s.nice_id >= 0) run_nice_net(f, f->nices[s.nice_id], B, st);
   }
 }
