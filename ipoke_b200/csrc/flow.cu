@@ -46,7 +46,7 @@ struct Stage {          // one segment launch followed (optionally) by one NICE 
   int nice_id = -1;     // NICE whose network runs after this segment (the segment ends with its IM2COL)
 };
 
-struct McfPacked { float* Wc; float* W1x; float* W1h; float* bias; int C, Cp, hid; };
+struct McfPacked { float* Wc; float* W1x; int C, Cp, hid; int hcol; const float* v_src; const float* os; const float* b_src; };
 
 }  // namespace ipk
 
@@ -72,6 +72,11 @@ struct ipk_flow {
   void* H2 = nullptr; void* H2_lo = nullptr;
   float* partials = nullptr;
   float* logdet_ws = nullptr;
+  // conditioning terms of all MCFs: Hterm[M][hstride] = bias + W1h * ELU(cond), one GEMM per flow pass
+  ConvW hterm_w;
+  int hterm_cols = 0, hstride = 0;
+  void* E = nullptr; void* E_lo = nullptr;   // ELU(cond) operand [M][hch]
+  float* Hterm = nullptr;
   int K1pad_max = 0, Npad3_max = 0;
   int act_mode = OUT_F32_NHWC;
 };
@@ -197,10 +202,10 @@ static const McfPacked& build_mcf(ipk_flow* f, const std::string& p, int C, int 
   weight_norm_scale((const float*)v.p, (const float*)g.p, os, C2, row, st);
   m.W1x = f->pool.alloc<float>((size_t)m.hid * C2);
   pack_rows4((const float*)v.p, os, m.W1x, C2, row, 0, m.hid, st);
-  m.W1h = f->pool.alloc<float>((size_t)hch * C2);
-  pack_rows4((const float*)v.p, os, m.W1h, C2, row, m.hid, hch, st);
-  m.bias = f->pool.alloc<float>(C2);
-  IPK_CUDA(cudaMemcpyAsync(m.bias, b.p, C2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  // the x-independent part of the 1x1 (columns hid.. of weight_v, macow_utils.py:429-432) goes into the shared Hterm GEMM
+  m.hcol = f->hterm_cols;
+  f->hterm_cols += round_up(C2, 4);
+  m.v_src = (const float*)v.p; m.os = os; m.b_src = (const float*)b.p;
   f->mcfs[p] = m;
   return f->mcfs[p];
 }
@@ -302,7 +307,7 @@ static std::vector<Stage> compile_program(ipk_flow* f, const std::vector<Logical
       case L_MCF: {
         const McfPacked& p = build_mcf(f, o.prefix, o.C, o.order, st);
         m.kind = MK_MCF; m.i0 = o.order; m.i1 = p.C; m.i2 = p.Cp; m.i3 = p.hid;
-        m.p0 = p.Wc; m.p1 = p.W1x; m.p2 = p.W1h; m.p3 = p.bias;
+        m.p0 = p.Wc; m.p1 = p.W1x; m.l0 = p.hcol;   // p2 / l0 patched after the Hterm buffer exists
         cur.host_ops.push_back(m);
         cur.has_mcf = true;
         break;
@@ -341,6 +346,7 @@ static void upload_programs(ipk_flow* f, std::vector<Stage>& stages, cudaStream_
     for (MicroOp& m : s.host_ops) {
       if (m.kind == MK_IM2COL) { m.out0 = f->A1; m.out1 = f->A1_lo; }
       if (m.kind == MK_AFFINE) { m.p0 = f->partials; m.l0 = Mmax * m.i1; }
+      if (m.kind == MK_MCF) { m.p2 = f->Hterm + m.l0; m.l0 = f->hstride; }
     }
     s.d_ops = f->pool.alloc<MicroOp>(s.host_ops.size());
     IPK_CUDA(cudaMemcpyAsync(s.d_ops, s.host_ops.data(), s.host_ops.size() * sizeof(MicroOp), cudaMemcpyHostToDevice, st));
@@ -375,12 +381,28 @@ static void run_nice_net(ipk_flow* f, const NiceLayer& n, int B, cudaStream_t st
   }
 }
 
+// Hterm[B*64][hstride] = bias + W1h_all * ELU(cond): the conditioning input of every MCF's 1x1 (MCFBlock.forward,
+// macow_utils.py:429-432: cat -> ELU -> 1x1 splits into a state part and this state-independent part)
+static void run_hterm(ipk_flow* f, int B, cudaStream_t st) {
+  if (f->hterm_cols == 0) return;
+  ProfScope ps("flow.hterm_gemm", st);
+  const long long M = (long long)B * 64;
+  NormApply e; e.x = f->cond; e.F = 1; e.P = M; e.C = f->hch; e.act = ACT_ELU;
+  if (f->hterm_w.engine == IPK_PREC_FP32_SIMT) e.out_f32 = (float*)f->E;
+  else { e.out_hi = (__nv_bfloat16*)f->E; e.out_lo = (__nv_bfloat16*)f->E_lo; }
+  norm_apply(e, st);
+  ConvIn in; in.p = f->E; in.p_lo = f->E_lo; in.cstride = f->hch; in.F = (int)M; in.H = 1; in.W = 1;
+  ConvOut out; out.p = f->Hterm; out.mode = OUT_F32_NHWC; out.cstride = f->hstride; out.Ho = 1; out.Wo = 1; out.bias = f->hterm_w.bias;
+  conv_run(f->hterm_w, in, out, taps_1x1(), 1, st);
+}
+
 static void run_program(ipk_flow* f, std::vector<Stage>& stages, bool fwd, int B, cudaStream_t st) {
+  run_hterm(f, B, st);
   for (Stage& s : stages) {
     SegmentLaunch sl{s.d_ops, (int)s.host_ops.size(), s.C, s.has_mcf};
     {
       ProfScope ps(s.has_mcf ? "flow.segment.mcf" : "flow.segment.light", st);
-      flow_segment_run(sl, fwd, f->state, f->C0, f->cond, f->hch, f->logdet_ws, B, st);
+      flow_segment_run(sl, fwd, f->state, f->C0, f->logdet_ws, B, st);
     }
     if (s.nice_id >= 0) run_nice_net(f, f->nices[s.nice_id], B, st);
   }
@@ -399,6 +421,8 @@ extern "C" int ipk_flow_create(const ipk_flow_config* cfg, ipk_flow** out) {
   IPK_CHECK(cfg->h_channels % 4 == 0 && cfg->h_channels > 0, IPK_ERR_UNSUPPORTED, "flow: h_channels must be a positive multiple of 4");
   IPK_CHECK(cfg->precision >= 0 && cfg->precision <= 2, IPK_ERR_INVALID, "flow: bad precision");
   IPK_CHECK(cfg->max_batch > 0, IPK_ERR_INVALID, "flow: max_batch must be positive");
+  if (cfg->precision != IPK_PREC_FP32_SIMT)
+    IPK_CHECK(cfg->h_channels % 8 == 0, IPK_ERR_UNSUPPORTED, "flow: tensor-core engine needs h_channels %% 8 == 0");
   if (cfg->precision != IPK_PREC_FP32_SIMT)
     IPK_CHECK(cfg->flow_mid_channels % 64 == 0, IPK_ERR_UNSUPPORTED, "flow: tensor-core engine needs flow_mid_channels %% 64 == 0");
   levels_of(*cfg);
@@ -428,13 +452,26 @@ extern "C" int ipk_flow_finalize(ipk_flow* f, void* stream) {
   auto pi = logical_program(f, false);
   f->prog_fwd = compile_program(f, pf, st);
   f->prog_inv = compile_program(f, pi, st);
+  // one GEMM for the conditioning terms of all MCFs (always error-compensated on the tensor-core engines: K = h_channels only)
+  {
+    const int heng = f->cfg.precision == IPK_PREC_FP32_SIMT ? IPK_PREC_FP32_SIMT : IPK_PREC_FP32_SPLIT;
+    f->hterm_w = conv_alloc(f->pool, heng, 1, f->hch, std::max(f->hterm_cols, 4), true);
+    for (auto& kv : f->mcfs) {
+      const McfPacked& m = kv.second;
+      PackSrc s;
+      s.w = m.v_src; s.N = 2 * m.C; s.Ksrc = m.hid + f->hch; s.k_off = m.hid; s.oscale = m.os;
+      conv_pack_into(f->hterm_w, m.hcol, s, {0}, st);
+      conv_pack_bias(f->hterm_w, m.hcol, m.b_src, 2 * m.C, 0.f, st);
+    }
+    f->hstride = f->hterm_w.Npad;
+  }
   // workspace
   const size_t Mmax = (size_t)f->cfg.max_batch * 64;
   const size_t esz = 4;  // fp32, or two bf16 planes
   size_t bytes = 0;
   auto rb = [](size_t b) { return (b + 255) / 256 * 256; };
   bytes += rb(Mmax * f->C0 * 4) + rb(Mmax * f->hch * 4) + rb(Mmax * f->K1pad_max * esz) + 2 * rb(Mmax * f->Hd * esz) +
-           rb(9 * Mmax * f->Npad3_max * 4) + rb(f->cfg.max_batch * 4) + 4096;
+           rb(9 * Mmax * f->Npad3_max * 4) + rb(f->cfg.max_batch * 4) + rb(Mmax * f->hch * 4) + rb(Mmax * (size_t)f->hstride * 4) + 4096;
   f->ws.init(bytes);
   f->state = f->ws.alloc<float>(Mmax * f->C0);
   f->cond = f->ws.alloc<float>(Mmax * f->hch);
@@ -449,6 +486,12 @@ extern "C" int ipk_flow_finalize(ipk_flow* f, void* stream) {
   }
   f->partials = f->ws.alloc<float>(9 * Mmax * f->Npad3_max);
   f->logdet_ws = f->ws.alloc<float>(f->cfg.max_batch);
+  {
+    char* e = (char*)f->ws.alloc<float>(Mmax * f->hch);
+    f->E = e;
+    f->E_lo = f->hterm_w.engine == IPK_PREC_FP32_SPLIT ? e + Mmax * f->hch * 2 : nullptr;
+    f->Hterm = f->ws.alloc<float>(Mmax * (size_t)f->hstride);
+  }
   upload_programs(f, f->prog_fwd, st);
   upload_programs(f, f->prog_inv, st);
   IPK_CUDA(cudaStreamSynchronize(st));

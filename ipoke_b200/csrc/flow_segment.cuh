@@ -25,7 +25,9 @@ struct MicroOp {
    MK_ACTNORM : i0 = channel offset, i1 = channel count, p0 = log_scale, p1 = bias
    MK_SHUFFLE : i0 = C, idx = gather index (new[c] = old[idx[c]])
    MK_MCF     : i0 = order (0 A,1 B,2 C,3 D), i1 = C, i2 = Cp (C rounded up to 4), i3 = hid,
-                p0 = Wc [6][Cp/4][hid][4], p1 = W1x [hid/4][2C][4], p2 = W1h [h_ch/4][2C][4], p3 = bias [2C]
+                p0 = Wc [6][Cp/4][hid][4], p1 = W1x [hid/4][2C][4],
+                p2 = conditioning term of this MCF: column block of the precomputed matrix
+                     Hterm[M = B*64][l0] = b + W1h * ELU(cond)  (round_up(2C, 4) columns, 16-byte aligned), l0 = row stride
    MK_AFFINE  : i0 = nsplit, i1 = Npad (row length of params), i2 = n_p, p0 = params partials [nsplit][M][Npad],
                 p1 = bias [2*n_p], idx = state channel of each transformed element, l0 = split stride (elements)
    MK_IM2COL  : i0 = n_z, i1 = K1pad, i2 = out mode (OUT_F32_NHWC / OUT_BF16_SPLIT / OUT_BF16), idx = state channels of z,
@@ -39,9 +41,10 @@ struct SegmentLaunch {
   bool has_mcf;
 };
 
-// state: [B][64][C0] fp32 NHWC (in place); cond: [B][64][h_ch]; logdet: [B] (forward only, accumulated)
-void flow_segment_run(const SegmentLaunch& s, bool forward, float* state, int C0, const float* cond, int h_ch,
-                      float* logdet, int B, cudaStream_t st);
+constexpr int MAX_NSPLIT = 9;   // split-K slices of a NICE conv3 (one per tap)
+
+// state: [B][64][C0] fp32 NHWC (in place); logdet: [B] (forward only, accumulated)
+void flow_segment_run(const SegmentLaunch& s, bool forward, float* state, int C0, float* logdet, int B, cudaStream_t st);
 size_t flow_segment_smem_bytes(int C, int h_ch, bool has_mcf);
 void flow_segment_init();
 
