@@ -21,16 +21,18 @@ namespace ipk {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr size_t TC_SMEM_BUDGET = 200 * 1024;
 
 struct TcArgs {
   int F, H, W;
   int bw, bh, bf;                 // pixel box (bw*bh*bf == 128)
-  int tiles_x, tiles_y;           // tiles along x and y (tiles along f = gridDim.x / (tiles_x*tiles_y))
+  int tiles_x, tiles_y;           // tiles along x and y
+  int tiles_m, tiles_n, nsplit;   // tiles_m = tiles_x * tiles_y * tiles_f
   int ntaps, taps_per_split, nkb; // nkb = Kpad / 64
   int dy[MAX_TAPS], dx[MAX_TAPS], widx[MAX_TAPS];
-  int Npad;
+  int Npad, N;
   int stages;
   // epilogue
   const float* bias;
@@ -123,6 +125,43 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------ kernel
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// activation applied to a register tile; the branch is warp-uniform.  ELU uses ex2.approx (abs error ~1e-7, far inside
+// the engine's own operand rounding); the fp32 SIMT validation engine keeps expm1f.
+template <int NV>
+__device__ __forceinline__ void act_tile(float (&v)[NV], int act) {
+  if (act == ACT_ELU) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] = v[j] > 0.f ? v[j] : (exp2f(v[j] * 1.4426950408889634f) - 1.0f);
+  } else if (act == ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] = fmaxf(v[j], 0.f);
+  } else if (act == ACT_LRELU02) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] = v[j] > 0.f ? v[j] : 0.2f * v[j];
+  } else if (act != ACT_NONE) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] = act_apply(v[j], act);
+  }
+}
+
+// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue.
+// Two TMEM accumulator stages (2 x BN columns): the epilogue of tile i overlaps the main loop of tile i+1.
+// Tile order: linear id -> (split z, m tile, n tile) with n fastest, so CTAs running side by side share the A tile in L2.
 template <int BN, int NSPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
@@ -133,35 +172,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   constexpr int STAGE_BYTES = NPLANES * (A_BYTES + W_BYTES);
   constexpr uint32_t IDESC = umma_idesc_bf16(TC_BM, BN);
   constexpr int MAX_STAGES = 8;
+  constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  constexpr int EPI_CHUNK = BN >= 64 ? 32 : 16;      // columns per TMEM load
+  constexpr int HALF_COLS = BN / 2;                  // columns owned by one of the two epilogue warps of a lane quarter
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B needs 1024-byte alignment
   __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
-  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int stages = a.stages;
-
-  // tile coordinates
   const int txy = a.tiles_x * a.tiles_y;
-  const int tf = blockIdx.x / txy;
-  const int ty = (blockIdx.x % txy) / a.tiles_x;
-  const int tx = blockIdx.x % a.tiles_x;
-  const int f0 = tf * a.bf, y0 = ty * a.bh, x0 = tx * a.bw;
-  const int n0 = blockIdx.y * BN;
-  const int tap_begin = blockIdx.z * a.taps_per_split;
-  const int tap_end = min(a.ntaps, tap_begin + a.taps_per_split);
-  const int iters = (tap_end - tap_begin) * a.nkb;
+  const int tiles_mn = a.tiles_m * a.tiles_n;
+  const int total_tiles = tiles_mn * a.nsplit;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(&tmem_full_bar, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], TC_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // TMEM allocation by one full warp; the same warp deallocates
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -174,19 +209,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int t = tap_begin; t < tap_end; ++t) {
-        const int dy = a.dy[t], dx = a.dx[t], wrow = a.widx[t] * a.Npad + n0;
-        for (int kb = 0; kb < a.nkb; ++kb) {
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* st = smem + (size_t)s * STAGE_BYTES;
-          mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-          tma_load_4d(st, &tmA_hi, &full_bar[s], kb * TC_BK, x0 + dx, y0 + dy, f0);
-          tma_load_2d(st + NPLANES * A_BYTES, &tmW_hi, &full_bar[s], kb * TC_BK, wrow);
-          if (NSPLIT == 3) {
-            tma_load_4d(st + A_BYTES, &tmA_lo, &full_bar[s], kb * TC_BK, x0 + dx, y0 + dy, f0);
-            tma_load_2d(st + NPLANES * A_BYTES + W_BYTES, &tmW_lo, &full_bar[s], kb * TC_BK, wrow);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int z = tile / tiles_mn, rem = tile - z * tiles_mn;
+        const int mt = rem / a.tiles_n, nt = rem - mt * a.tiles_n;
+        const int tf = mt / txy, r2 = mt - tf * txy;
+        const int ty = r2 / a.tiles_x, tx = r2 - ty * a.tiles_x;
+        const int f0 = tf * a.bf, y0 = ty * a.bh, x0 = tx * a.bw, n0 = nt * BN;
+        const int tap_begin = z * a.taps_per_split, tap_end = min(a.ntaps, tap_begin + a.taps_per_split);
+        for (int t = tap_begin; t < tap_end; ++t) {
+          const int dy = a.dy[t], dx = a.dx[t], wrow = a.widx[t] * a.Npad + n0;
+          for (int kb = 0; kb < a.nkb; ++kb) {
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            uint8_t* st = smem + (size_t)s * STAGE_BYTES;
+            mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+            tma_load_4d(st, &tmA_hi, &full_bar[s], kb * TC_BK, x0 + dx, y0 + dy, f0);
+            tma_load_2d(st + NPLANES * A_BYTES, &tmW_hi, &full_bar[s], kb * TC_BK, wrow);
+            if (NSPLIT == 3) {
+              tma_load_4d(st + A_BYTES, &tmA_lo, &full_bar[s], kb * TC_BK, x0 + dx, y0 + dy, f0);
+              tma_load_2d(st + NPLANES * A_BYTES + W_BYTES, &tmW_lo, &full_bar[s], kb * TC_BK, wrow);
+            }
+            if (++s == stages) { s = 0; ph ^= 1; }
           }
-          if (++s == stages) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -195,85 +238,132 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int it = 0; it < iters; ++it) {
-        mbar_wait(&full_bar[s], ph);
+      int as = 0;
+      uint32_t aph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int z = tile / tiles_mn;
+        const int tap_begin = z * a.taps_per_split, tap_end = min(a.ntaps, tap_begin + a.taps_per_split);
+        const int iters = (tap_end - tap_begin) * a.nkb;
+        mbar_wait(&tmem_empty_bar[as], aph ^ 1);      // epilogue has drained this accumulator stage
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
-        const uint32_t sw = sa + NPLANES * A_BYTES;
-        const uint64_t da_hi = umma_desc_sw128(sa), dw_hi = umma_desc_sw128(sw);
+        const uint32_t tacc = tmem_base + (uint32_t)(as * BN);
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+          const uint32_t sw = sa + NPLANES * A_BYTES;
+          const uint64_t da_hi = umma_desc_sw128(sa), dw_hi = umma_desc_sw128(sw);
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k) {
-          const uint64_t koff = (uint64_t)((k * 32) >> 4);   // 16 bf16 = 32 bytes along K inside the swizzle atom
-          umma_bf16(tmem_base, da_hi + koff, dw_hi + koff, IDESC, (it > 0 || k > 0) ? 1u : 0u);
-          if (NSPLIT == 3) {
-            const uint64_t da_lo = umma_desc_sw128(sa + A_BYTES), dw_lo = umma_desc_sw128(sw + W_BYTES);
-            umma_bf16(tmem_base, da_lo + koff, dw_hi + koff, IDESC, 1u);
-            umma_bf16(tmem_base, da_hi + koff, dw_lo + koff, IDESC, 1u);
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint64_t koff = (uint64_t)((k * 32) >> 4);   // 16 bf16 = 32 bytes along K inside the swizzle atom
+            umma_bf16(tacc, da_hi + koff, dw_hi + koff, IDESC, (it > 0 || k > 0) ? 1u : 0u);
+            if (NSPLIT == 3) {
+              const uint64_t da_lo = umma_desc_sw128(sa + A_BYTES), dw_lo = umma_desc_sw128(sw + W_BYTES);
+              umma_bf16(tacc, da_lo + koff, dw_hi + koff, IDESC, 1u);
+              umma_bf16(tacc, da_hi + koff, dw_lo + koff, IDESC, 1u);
+            }
           }
+          umma_commit(&empty_bar[s]);                 // frees the stage once the MMAs above have read it
+          if (it == iters - 1) umma_commit(&tmem_full_bar[as]);
+          if (++s == stages) { s = 0; ph ^= 1; }
         }
-        umma_commit(&empty_bar[s]);                 // frees the stage once the MMAs above have read it
-        if (it == iters - 1) umma_commit(&tmem_full_bar);
-        if (++s == stages) { s = 0; ph ^= 1; }
+        if (++as == 2) { as = 0; aph ^= 1; }
       }
     }
   } else {
-    // ===================== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====================
-    mbar_wait(&tmem_full_bar, 0);
-    tc_fence_after();
+    // ===================== epilogue: warps 2..9; TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 ============
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int r = q * 32 + lane;                    // accumulator row == pixel index inside the box
     const int xl = r % a.bw, yl = (r / a.bw) % a.bh, fl = r / (a.bw * a.bh);
-    const int f = f0 + fl, y = y0 + yl, x = x0 + xl;
-    const bool valid = (f < a.F) && (y < a.H) && (x < a.W);
-    const size_t opix = ((size_t)f * a.Ho + (size_t)(y * a.ymul + a.yadd)) * a.Wo + (size_t)(x * a.xmul + a.xadd);
-    const size_t obase = opix * a.out_cstride + a.out_coff;
-    float* outf = (float*)a.out + (size_t)blockIdx.z * a.split_stride;
+    int as = 0;
+    uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int z = tile / tiles_mn, rem = tile - z * tiles_mn;
+      const int mt = rem / a.tiles_n, nt = rem - mt * a.tiles_n;
+      const int tf = mt / txy, r2 = mt - tf * txy;
+      const int ty = r2 / a.tiles_x, tx = r2 - ty * a.tiles_x;
+      const int f = tf * a.bf + fl, y = ty * a.bh + yl, x = tx * a.bw + xl;
+      const int n0 = nt * BN;
+      const bool valid = (f < a.F) && (y < a.H) && (x < a.W);
+      const int oy = y * a.ymul + a.yadd, ox = x * a.xmul + a.xadd;
+      const size_t opix = ((size_t)f * a.Ho + (size_t)oy) * a.Wo + (size_t)ox;
+      const size_t obase = opix * a.out_cstride + a.out_coff;
+      float* outf = (float*)a.out + (size_t)z * a.split_stride;
+
+      mbar_wait(&tmem_full_bar[as], aph);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 16) {
-      if (n0 + c >= a.Npad) break;                  // warp-uniform
-      uint32_t rr[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, rr);
-      tmem_ld_wait();
-      if (!valid) continue;
-      float v[16];
+      for (int c = half * HALF_COLS; c < (half + 1) * HALF_COLS; c += EPI_CHUNK) {
+        if (n0 + c >= a.Npad) break;                  // warp-uniform
+        const int ncols = min(EPI_CHUNK, a.Npad - (n0 + c));   // Npad is a multiple of 16: a 32-column chunk may be half valid
+        float v[EPI_CHUNK];
+        {
+          uint32_t rr[EPI_CHUNK];
+          if constexpr (EPI_CHUNK == 32) tmem_ld32(tacc + (uint32_t)c, rr);
+          else tmem_ld16(tacc + (uint32_t)c, rr);
+          tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float t = __uint_as_float(rr[j]);
-        if (a.bias) t += __ldg(a.bias + n0 + c + j);
-        v[j] = act_apply(t, a.act);
-      }
-      const size_t o = obase + n0 + c;
-      if (a.out_mode == OUT_F32_NHWC) {
-        float4* p = (float4*)(outf + o);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) p[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-      } else {
-        uint32_t hi[8], lo[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          __nv_bfloat16 h0, l0, h1, l1;
-          split_bf16(v[2 * j], h0, l0);
-          split_bf16(v[2 * j + 1], h1, l1);
-          __nv_bfloat162 hh(h0, h1), ll(l0, l1);
-          hi[j] = *(uint32_t*)&hh;
-          lo[j] = *(uint32_t*)&ll;
+          for (int j = 0; j < EPI_CHUNK; ++j) v[j] = __uint_as_float(rr[j]);
         }
-        uint4* ph = (uint4*)((__nv_bfloat16*)a.out + o);
-        ph[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        ph[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-        if (a.out_mode == OUT_BF16_SPLIT) {
-          uint4* pl = (uint4*)((__nv_bfloat16*)a.out_lo + o);
-          pl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-          pl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+        if (!valid) continue;
+        if (a.bias) {
+          const float4* b4 = (const float4*)(a.bias + n0 + c);
+#pragma unroll
+          for (int j = 0; j < EPI_CHUNK / 4; ++j) {
+            if (4 * j >= ncols) break;
+            const float4 b = __ldg(b4 + j);
+            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+          }
+        }
+        act_tile<EPI_CHUNK>(v, a.act);
+        if (a.out_mode == OUT_F32_NHWC) {
+          float4* p = (float4*)(outf + obase + n0 + c);
+#pragma unroll
+          for (int j = 0; j < EPI_CHUNK / 4; ++j)
+            if (4 * j < ncols) p[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else if (a.out_mode == OUT_F32_NCHW) {
+          // frames at the ABI edge: [f][N][Ho][Wo]; consecutive lanes are consecutive x -> coalesced per channel
+#pragma unroll
+          for (int j = 0; j < EPI_CHUNK; ++j) {
+            const int n = n0 + c + j;
+            if (n < a.N) ((float*)a.out)[(((size_t)f * a.N + n) * a.Ho + oy) * a.Wo + ox] = v[j];
+          }
+        } else {
+          uint32_t hi[EPI_CHUNK / 2], lo[EPI_CHUNK / 2];
+#pragma unroll
+          for (int j = 0; j < EPI_CHUNK / 2; ++j) {
+            const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            const float2 hf = __bfloat1622float2(hh);
+            const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
+            hi[j] = *(const uint32_t*)&hh;
+            lo[j] = *(const uint32_t*)&ll;
+          }
+          uint4* ph4 = (uint4*)((__nv_bfloat16*)a.out + obase + n0 + c);
+#pragma unroll
+          for (int j = 0; j < EPI_CHUNK / 8; ++j)
+            if (8 * j < ncols) ph4[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+          if (a.out_mode == OUT_BF16_SPLIT) {
+            uint4* pl4 = (uint4*)((__nv_bfloat16*)a.out_lo + obase + n0 + c);
+#pragma unroll
+            for (int j = 0; j < EPI_CHUNK / 8; ++j)
+              if (8 * j < ncols) pl4[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+          }
         }
       }
+      // all TMEM reads of this warp are complete (wait::ld above): hand the accumulator stage back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+      if (++as == 2) { as = 0; aph ^= 1; }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -325,9 +415,19 @@ static CUtensorMap make_map(const void* base, int rank, const long long* dims, c
   return m;
 }
 
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    IPK_CUDA(cudaGetDevice(&dev));
+    IPK_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  }
+  return n;
+}
+
 template <int BN, int NSPLIT>
 static void launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo, TcArgs& a,
-                      dim3 grid, cudaStream_t st) {
+                      cudaStream_t st) {
   constexpr int STAGE_BYTES = (NSPLIT == 3 ? 2 : 1) * (TC_BM * TC_BK * 2 + BN * TC_BK * 2);
   int stages = (int)std::min<size_t>(8, TC_SMEM_BUDGET / STAGE_BYTES);
   a.stages = stages;
@@ -337,6 +437,8 @@ static void launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CU
     IPK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TC_SMEM_BUDGET + 1024)));
     attr_set = true;
   }
+  const long long total = (long long)a.tiles_m * a.tiles_n * a.nsplit;
+  const unsigned grid = (unsigned)std::min<long long>(total, sm_count());     // persistent: one CTA per SM
   conv_tc_kernel<BN, NSPLIT><<<grid, TC_THREADS, smem, st>>>(a_hi, a_lo, w_hi, w_lo, a);
   IPK_LAUNCH_CHECK();
 }
@@ -346,10 +448,10 @@ void conv_tc_run(const ConvW& w, const ConvIn& in, const ConvOut& out, const Tap
   const bool split = w.engine == IPK_PREC_FP32_SPLIT;
   IPK_CHECK(!split || (in.p_lo && w.w_lo), IPK_ERR_STATE, "conv_tc_run: split precision needs hi and lo operand planes");
   IPK_CHECK(in.cstride % 8 == 0 && in.coff % 8 == 0, IPK_ERR_UNSUPPORTED, "conv_tc_run: activation rows must be 16-byte aligned (cstride %d, coff %d)", in.cstride, in.coff);
-  IPK_CHECK(out.mode != OUT_F32_NCHW, IPK_ERR_UNSUPPORTED, "conv_tc_run: NCHW output is served by the SIMT engine");
-  IPK_CHECK((out.cstride % 4 == 0) && (out.coff % 4 == 0) && out.coff + w.Npad <= out.cstride, IPK_ERR_UNSUPPORTED,
-            "conv_tc_run: output row (cstride %d, coff %d) cannot hold Npad %d", out.cstride, out.coff, w.Npad);
-  if (out.mode != OUT_F32_NHWC) IPK_CHECK(out.cstride % 8 == 0 && out.coff % 8 == 0, IPK_ERR_UNSUPPORTED, "conv_tc_run: bf16 output rows must be 16-byte aligned");
+  if (out.mode != OUT_F32_NCHW)
+    IPK_CHECK((out.cstride % 4 == 0) && (out.coff % 4 == 0) && out.coff + w.Npad <= out.cstride, IPK_ERR_UNSUPPORTED,
+              "conv_tc_run: output row (cstride %d, coff %d) cannot hold Npad %d", out.cstride, out.coff, w.Npad);
+  if (out.mode == OUT_BF16_SPLIT || out.mode == OUT_BF16) IPK_CHECK(out.cstride % 8 == 0 && out.coff % 8 == 0, IPK_ERR_UNSUPPORTED, "conv_tc_run: bf16 output rows must be 16-byte aligned");
   long long M = (long long)in.F * in.H * in.W;
   if (M == 0) return;
   TcArgs a;
@@ -372,7 +474,7 @@ void conv_tc_run(const ConvW& w, const ConvIn& in, const ConvOut& out, const Tap
   IPK_CHECK(nsplit == 1 || (out.mode == OUT_F32_NHWC && out.split_stride > 0), IPK_ERR_INVALID, "split-K needs fp32 partial slices");
   a.nkb = w.Kpad / TC_BK;
   for (int i = 0; i < MAX_TAPS; ++i) { a.dy[i] = taps.dy[i]; a.dx[i] = taps.dx[i]; a.widx[i] = taps.widx[i]; }
-  a.Npad = w.Npad;
+  a.Npad = w.Npad; a.N = w.N;
   a.bias = out.bias; a.act = out.act; a.out_mode = out.mode; a.out_cstride = out.cstride; a.out_coff = out.coff;
   a.Ho = out.Ho; a.Wo = out.Wo; a.ymul = out.ymul; a.yadd = out.yadd; a.xmul = out.xmul; a.xadd = out.xadd;
   a.out = out.p; a.out_lo = out.p_lo; a.split_stride = out.split_stride;
@@ -392,11 +494,13 @@ void conv_tc_run(const ConvW& w, const ConvIn& in, const ConvOut& out, const Tap
   CUtensorMap mW_hi = make_map(w.w_hi, 2, wd, wsb, wb);
   CUtensorMap mW_lo = split ? make_map(w.w_lo, 2, wd, wsb, wb) : mW_hi;
 
-  dim3 grid((unsigned)(a.tiles_x * a.tiles_y * tiles_f), (unsigned)cdiv(w.Npad, BN), (unsigned)nsplit);
-#define IPK_TC_CASE(bn)                                                             \
-  case bn:                                                                          \
-    if (split) launch_tc<bn, 3>(mA_hi, mA_lo, mW_hi, mW_lo, a, grid, st);           \
-    else launch_tc<bn, 1>(mA_hi, mA_lo, mW_hi, mW_lo, a, grid, st);                 \
+  a.tiles_m = a.tiles_x * a.tiles_y * tiles_f;
+  a.tiles_n = cdiv(w.Npad, BN);
+  a.nsplit = nsplit;
+#define IPK_TC_CASE(bn)                                                       \
+  case bn:                                                                    \
+    if (split) launch_tc<bn, 3>(mA_hi, mA_lo, mW_hi, mW_lo, a, st);           \
+    else launch_tc<bn, 1>(mA_hi, mA_lo, mW_hi, mW_lo, a, st);                 \
     break;
   switch (BN) {
     IPK_TC_CASE(32)

@@ -201,14 +201,13 @@ static void decode_frames(ipk_fs* d, const float* h, int nv, int T, int v0, floa
     // SPADE: GroupNorm(16, affine=False)(out) * (1 + gamma) + beta
     stats_norm(d, d->bufS, F, P, ub.Cout, ub.groups, st);
     NormApply sp; sp.x = d->bufS; sp.F = F; sp.C = ub.Cout; sp.P = P; sp.mr = d->mr; sp.spade = ub.SP + (size_t)v0 * P * 2 * ub.Cout; sp.T = T;
-    if (last) sp.out_f32 = d->bufR;          // out_conv runs on the fp32 SIMT engine
-    else to_operand(d, sp, d->bufA, d->bufA_lo);
+    to_operand(d, sp, d->bufA, d->bufA_lo);
     norm_apply(sp, st);
   }
   // ---- out_conv: 3x3 -> 3 channels + tanh, written straight into the NCHW frame tensor
   {
     const int Cl = d->cfg.dec_channels[d->nd - 1];
-    ConvIn in; in.p = d->bufR; in.cstride = Cl; in.F = F; in.H = d->S; in.W = d->S;
+    ConvIn in; in.p = d->bufA; in.p_lo = d->bufA_lo; in.cstride = Cl; in.F = F; in.H = d->S; in.W = d->S;
     ConvOut o; o.p = frames; o.mode = OUT_F32_NCHW; o.Ho = d->S; o.Wo = d->S; o.act = ACT_TANH; o.bias = d->out_conv.bias;
     ProfScope ps("dec.out_conv", st);
     conv_run(d->out_conv, in, o, taps_3x3(), 1, st);
@@ -333,7 +332,7 @@ extern "C" int ipk_fs_finalize(ipk_fs* d, void* stream) {
     fe = std::max(fe, (size_t)ub.s_in * ub.s_in * ub.Cin);
     d->blocks.push_back(ub);
   }
-  d->out_conv = build_conv3(d, "gen.out_conv.conv.", IPK_PREC_FP32_SIMT, 3, dc[d->nd - 1], false, 0.f, st);
+  d->out_conv = build_conv3(d, "gen.out_conv.conv.", eng, 3, dc[d->nd - 1], false, 0.f, st);
   d->frame_elems = fe;
   // ---- workspace
   const size_t Mmax = (size_t)d->cfg.max_batch * 64;
