@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--frames", type=int, default=16)
     ap.add_argument("--spatial", type=int, default=128)
     ap.add_argument("--cpu-sample", type=int, default=2, help="videos per CPU-baseline step")
+    ap.add_argument("--chunk-videos", type=int, default=0, help="videos decoded per decoder pass (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-phases", action="store_true")
@@ -201,7 +202,7 @@ def run_ours(a):
                 ipk_precision=a.precision, ipk_max_batch=B)
     dec = [256, 256, 256, 128, 64] if S == 128 else [256, 256, 128, 64]
     dcfg = dict(z_dim=32, norm="group", spectral_norm=True, n_gru_layers=4, dec_channels=dec, min_spatial_size=8, motion_bias=True,
-                spatial=S, ipk_precision=a.precision, ipk_max_batch=B, ipk_max_frames=T)
+                spatial=S, ipk_precision=a.precision, ipk_max_batch=B, ipk_max_frames=T, ipk_chunk_videos=a.chunk_videos)
     torch.manual_seed(1234)
     with torch.device(dev):
         flow = ipk.SupervisedMacowTransformer(fcfg)

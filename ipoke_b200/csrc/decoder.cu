@@ -44,7 +44,10 @@ struct ipk_fs {
   std::vector<UpBlock> blocks;
   ConvW out_conv;
   // workspace
-  std::vector<float*> XH, XRH;   // [L] each [Mmax][2z]
+  std::vector<char*> XH, XRH;    // [L] conv-input operands (x | h), (x | r*h): [Mmax][2z] in the engine's storage mode
+  std::vector<float*> Hf;        // [L] fp32 hidden state [Mmax][z]
+  float* xtmp = nullptr;         // [Mmax][z] fp32 staging of the layer-0 input
+  void* spI = nullptr; void* spI_lo = nullptr;   // SPADE 3->128 conv input: 3x3 im2col rows [B*S*S][32]
   float* U = nullptr; float* graw = nullptr; float* Hseq = nullptr;
   float* x0r = nullptr; void* spY = nullptr; void* spY_lo = nullptr;
   void* bufA = nullptr; void* bufA_lo = nullptr; void* bufY1 = nullptr; void* bufY1_lo = nullptr;
@@ -132,9 +135,16 @@ static void spade_maps(ipk_fs* d, const float* x0, int B, cudaStream_t st) {
   for (UpBlock& ub : d->blocks) {
     const int s = 2 * ub.s_in;
     bilinear_nchw_to_nhwc(x0, d->x0r, B, 3, d->S, s, st);
-    ConvIn in; in.p = d->x0r; in.cstride = 3; in.F = B; in.H = s; in.W = s;
     ConvOut o; o.p = d->spY; o.p_lo = d->spY_lo; o.mode = d->act_mode; o.cstride = 128; o.Ho = s; o.Wo = s; o.act = ACT_LRELU02; o.bias = ub.sp1.bias;
-    conv_run(ub.sp1, in, o, taps_3x3(), 1, st);
+    if (d->eng == IPK_PREC_FP32_SIMT) {
+      ConvIn in; in.p = d->x0r; in.cstride = 3; in.F = B; in.H = s; in.W = s;
+      conv_run(ub.sp1, in, o, taps_3x3(), 1, st);
+    } else {
+      OperandDst im; im.p = d->spI; im.p_lo = d->spI_lo; im.mode = d->act_mode; im.cstride = 32; im.coff = 0;
+      im2col3x3_small(d->x0r, B, s, 3, im, 32, st);
+      ConvIn in; in.p = d->spI; in.p_lo = d->spI_lo; in.cstride = 32; in.F = B; in.H = s; in.W = s;
+      conv_run(ub.sp1, in, o, taps_1x1(), 1, st);
+    }
     ConvIn in2; in2.p = d->spY; in2.p_lo = d->spY_lo; in2.cstride = 128; in2.F = B; in2.H = s; in2.W = s;
     ConvOut o2; o2.p = ub.SP; o2.mode = OUT_F32_NHWC; o2.cstride = 2 * ub.Cout; o2.Ho = s; o2.Wo = s; o2.bias = ub.spgb.bias;
     conv_run(ub.spgb, in2, o2, taps_3x3(), 1, st);
@@ -214,26 +224,46 @@ static void decode_frames(ipk_fs* d, const float* h, int nv, int T, int v0, floa
   }
 }
 
+static OperandDst gru_operand(ipk_fs* d, char* base, int coff) {
+  const size_t Mmax = (size_t)d->cfg.max_batch * 64;
+  OperandDst o;
+  o.p = base; o.mode = d->act_mode; o.cstride = 2 * d->z; o.coff = coff;
+  o.p_lo = d->act_mode == OUT_BF16_SPLIT ? base + Mmax * 2 * d->z * 2 : nullptr;
+  return o;
+}
+
+// (x | h) and (x | r*h) operands of layer l from fp32 sources: x [M][z] (may be null = leave), h = Hf[l]
+static void gru_load_layer(ipk_fs* d, int l, const float* x, int B, cudaStream_t st) {
+  const int z = d->z;
+  const long long M = (long long)B * 64;
+  operand_copy(d->Hf[l], z, 0, gru_operand(d, d->XH[l], z), M, z, st);
+  if (x) {
+    operand_copy(x, z, 0, gru_operand(d, d->XH[l], 0), M, z, st);
+    operand_copy(x, z, 0, gru_operand(d, d->XRH[l], 0), M, z, st);
+  }
+}
+
 // one ConvGRU step over all layers (ConvGRU.forward, rnn.py:104-133); XH[l] = (x | h), XRH[l] = (x | r*h)
 static void gru_step(ipk_fs* d, int B, float* seq_out, int T, int t, cudaStream_t st) {
   const int z = d->z;
   const long long M = (long long)B * 64;
   for (int l = 0; l < d->L; ++l) {
-    ConvIn in; in.p = d->XH[l]; in.cstride = 2 * z; in.F = B; in.H = 8; in.W = 8;
-    ConvOut o; o.p = d->graw; o.cstride = 2 * z; o.Ho = 8; o.Wo = 8; o.bias = d->gru_ur[l].bias;
+    const OperandDst xh = gru_operand(d, d->XH[l], 0), xrh = gru_operand(d, d->XRH[l], 0);
+    ConvIn in; in.p = xh.p; in.p_lo = xh.p_lo; in.cstride = 2 * z; in.F = B; in.H = 8; in.W = 8;
+    ConvOut o; o.p = d->graw; o.cstride = d->gru_ur[l].Npad; o.Ho = 8; o.Wo = 8; o.bias = d->gru_ur[l].bias;
     conv_run(d->gru_ur[l], in, o, taps_3x3(), 1, st);
-    gru_gate1(d->graw, d->XH[l], d->U, d->XRH[l], M, z, st);
-    ConvIn in2; in2.p = d->XRH[l]; in2.cstride = 2 * z; in2.F = B; in2.H = 8; in2.W = 8;
-    ConvOut o2; o2.p = d->graw; o2.cstride = z; o2.Ho = 8; o2.Wo = 8; o2.bias = d->gru_o[l].bias;
+    gru_gate1(d->graw, d->Hf[l], d->U, gru_operand(d, d->XRH[l], z), M, z, st);
+    ConvIn in2; in2.p = xrh.p; in2.p_lo = xrh.p_lo; in2.cstride = 2 * z; in2.F = B; in2.H = 8; in2.W = 8;
+    ConvOut o2; o2.p = d->graw; o2.cstride = d->gru_o[l].Npad; o2.Ho = 8; o2.Wo = 8; o2.bias = d->gru_o[l].bias;
     conv_run(d->gru_o[l], in2, o2, taps_3x3(), 1, st);
-    GruDst dst[3];
+    OperandDst dst[3];
     int nd = 0;
-    dst[nd++] = GruDst{d->XH[l], 2 * z, z};
+    dst[nd++] = gru_operand(d, d->XH[l], z);
     if (l + 1 < d->L) {
-      dst[nd++] = GruDst{d->XH[l + 1], 2 * z, 0};
-      dst[nd++] = GruDst{d->XRH[l + 1], 2 * z, 0};
+      dst[nd++] = gru_operand(d, d->XH[l + 1], 0);
+      dst[nd++] = gru_operand(d, d->XRH[l + 1], 0);
     }
-    gru_gate2(d->graw, d->U, d->XH[l], M, z, dst, nd, (l + 1 == d->L) ? seq_out : nullptr, T, t, st);
+    gru_gate2(d->graw, d->U, d->Hf[l], M, z, dst, nd, (l + 1 == d->L) ? seq_out : nullptr, T, t, st);
   }
 }
 
@@ -257,7 +287,7 @@ extern "C" int ipk_fs_create(const ipk_fs_config* cfg, ipk_fs** out) {
   d->cfg = *cfg;
   d->z = cfg->z_dim; d->S = cfg->spatial; d->L = cfg->n_gru_layers; d->nd = cfg->n_dec; d->eng = cfg->precision;
   d->act_mode = d->eng == IPK_PREC_FP32_SIMT ? OUT_F32_NHWC : (d->eng == IPK_PREC_FP32_SPLIT ? OUT_BF16_SPLIT : OUT_BF16);
-  d->chunk_videos = cfg->chunk_videos > 0 ? cfg->chunk_videos : std::max(1, 64 / cfg->max_frames);
+  d->chunk_videos = cfg->chunk_videos > 0 ? cfg->chunk_videos : std::max(1, 256 / cfg->max_frames);
   d->chunk_videos = std::min(d->chunk_videos, cfg->max_batch);
   *out = d;
   IPK_CATCH
@@ -277,10 +307,12 @@ extern "C" int ipk_fs_finalize(ipk_fs* d, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int z = d->z, eng = d->eng;
   const int* dc = d->cfg.dec_channels;
-  // ---- ConvGRU: update|reset gates share one contraction (N = 2z); fp32 SIMT engine
+  // ---- ConvGRU: update|reset gates share one contraction (N = 2z)
+  const int geng = (eng != IPK_PREC_FP32_SIMT && z % 16 == 0) ? eng : IPK_PREC_FP32_SIMT;
+  IPK_CHECK(geng == eng, IPK_ERR_UNSUPPORTED, "first stage: tensor-core engine needs z_dim %% 16 == 0");
   for (int l = 0; l < d->L; ++l) {
     std::string p = "rnn.cells." + std::to_string(l) + ".";
-    ConvW ur = conv_alloc(d->pool, IPK_PREC_FP32_SIMT, 9, 2 * z, 2 * z, true);
+    ConvW ur = conv_alloc(d->pool, geng, 9, 2 * z, 2 * z, true);
     PackSrc s; s.N = z; s.Ksrc = 2 * z; s.kh = 3; s.kw = 3;
     s.w = (const float*)fneed(d, p + "update_gate.weight", (int64_t)z * 2 * z * 9).p;
     conv_pack_into(ur, 0, s, ALL9, st);
@@ -289,7 +321,7 @@ extern "C" int ipk_fs_finalize(ipk_fs* d, void* stream) {
     conv_pack_into(ur, z, s, ALL9, st);
     conv_pack_bias(ur, z, (const float*)fneed(d, p + "reset_gate.bias", z).p, z, 0.f, st);
     d->gru_ur.push_back(ur);
-    ConvW og = conv_alloc(d->pool, IPK_PREC_FP32_SIMT, 9, 2 * z, z, true);
+    ConvW og = conv_alloc(d->pool, geng, 9, 2 * z, z, true);
     s.w = (const float*)fneed(d, p + "out_gate.weight", (int64_t)z * 2 * z * 9).p;
     conv_pack_into(og, 0, s, ALL9, st);
     conv_pack_bias(og, 0, (const float*)fneed(d, p + "out_gate.bias", z).p, z, 0.f, st);
@@ -315,7 +347,21 @@ extern "C" int ipk_fs_finalize(ipk_fs* d, void* stream) {
     ub.ctr = build_conv3(d, p + "res_conv.conv.", eng, ub.Cout, ub.Cin, true, 0.f, st);
     ub.c2 = build_conv3(d, p + "conv2.conv.", eng, ub.Cout, ub.Cout, false, 0.f, st);
     std::string sp = "gen.spade_blocks." + std::to_string(i) + ".";
-    ub.sp1 = build_conv3(d, sp + "conv.", IPK_PREC_FP32_SIMT, 128, 3, false, 0.f, st);
+    if (eng == IPK_PREC_FP32_SIMT) {
+      ub.sp1 = build_conv3(d, sp + "conv.", IPK_PREC_FP32_SIMT, 128, 3, false, 0.f, st);
+    } else {
+      // one-tap GEMM over 3x3 im2col rows: k = tap*3 + c  <-  OIHW column c*9 + tap
+      ub.sp1 = conv_alloc(d->pool, eng, 1, 27, 128, true);
+      std::vector<int> kmap(27);
+      for (int t = 0; t < 9; ++t)
+        for (int c = 0; c < 3; ++c) kmap[t * 3 + c] = c * 9 + t;
+      int* d_kmap = d->pool.alloc<int>(27);
+      IPK_CUDA(cudaMemcpyAsync(d_kmap, kmap.data(), 27 * sizeof(int), cudaMemcpyHostToDevice, st));
+      IPK_CUDA(cudaStreamSynchronize(st));
+      PackSrc ps; ps.w = (const float*)fneed(d, sp + "conv.weight", 128 * 27).p; ps.N = 128; ps.Ksrc = 27; ps.k_map = d_kmap;
+      conv_pack_into(ub.sp1, 0, ps, {0}, st);
+      conv_pack_bias(ub.sp1, 0, (const float*)fneed(d, sp + "conv.bias", 128).p, 128, 0.f, st);
+    }
     // gamma and beta convolutions fused along N; "+1" of (1 + gamma) folded into the gamma bias
     ub.spgb = conv_alloc(d->pool, eng, 9, 128, 2 * ub.Cout, true);
     PackSrc s; s.N = ub.Cout; s.Ksrc = 128; s.kh = 3; s.kw = 3;
@@ -340,15 +386,24 @@ extern "C" int ipk_fs_finalize(ipk_fs* d, void* stream) {
   const size_t Fm = std::max<size_t>(d->Fmax, 1);
   auto rb = [](size_t b) { return (b + 255) / 256 * 256; };
   size_t bytes = 0;
-  bytes += (size_t)d->L * 2 * rb(Mmax * 2 * z * 4) + rb(Mmax * z * 4) + rb(Mmax * 2 * z * 4);
+  bytes += (size_t)d->L * (2 * rb(Mmax * 2 * z * 4) + rb(Mmax * z * 4)) + 2 * rb(Mmax * z * 4) + rb(Mmax * 2 * z * 4);
+  bytes += rb((size_t)d->cfg.max_batch * d->S * d->S * 32 * 4);
   bytes += rb(Mmax * d->cfg.max_frames * z * 4);                               // Hseq
   bytes += rb((size_t)d->cfg.max_batch * d->S * d->S * 3 * 4) + rb((size_t)d->cfg.max_batch * d->S * d->S * 128 * 4);
   bytes += 5 * rb(Fm * fe * 4);
   bytes += rb(Fm * 512 * 2 * 8) + rb(Fm * 512 * 2 * 4) + 65536;
   d->ws.init(bytes);
   for (int l = 0; l < d->L; ++l) {
-    d->XH.push_back(d->ws.alloc<float>(Mmax * 2 * z));
-    d->XRH.push_back(d->ws.alloc<float>(Mmax * 2 * z));
+    d->XH.push_back((char*)d->ws.alloc<float>(Mmax * 2 * z));
+    d->XRH.push_back((char*)d->ws.alloc<float>(Mmax * 2 * z));
+    d->Hf.push_back(d->ws.alloc<float>(Mmax * z));
+  }
+  d->xtmp = d->ws.alloc<float>(Mmax * z);
+  {
+    const size_t n = (size_t)d->cfg.max_batch * d->S * d->S * 32;
+    char* p = (char*)d->ws.alloc<float>(n);
+    d->spI = p;
+    d->spI_lo = d->act_mode == OUT_BF16_SPLIT ? p + n * 2 : nullptr;
   }
   d->U = d->ws.alloc<float>(Mmax * z);
   d->graw = d->ws.alloc<float>(Mmax * 2 * z);
@@ -382,11 +437,11 @@ static void fs_decode_impl(ipk_fs* d, const float* motion, bool motion_is_nhwc, 
   const long long M = (long long)B * 64;
   // hidden = [motion] * n_layers ; in_rnn = motion_bias repeated over the batch (second_stage_video.py:365-372)
   for (int l = 0; l < d->L; ++l) {
-    if (motion_is_nhwc) copy_channels(motion, z, 0, d->XH[l], 2 * z, z, M, z, st);
-    else nchw_to_nhwc(motion, d->XH[l] + z, B, z, 64, 2 * z, st);
+    if (motion_is_nhwc) copy_channels(motion, z, 0, d->Hf[l], z, 0, M, z, st);
+    else nchw_to_nhwc(motion, d->Hf[l], B, z, 64, z, st);
   }
-  broadcast_chw_to_nhwc(d->motion_bias, d->XH[0], B, z, 64, 2 * z, 0, st);
-  broadcast_chw_to_nhwc(d->motion_bias, d->XRH[0], B, z, 64, 2 * z, 0, st);
+  broadcast_chw_to_nhwc(d->motion_bias, d->xtmp, B, z, 64, z, 0, st);
+  for (int l = 0; l < d->L; ++l) gru_load_layer(d, l, l == 0 ? d->xtmp : nullptr, B, st);
   {
     ProfScope ps("gru", st);
     for (int t = 0; t < T; ++t) gru_step(d, B, d->Hseq, T, t, st);
@@ -421,11 +476,11 @@ extern "C" int ipk_fs_gru_step(ipk_fs* d, const float* x, const float* hidden, f
   cudaStream_t st = (cudaStream_t)stream;
   const int z = d->z;
   const size_t per = (size_t)B * z * 64;
-  for (int l = 0; l < d->L; ++l) nchw_to_nhwc(hidden + l * per, d->XH[l] + z, B, z, 64, 2 * z, st);
-  nchw_to_nhwc(x, d->XH[0], B, z, 64, 2 * z, st);
-  nchw_to_nhwc(x, d->XRH[0], B, z, 64, 2 * z, st);
+  for (int l = 0; l < d->L; ++l) nchw_to_nhwc(hidden + l * per, d->Hf[l], B, z, 64, z, st);
+  nchw_to_nhwc(x, d->xtmp, B, z, 64, z, st);
+  for (int l = 0; l < d->L; ++l) gru_load_layer(d, l, l == 0 ? d->xtmp : nullptr, B, st);
   gru_step(d, B, nullptr, 1, 0, st);
-  for (int l = 0; l < d->L; ++l) nhwc_to_nchw(d->XH[l] + z, new_hidden + l * per, B, z, 64, 2 * z, st);
+  for (int l = 0; l < d->L; ++l) nhwc_to_nchw(d->Hf[l], new_hidden + l * per, B, z, 64, z, st);
   IPK_CATCH
 }
 

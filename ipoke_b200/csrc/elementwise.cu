@@ -186,48 +186,92 @@ void norm_apply(const NormApply& n, cudaStream_t st) {
   IPK_LAUNCH_CHECK();
 }
 
-// ------------------------------------------------------------------ ConvGRU gates
-__global__ void gru_gate1_kernel(const float* __restrict__ raw, const float* __restrict__ xh, float* __restrict__ U,
-                                 float* __restrict__ xrh, long long M, int z) {
+// ------------------------------------------------------------------ operand stores / ConvGRU gates
+__device__ __forceinline__ void store_operand(const OperandDst& d, long long m, int c, float v) {
+  const size_t i = (size_t)m * d.cstride + d.coff + c;
+  if (d.mode == OUT_F32_NHWC) {
+    ((float*)d.p)[i] = v;
+  } else {
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    ((__nv_bfloat16*)d.p)[i] = hi;
+    if (d.mode == OUT_BF16_SPLIT) ((__nv_bfloat16*)d.p_lo)[i] = __float2bfloat16_rn(v - __bfloat162float(hi));
+  }
+}
+__global__ void operand_copy_kernel(const float* __restrict__ src, int scs, int scoff, OperandDst dst, long long M, int C) {
+  long long total = M * C;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(e % C);
+    long long m = e / C;
+    store_operand(dst, m, c, src[m * scs + scoff + c]);
+  }
+}
+void operand_copy(const float* src, int scs, int scoff, const OperandDst& dst, long long M, int C, cudaStream_t st) {
+  if (M * C == 0) return;
+  operand_copy_kernel<<<grid_for(M * C), 256, 0, st>>>(src, scs, scoff, dst, M, C);
+  IPK_LAUNCH_CHECK();
+}
+__global__ void gru_gate1_kernel(const float* __restrict__ raw, const float* __restrict__ Hf, float* __restrict__ U, OperandDst xrh,
+                                 long long M, int z) {
   long long total = M * z;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     int c = (int)(e % z);
     long long m = e / z;
     float u = 1.f / (1.f + expf(-raw[m * 2 * z + c]));
     float r = 1.f / (1.f + expf(-raw[m * 2 * z + z + c]));
-    float h = xh[m * 2 * z + z + c];
     U[e] = u;
-    xrh[m * 2 * z + z + c] = h * r;
+    store_operand(xrh, m, c, Hf[e] * r);
   }
 }
-void gru_gate1(const float* raw, const float* xh, float* U, float* xrh, long long M, int z, cudaStream_t st) {
-  gru_gate1_kernel<<<grid_for(M * z), 256, 0, st>>>(raw, xh, U, xrh, M, z);
+void gru_gate1(const float* raw, const float* Hf, float* U, const OperandDst& xrh, long long M, int z, cudaStream_t st) {
+  gru_gate1_kernel<<<grid_for(M * z), 256, 0, st>>>(raw, Hf, U, xrh, M, z);
   IPK_LAUNCH_CHECK();
 }
-struct GruDst4 { GruDst d[4]; int n; };
-__global__ void gru_gate2_kernel(const float* __restrict__ raw, const float* __restrict__ U, const float* __restrict__ xh,
-                                 long long M, int z, GruDst4 dst, float* __restrict__ seq_out, int T, int t) {
+struct OperandDst3 { OperandDst d[3]; int n; };
+__global__ void gru_gate2_kernel(const float* __restrict__ raw, const float* __restrict__ U, float* __restrict__ Hf,
+                                 long long M, int z, OperandDst3 dst, float* __restrict__ seq_out, int T, int t) {
   long long total = M * z;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     int c = (int)(e % z);
     long long m = e / z;
     float o = tanhf(raw[e]);
     float u = U[e];
-    float h = xh[m * 2 * z + z + c];
+    float h = Hf[e];
     float hn = h * (1.f - u) + o * u;
-    for (int i = 0; i < dst.n; ++i) dst.d[i].p[m * dst.d[i].cstride + dst.d[i].coff + c] = hn;
+    Hf[e] = hn;
+    for (int i = 0; i < dst.n; ++i) store_operand(dst.d[i], m, c, hn);
     if (seq_out) {
       long long b = m / 64, p = m % 64;      // 8x8 latent grid
       seq_out[((b * T + t) * 64 + p) * z + c] = hn;
     }
   }
 }
-void gru_gate2(const float* raw, const float* U, const float* xh, long long M, int z, const GruDst* dst, int ndst,
+void gru_gate2(const float* raw, const float* U, float* Hf, long long M, int z, const OperandDst* dst, int ndst,
                float* seq_out, int T, int t, cudaStream_t st) {
-  GruDst4 d;
+  OperandDst3 d;
   d.n = ndst;
-  for (int i = 0; i < ndst && i < 4; ++i) d.d[i] = dst[i];
-  gru_gate2_kernel<<<grid_for(M * z), 256, 0, st>>>(raw, U, xh, M, z, d, seq_out, T, t);
+  for (int i = 0; i < ndst && i < 3; ++i) d.d[i] = dst[i];
+  gru_gate2_kernel<<<grid_for(M * z), 256, 0, st>>>(raw, U, Hf, M, z, d, seq_out, T, t);
+  IPK_LAUNCH_CHECK();
+}
+
+__global__ void im2col3x3_small_kernel(const float* __restrict__ src, int B, int s, int C, OperandDst dst, int Kfill) {
+  long long total = (long long)B * s * s * Kfill;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    int k = (int)(e % Kfill);
+    long long m = e / Kfill;
+    float v = 0.f;
+    if (k < 9 * C) {
+      int tap = k / C, c = k - tap * C;
+      int x = (int)(m % s), y = (int)((m / s) % s);
+      long long b = m / ((long long)s * s);
+      int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+      if (yy >= 0 && yy < s && xx >= 0 && xx < s) v = src[((b * s + yy) * s + xx) * C + c];
+    }
+    store_operand(dst, m, k, v);
+  }
+}
+void im2col3x3_small(const float* src, int B, int s, int C, const OperandDst& dst, int Kfill, cudaStream_t st) {
+  im2col3x3_small_kernel<<<grid_for((long long)B * s * s * Kfill), 256, 0, st>>>(src, B, s, C, dst, Kfill);
   IPK_LAUNCH_CHECK();
 }
 

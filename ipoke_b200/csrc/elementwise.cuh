@@ -35,14 +35,27 @@ struct NormApply {
 };
 void norm_apply(const NormApply& a, cudaStream_t st);
 
-// ConvGRUCell gate math (models/modules/motion_models/rnn.py:50-54)
-// raw[M][2z] = (update_pre | reset_pre); xh[M][2z] holds (x | h); writes U[M][z] = sigmoid(update_pre) and
-// xrh[M][z + c] = sigmoid(reset_pre) * h
-void gru_gate1(const float* raw, const float* xh, float* U, float* xrh, long long M, int z, cudaStream_t st);
-// raw[M][z] = out_pre; h' = h*(1-u) + tanh(out_pre)*u; writes h' to up to four destinations (null = skip)
-struct GruDst { float* p; int cstride, coff; };
-void gru_gate2(const float* raw, const float* U, const float* xh, long long M, int z, const GruDst* dst, int ndst,
+// Destination of a conv-input operand: fp32 rows, or bf16 (hi [, lo]) planes, channels [coff, coff + C) of rows of cstride
+struct OperandDst {
+  void* p = nullptr;      // float* or bf16* (hi plane)
+  void* p_lo = nullptr;   // bf16 lo plane (OUT_BF16_SPLIT)
+  int mode = OUT_F32_NHWC;
+  int cstride = 0, coff = 0;
+};
+// dst[m][coff + c] = src[m][scoff + c]   (m < M, c < C), converted to the operand storage mode
+void operand_copy(const float* src, int scs, int scoff, const OperandDst& dst, long long M, int C, cudaStream_t st);
+
+// ConvGRUCell gate math (models/modules/motion_models/rnn.py:50-54); the hidden state lives in fp32 (Hf [M][z]) and the
+// conv inputs (x | h), (x | r*h) in the engine's operand storage.
+// raw[M][2z] = (update_pre | reset_pre): writes U[M][z] = sigmoid(update_pre) and xrh[m][coff + c] = sigmoid(reset_pre) * h
+void gru_gate1(const float* raw, const float* Hf, float* U, const OperandDst& xrh, long long M, int z, cudaStream_t st);
+// raw[M][z] = out_pre; h' = h*(1-u) + tanh(out_pre)*u; updates Hf in place and writes h' to up to three operand destinations
+void gru_gate2(const float* raw, const float* U, float* Hf, long long M, int z, const OperandDst* dst, int ndst,
                float* seq_out, int T, int t, cudaStream_t st);
+
+// 3x3 im2col of a small-channel NHWC image: dst[(b, y, x)][tap*C + c] = src[b][y+ky-1][x+kx-1][c] (zero outside, zero for
+// k >= 9*C up to Kfill), tap = ky*3 + kx.  Feeds the SPADE 3->128 conv as a one-tap GEMM.
+void im2col3x3_small(const float* src, int B, int s, int C, const OperandDst& dst, int Kfill, cudaStream_t st);
 
 // F.interpolate(mode='bilinear', align_corners=True): in [B][3][S][S] NCHW -> out [B][s][s][3] NHWC
 void bilinear_nchw_to_nhwc(const float* in, float* out, int B, int C, int S, int s, cudaStream_t st);
