@@ -45,13 +45,21 @@ struct TapList {
   int widx[MAX_TAPS] = {0};          // index of the packed weight slice used by each tap
 };
 
-// Run taps [tap_begin, tap_end) of `taps`, optionally split over gridDim.z (nsplit slices of the tap range).
-void conv_simt_run(const ConvW& w, const ConvIn& in, const ConvOut& out, const TapList& taps, int nsplit, cudaStream_t st);
-void conv_tc_run(const ConvW& w, const ConvIn& in, const ConvOut& out, const TapList& taps, int nsplit, cudaStream_t st);
+// Run all taps of `taps`.  nsplit > 1 asks for split-K into fp32 partial slices (out.split_stride apart): the SIMT engine
+// splits the tap range, the tensor-core engine the (tap, 64-wide k-block) iteration range.  Both return the number of
+// slices actually written.
+int conv_simt_run(const ConvW& w, const ConvIn& in, const ConvOut& out, const TapList& taps, int nsplit, cudaStream_t st);
+int conv_tc_run(const ConvW& w, const ConvIn& in, const ConvOut& out, const TapList& taps, int nsplit, cudaStream_t st);
 
-inline void conv_run(const ConvW& w, const ConvIn& in, const ConvOut& out, const TapList& taps, int nsplit, cudaStream_t st) {
-  if (w.engine == IPK_PREC_FP32_SIMT) conv_simt_run(w, in, out, taps, nsplit, st);
-  else conv_tc_run(w, in, out, taps, nsplit, st);
+inline int conv_run(const ConvW& w, const ConvIn& in, const ConvOut& out, const TapList& taps, int nsplit, cudaStream_t st) {
+  if (w.engine == IPK_PREC_FP32_SIMT) return conv_simt_run(w, in, out, taps, nsplit, st);
+  return conv_tc_run(w, in, out, taps, nsplit, st);
+}
+inline int conv_split_count(const ConvW& w, const TapList& taps, int nsplit) {
+  const int total = w.engine == IPK_PREC_FP32_SIMT ? taps.n : taps.n * (w.Kpad / 64);
+  nsplit = std::max(1, std::min(nsplit, total));
+  const int per = (total + nsplit - 1) / nsplit;
+  return (total + per - 1) / per;
 }
 
 // ---- packing (device kernels; sources are the reference's parameter tensors, fp32 on device) ----

@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const SimtArgs a) {
   }
 }
 
-void conv_simt_run(const ConvW& w, const ConvIn& in, const ConvOut& out, const TapList& taps, int nsplit, cudaStream_t st) {
+int conv_simt_run(const ConvW& w, const ConvIn& in, const ConvOut& out, const TapList& taps, int nsplit, cudaStream_t st) {
   IPK_CHECK(w.w_f32 != nullptr, IPK_ERR_STATE, "conv_simt_run: layer was not packed for the SIMT engine");
   SimtArgs a;
   a.in = (const float*)in.p; a.in_cstride = in.cstride; a.in_coff = in.coff; a.K = w.K;
@@ -153,7 +153,7 @@ void conv_simt_run(const ConvW& w, const ConvIn& in, const ConvOut& out, const T
   a.split_stride = out.split_stride;
   IPK_CHECK(nsplit == 1 || (out.mode == OUT_F32_NHWC && out.split_stride > 0), IPK_ERR_INVALID, "split-K needs fp32 partial slices");
   long long M = (long long)in.F * in.H * in.W;
-  if (M == 0) return;
+  if (M == 0) return 0;
   if (w.N <= 4) {
     dim3 g((unsigned)((M + 255) / 256), cdiv(w.N, 4), nsplit);
     conv_simt_kernel<256, 4, 1, 4><<<g, 256, 0, st>>>(a);
@@ -165,6 +165,7 @@ void conv_simt_run(const ConvW& w, const ConvIn& in, const ConvOut& out, const T
     conv_simt_kernel<128, 64, 8, 4><<<g, 256, 0, st>>>(a);
   }
   IPK_LAUNCH_CHECK();
+  return nsplit;
 }
 
 // ------------------------------------------------------------------------------------------ packing

@@ -30,7 +30,7 @@ struct TcArgs {
   int bw, bh, bf;                 // pixel box (bw*bh*bf == 128)
   int tiles_x, tiles_y;           // tiles along x and y
   int tiles_m, tiles_n, nsplit;   // tiles_m = tiles_x * tiles_y * tiles_f
-  int ntaps, taps_per_split, nkb; // nkb = Kpad / 64
+  int ntaps, iters_per_split, nkb; // nkb = Kpad / 64; a split covers iters_per_split consecutive (tap, k-block) iterations
   int dy[MAX_TAPS], dx[MAX_TAPS], widx[MAX_TAPS];
   int Npad, N;
   int stages;
@@ -215,10 +215,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int tf = mt / txy, r2 = mt - tf * txy;
         const int ty = r2 / a.tiles_x, tx = r2 - ty * a.tiles_x;
         const int f0 = tf * a.bf, y0 = ty * a.bh, x0 = tx * a.bw, n0 = nt * BN;
-        const int tap_begin = z * a.taps_per_split, tap_end = min(a.ntaps, tap_begin + a.taps_per_split);
-        for (int t = tap_begin; t < tap_end; ++t) {
+        const int it_begin = z * a.iters_per_split, it_end = min(a.ntaps * a.nkb, it_begin + a.iters_per_split);
+        int t = it_begin / a.nkb, kb = it_begin - t * a.nkb;
+        for (int it = it_begin; it < it_end; ++it) {
           const int dy = a.dy[t], dx = a.dx[t], wrow = a.widx[t] * a.Npad + n0;
-          for (int kb = 0; kb < a.nkb; ++kb) {
+          {
             mbar_wait(&empty_bar[s], ph ^ 1);
             uint8_t* st = smem + (size_t)s * STAGE_BYTES;
             mbar_expect_tx(&full_bar[s], STAGE_BYTES);
@@ -230,6 +231,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             }
             if (++s == stages) { s = 0; ph ^= 1; }
           }
+          if (++kb == a.nkb) { kb = 0; ++t; }
         }
       }
     }
@@ -242,8 +244,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       uint32_t aph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int z = tile / tiles_mn;
-        const int tap_begin = z * a.taps_per_split, tap_end = min(a.ntaps, tap_begin + a.taps_per_split);
-        const int iters = (tap_end - tap_begin) * a.nkb;
+        const int it_begin = z * a.iters_per_split;
+        const int iters = min(a.ntaps * a.nkb, it_begin + a.iters_per_split) - it_begin;
         mbar_wait(&tmem_empty_bar[as], aph ^ 1);      // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(as * BN);
@@ -443,7 +445,7 @@ static void launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CU
   IPK_LAUNCH_CHECK();
 }
 
-void conv_tc_run(const ConvW& w, const ConvIn& in, const ConvOut& out, const TapList& taps, int nsplit, cudaStream_t st) {
+int conv_tc_run(const ConvW& w, const ConvIn& in, const ConvOut& out, const TapList& taps, int nsplit, cudaStream_t st) {
   IPK_CHECK(w.w_hi != nullptr, IPK_ERR_STATE, "conv_tc_run: layer was not packed for the tensor-core engine");
   const bool split = w.engine == IPK_PREC_FP32_SPLIT;
   IPK_CHECK(!split || (in.p_lo && w.w_lo), IPK_ERR_STATE, "conv_tc_run: split precision needs hi and lo operand planes");
@@ -453,7 +455,7 @@ void conv_tc_run(const ConvW& w, const ConvIn& in, const ConvOut& out, const Tap
               "conv_tc_run: output row (cstride %d, coff %d) cannot hold Npad %d", out.cstride, out.coff, w.Npad);
   if (out.mode == OUT_BF16_SPLIT || out.mode == OUT_BF16) IPK_CHECK(out.cstride % 8 == 0 && out.coff % 8 == 0, IPK_ERR_UNSUPPORTED, "conv_tc_run: bf16 output rows must be 16-byte aligned");
   long long M = (long long)in.F * in.H * in.W;
-  if (M == 0) return;
+  if (M == 0) return 0;
   TcArgs a;
   a.F = in.F; a.H = in.H; a.W = in.W;
   if ((long long)in.H * in.W <= TC_BM) {
@@ -468,11 +470,12 @@ void conv_tc_run(const ConvW& w, const ConvIn& in, const ConvOut& out, const Tap
   a.tiles_x = cdiv(in.W, a.bw); a.tiles_y = cdiv(in.H, a.bh);
   const int tiles_f = cdiv(in.F, a.bf);
   a.ntaps = taps.n;
-  nsplit = std::max(1, std::min(nsplit, taps.n));
-  a.taps_per_split = cdiv(taps.n, nsplit);
-  nsplit = cdiv(taps.n, a.taps_per_split);
-  IPK_CHECK(nsplit == 1 || (out.mode == OUT_F32_NHWC && out.split_stride > 0), IPK_ERR_INVALID, "split-K needs fp32 partial slices");
   a.nkb = w.Kpad / TC_BK;
+  const int total_iters = taps.n * a.nkb;
+  nsplit = std::max(1, std::min(nsplit, total_iters));
+  a.iters_per_split = cdiv(total_iters, nsplit);
+  nsplit = cdiv(total_iters, a.iters_per_split);
+  IPK_CHECK(nsplit == 1 || (out.mode == OUT_F32_NHWC && out.split_stride > 0), IPK_ERR_INVALID, "split-K needs fp32 partial slices");
   for (int i = 0; i < MAX_TAPS; ++i) { a.dy[i] = taps.dy[i]; a.dx[i] = taps.dx[i]; a.widx[i] = taps.widx[i]; }
   a.Npad = w.Npad; a.N = w.N;
   a.bias = out.bias; a.act = out.act; a.out_mode = out.mode; a.out_cstride = out.cstride; a.out_coff = out.coff;
@@ -487,7 +490,15 @@ void conv_tc_run(const ConvW& w, const ConvIn& in, const ConvOut& out, const Tap
   const __nv_bfloat16* ahi = (const __nv_bfloat16*)in.p + in.coff;
   CUtensorMap mA_hi = make_map(ahi, 4, ad, as, ab);
   CUtensorMap mA_lo = split ? make_map((const __nv_bfloat16*)in.p_lo + in.coff, 4, ad, as, ab) : mA_hi;
-  int BN = w.Npad >= 256 ? 256 : (w.Npad > 64 ? 128 : (w.Npad > 32 ? 64 : 32));
+  // N tile: weigh padded columns (MMA work) against A-tile re-reads (one per N tile)
+  int BN = 32;
+  {
+    double best = 1e30;
+    for (int bn : {256, 128, 64, 32}) {
+      double cost = (double)cdiv(w.Npad, bn) * bn * (1.0 + 32.0 / bn);
+      if (cost < best) { best = cost; BN = bn; }
+    }
+  }
   long long wd[2] = {w.Kpad, (long long)w.ntaps * w.Npad};
   long long wsb[1] = {(long long)w.Kpad * 2};
   int wb[2] = {TC_BK, BN};
@@ -509,6 +520,7 @@ void conv_tc_run(const ConvW& w, const ConvIn& in, const ConvOut& out, const Tap
     IPK_TC_CASE(256)
   }
 #undef IPK_TC_CASE
+  return nsplit;
 }
 
 }  // namespace ipk

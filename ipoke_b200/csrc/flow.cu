@@ -19,8 +19,8 @@ namespace ipk {
 struct TensorRef { const void* p; int64_t numel; int dtype; };
 
 struct NiceLayer {
-  ConvW c1, c2, c3;
-  int n_z = 0, n_p = 0, K1pad = 0;
+  ConvW c1, c2, c3;          // c3: one GEMM producing all 9 tap responses, N = 9 * N3p (tap-major columns)
+  int n_z = 0, n_p = 0, K1pad = 0, N3p = 0, nsplit3 = 1;
   int* d_iz = nullptr;
   int* d_ip = nullptr;
   float* bias3 = nullptr;  // [2*n_p]
@@ -169,11 +169,20 @@ static int build_nice(ipk_flow* f, const std::string& p, int C, int factor, bool
   const TensorRef& b3 = need(f, p + "net.conv3.conv.bias", N3, IPK_F32);
   float* os = f->pool.alloc<float>(N3);
   weight_norm_scale((const float*)v3.p, (const float*)g3.p, os, N3, Hd * 9, st);
-  n.c3 = conv_alloc(f->pool, eng, 9, Hd, N3, false);
-  {
+  // conv3 runs as ONE 1x1 GEMM T[q][t*N3p + j] = W_t[j,:] . H2[q,:] over all pixels q (the hidden activations are read
+  // once instead of once per tap); the 3x3 gather  out[p] = sum_t T[p + delta_t][t]  happens in the affine micro-op.
+  n.N3p = round_up(N3, 4);
+  n.c3 = conv_alloc(f->pool, eng, 1, Hd, 9 * n.N3p, false);
+  for (int t = 0; t < 9; ++t) {
     PackSrc s;
     s.w = (const float*)v3.p; s.N = N3; s.Ksrc = Hd; s.kh = 3; s.kw = 3; s.oscale = os;
-    conv_pack_into(n.c3, 0, s, {0, 1, 2, 3, 4, 5, 6, 7, 8}, st);
+    conv_pack_into(n.c3, t * n.N3p, s, {t}, st);
+  }
+  {
+    // split-K so that one launch fills the machine about twice over (tensor-core engine only)
+    const int mt = cdiv(f->cfg.max_batch * 64, 128);
+    const int want = std::max(1, std::min(MAX_NSPLIT - 1, (2 * 148) / std::max(1, mt * cdiv(n.c3.Npad, 128))));
+    n.nsplit3 = conv_split_count(n.c3, taps_1x1(), want);
   }
   n.bias3 = f->pool.alloc<float>(N3);
   IPK_CUDA(cudaMemcpyAsync(n.bias3, b3.p, N3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -330,7 +339,7 @@ static std::vector<Stage> compile_program(ipk_flow* f, const std::vector<Logical
         ensure(C);
         MicroOp a;
         memset(&a, 0, sizeof(a));
-        a.kind = MK_AFFINE; a.i0 = 9; a.i1 = n.c3.Npad; a.i2 = n.n_p; a.p1 = n.bias3; a.idx = n.d_ip;   // p0 / l0 patched later
+        a.kind = MK_AFFINE; a.i0 = n.nsplit3; a.i1 = n.c3.Npad; a.i2 = n.n_p; a.i3 = n.N3p; a.p1 = n.bias3; a.idx = n.d_ip;   // p0 / l0 patched later
         cur.host_ops.push_back(a);
         break;
       }
@@ -345,7 +354,7 @@ static void upload_programs(ipk_flow* f, std::vector<Stage>& stages, cudaStream_
   for (Stage& s : stages) {
     for (MicroOp& m : s.host_ops) {
       if (m.kind == MK_IM2COL) { m.out0 = f->A1; m.out1 = f->A1_lo; }
-      if (m.kind == MK_AFFINE) { m.p0 = f->partials; m.l0 = Mmax * m.i1; }
+      if (m.kind == MK_AFFINE) { m.p0 = f->partials; m.l0 = Mmax * f->Npad3_max; }
       if (m.kind == MK_MCF) { m.p2 = f->Hterm + m.l0; m.l0 = f->hstride; }
     }
     s.d_ops = f->pool.alloc<MicroOp>(s.host_ops.size());
@@ -371,13 +380,15 @@ static void run_nice_net(ipk_flow* f, const NiceLayer& n, int B, cudaStream_t st
     ProfScope ps("flow.nice.conv2", st);
     conv_run(n.c2, in, out, taps_1x1(), 1, st);
   }
-  // conv3 (3x3 over the 8x8 grid), split over the 9 taps into partial slices; bias + affine happen in the next segment
+  // conv3: all nine tap responses in one GEMM, split-K into fp32 partial slices; bias, the 3x3 gather and the affine
+  // transform happen in the next segment
   {
-    ConvIn in; in.p = f->H2; in.p_lo = f->H2_lo; in.cstride = Hd; in.F = B; in.H = 8; in.W = 8;
-    ConvOut out; out.p = f->partials; out.mode = OUT_F32_NHWC; out.cstride = n.c3.Npad; out.Ho = 8; out.Wo = 8;
-    out.split_stride = Mmax * n.c3.Npad;
+    ConvIn in; in.p = f->H2; in.p_lo = f->H2_lo; in.cstride = Hd; in.F = M; in.H = 1; in.W = 1;
+    ConvOut out; out.p = f->partials; out.mode = OUT_F32_NHWC; out.cstride = n.c3.Npad; out.Ho = 1; out.Wo = 1;
+    out.split_stride = Mmax * f->Npad3_max;
     ProfScope ps("flow.nice.conv3", st);
-    conv_run(n.c3, in, out, taps_3x3(), 9, st);
+    const int ns = conv_run(n.c3, in, out, taps_1x1(), n.nsplit3, st);
+    IPK_CHECK(ns == n.nsplit3, IPK_ERR_STATE, "flow: conv3 split-K produced %d slices, plan expected %d", ns, n.nsplit3);
   }
 }
 
@@ -471,7 +482,7 @@ extern "C" int ipk_flow_finalize(ipk_flow* f, void* stream) {
   size_t bytes = 0;
   auto rb = [](size_t b) { return (b + 255) / 256 * 256; };
   bytes += rb(Mmax * f->C0 * 4) + rb(Mmax * f->hch * 4) + rb(Mmax * f->K1pad_max * esz) + 2 * rb(Mmax * f->Hd * esz) +
-           rb(9 * Mmax * f->Npad3_max * 4) + rb(f->cfg.max_batch * 4) + rb(Mmax * f->hch * 4) + rb(Mmax * (size_t)f->hstride * 4) + 4096;
+           rb((size_t)MAX_NSPLIT * Mmax * f->Npad3_max * 4) + rb(f->cfg.max_batch * 4) + rb(Mmax * f->hch * 4) + rb(Mmax * (size_t)f->hstride * 4) + 4096;
   f->ws.init(bytes);
   f->state = f->ws.alloc<float>(Mmax * f->C0);
   f->cond = f->ws.alloc<float>(Mmax * f->hch);
@@ -484,7 +495,7 @@ extern "C" int ipk_flow_finalize(ipk_flow* f, void* stream) {
     f->H1_lo = h1 + Mmax * f->Hd * 2;
     f->H2_lo = h2 + Mmax * f->Hd * 2;
   }
-  f->partials = f->ws.alloc<float>(9 * Mmax * f->Npad3_max);
+  f->partials = f->ws.alloc<float>((size_t)MAX_NSPLIT * Mmax * f->Npad3_max);
   f->logdet_ws = f->ws.alloc<float>(f->cfg.max_batch);
   {
     char* e = (char*)f->ws.alloc<float>(Mmax * f->hch);

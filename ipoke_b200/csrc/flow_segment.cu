@@ -423,28 +423,35 @@ __global__ void __launch_bounds__(SEG_THREADS, 1) flow_segment_kernel(const Micr
         break;
       }
       case MK_AFFINE: {
-        // finishes a NICE coupling: params = bias + sum of the split-K partial slices of conv3 (Affine.fwd / bwd)
-        const int nsplit = op.i0, Npad = op.i1, n_p = op.i2;
+        // finishes a NICE coupling: params[p] = bias + sum over taps t and split-K slices of T[p + delta_t][t]  (the 3x3
+        // gather of conv3 with zero padding), then Affine.fwd / bwd on the transformed channels
+        const int nsplit = op.i0, Npad = op.i1, n_p = op.i2, N3p = op.i3;
         for (int i = tid; i < 64 * n_p; i += SEG_THREADS) {
-          int p = i / n_p, j = i % n_p;
-          size_t row = ((size_t)b * 64 + p) * Npad;
-          float pm[MAX_NSPLIT], pl[MAX_NSPLIT];
-#pragma unroll
-          for (int s = 0; s < MAX_NSPLIT; ++s) {       // all loads in flight together
-            pm[s] = s < nsplit ? op.p0[(size_t)s * op.l0 + row + j] : 0.f;
-            pl[s] = s < nsplit ? op.p0[(size_t)s * op.l0 + row + n_p + j] : 0.f;
-          }
+          const int p = i / n_p, j = i - p * n_p;
+          const int y = p >> 3, x = p & 7;
           float mu = __ldg(op.p1 + j), ls = __ldg(op.p1 + n_p + j);
+          for (int s = 0; s < nsplit; ++s) {
+            const float* T = op.p0 + (size_t)s * op.l0 + (size_t)b * 64 * Npad;
+            float pm[9], pl[9];
 #pragma unroll
-          for (int s = 0; s < MAX_NSPLIT; ++s) { mu += pm[s]; ls += pl[s]; }
+            for (int t = 0; t < 9; ++t) {           // nine independent loads in flight
+              const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+              const bool ok = yy >= 0 && yy < 8 && xx >= 0 && xx < 8;
+              const float* r = T + (size_t)(ok ? yy * 8 + xx : 0) * Npad + t * N3p;
+              pm[t] = ok ? r[j] : 0.f;
+              pl[t] = ok ? r[n_p + j] : 0.f;
+            }
+#pragma unroll
+            for (int t = 0; t < 9; ++t) { mu += pm[t]; ls += pl[t]; }
+          }
           float sc = 1.0f + tanhf(0.5f * ls);
           int c = op.idx[j];
-          float x = sm.s[p * Cs + c];
+          float xv = sm.s[p * Cs + c];
           if (FWD) {
-            sm.s[p * Cs + c] = sc * x + mu;
+            sm.s[p * Cs + c] = sc * xv + mu;
             ld += logf(sc);
           } else {
-            sm.s[p * Cs + c] = (x - mu) / (sc + 1e-12f);
+            sm.s[p * Cs + c] = (xv - mu) / (sc + 1e-12f);
           }
         }
         __syncthreads();

@@ -28,8 +28,9 @@ struct MicroOp {
                 p0 = Wc [6][Cp/4][hid][4], p1 = W1x [hid/4][2C][4],
                 p2 = conditioning term of this MCF: column block of the precomputed matrix
                      Hterm[M = B*64][l0] = b + W1h * ELU(cond)  (round_up(2C, 4) columns, 16-byte aligned), l0 = row stride
-   MK_AFFINE  : i0 = nsplit, i1 = Npad (row length of params), i2 = n_p, p0 = params partials [nsplit][M][Npad],
-                p1 = bias [2*n_p], idx = state channel of each transformed element, l0 = split stride (elements)
+   MK_AFFINE  : i0 = nsplit, i1 = Npad (row length of the tap-response matrix), i2 = n_p, i3 = N3p (columns per tap),
+                p0 = split-K partial slices T[nsplit][M][Npad] with T[q][t*N3p + j] = response of tap t at pixel q,
+                p1 = bias [2*n_p], idx = state channel of each transformed element, l0 = slice stride (elements)
    MK_IM2COL  : i0 = n_z, i1 = K1pad, i2 = out mode (OUT_F32_NHWC / OUT_BF16_SPLIT / OUT_BF16), idx = state channels of z,
                 out0 / out1 = A1 [M][K1pad] (hi / lo)
 */
@@ -41,7 +42,7 @@ struct SegmentLaunch {
   bool has_mcf;
 };
 
-constexpr int MAX_NSPLIT = 9;   // split-K slices of a NICE conv3 (one per tap)
+constexpr int MAX_NSPLIT = 9;   // upper bound on the split-K slices of a NICE conv3
 
 // state: [B][64][C0] fp32 NHWC (in place); logdet: [B] (forward only, accumulated)
 void flow_segment_run(const SegmentLaunch& s, bool forward, float* state, int C0, float* logdet, int B, cudaStream_t st);
