@@ -205,12 +205,21 @@ static const McfPacked& build_mcf(ipk_flow* f, const std::string& p, int C, int 
   const TensorRef& v = need(f, p + "net.conv1x1.conv.weight_v", (int64_t)C2 * row, IPK_F32);
   const TensorRef& g = need(f, p + "net.conv1x1.conv.weight_g", C2, IPK_F32);
   const TensorRef& b = need(f, p + "net.conv1x1.conv.bias", C2, IPK_F32);
-  m.Wc = f->pool.alloc<float>((size_t)6 * m.Cp * m.hid);
-  pack_mcf_shift((const float*)ws.p, m.Wc, m.hid, C, m.Cp, kh, kw, order, st);
   float* os = f->pool.alloc<float>(C2);
   weight_norm_scale((const float*)v.p, (const float*)g.p, os, C2, row, st);
-  m.W1x = f->pool.alloc<float>((size_t)m.hid * C2);
-  pack_rows4((const float*)v.p, os, m.W1x, C2, row, 0, m.hid, st);
+  if (f->cfg.precision != IPK_PREC_FP32_SIMT && C <= MCF_MMA_MAXC) {
+    // tensor-core precisions: mma.sync bf16x3 fragments (flow_segment.cu: mcf_mma)
+    uint32_t* wa = f->pool.alloc<uint32_t>(mcf_mma_conv_words(C));
+    uint32_t* w1 = f->pool.alloc<uint32_t>(mcf_mma_1x1_words(C));
+    pack_mcf_mma((const float*)ws.p, (const float*)v.p, os, wa, w1, m.hid, C, kh, kw, order, row, st);
+    m.Wc = (float*)wa;
+    m.W1x = (float*)w1;
+  } else {
+    m.Wc = f->pool.alloc<float>((size_t)6 * m.Cp * m.hid);
+    pack_mcf_shift((const float*)ws.p, m.Wc, m.hid, C, m.Cp, kh, kw, order, st);
+    m.W1x = f->pool.alloc<float>((size_t)m.hid * C2);
+    pack_rows4((const float*)v.p, os, m.W1x, C2, row, 0, m.hid, st);
+  }
   // the x-independent part of the 1x1 (columns hid.. of weight_v, macow_utils.py:429-432) goes into the shared Hterm GEMM
   m.hcol = f->hterm_cols;
   f->hterm_cols += round_up(C2, 4);
@@ -410,7 +419,7 @@ static void run_hterm(ipk_flow* f, int B, cudaStream_t st) {
 static void run_program(ipk_flow* f, std::vector<Stage>& stages, bool fwd, int B, cudaStream_t st) {
   run_hterm(f, B, st);
   for (Stage& s : stages) {
-    SegmentLaunch sl{s.d_ops, (int)s.host_ops.size(), s.C, s.has_mcf};
+    SegmentLaunch sl{s.d_ops, (int)s.host_ops.size(), s.C, s.has_mcf, f->cfg.precision != IPK_PREC_FP32_SIMT};
     {
       ProfScope ps(s.has_mcf ? "flow.segment.mcf" : "flow.segment.light", st);
       flow_segment_run(sl, fwd, f->state, f->C0, f->logdet_ws, B, st);

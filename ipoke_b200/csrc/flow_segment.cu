@@ -14,7 +14,15 @@
 //     (precomputed for all MCFs by one GEMM, flow.cu) is prefetched one MCF ahead with cp.async into a double buffer.
 //     A line then costs four phases: conv partials (2 tap rows on the two thread halves) -> combine + ELU ->
 //     1x1 partials (K split four ways) -> reduce + affine transform.
+//   * C <= 32 on the tensor-core precisions ("mma"): the two contractions of a line run on mma.sync.m16n8k16 bf16 with the
+//     bf16x3 error-compensated split (hi*hi + lo*hi + hi*lo, fp32 accumulate) -- hidden units / outputs on the M axis, the 8
+//     positions of the line on the N axis, so nothing is padded.  Weight fragments live in registers for the 8 lines of an
+//     MCF (prefetched like above); the last two finished lines are kept as bf16 hi/lo rows with a zero halo in a 3-row
+//     ring, so the shifted-conv operand is read straight from shared memory.  A line is two phases: conv + ELU, then
+//     1x1 + conditioning term + affine transform entirely in the accumulator registers (mu and log-scale of a channel sit
+//     in rows g and g+8 of the same m-tile).
 //   * C > 32 (generic): weights streamed from L2 every line.
+#include <type_traits>
 #include "flow_segment.cuh"
 
 namespace ipk {
@@ -30,13 +38,19 @@ struct SegSmem {
   float* act;     // [8][hidS] ELU(hidden) of the current line
   float* p1;      // fast: [4][8][64] 1x1 partials        generic: [8][C2s] params of the line
   float* red;     // [32]
+  __nv_bfloat16* ring;   // mma: [2 planes][3 lines][10 positions (zero halo at 0 and 9)][XS]
+  __nv_bfloat16* actb;   // mma: [2 planes][8 positions][HS] ELU(hidden) of the current line
 };
 
 __host__ __device__ inline int seg_hidmax(int C) { return C <= 96 ? 4 * C : (2 * C < 512 ? 2 * C : 512); }
 
-struct SegOffsets { size_t tmp, hterm, pc, act, p1, red, total; };
+struct SegOffsets { size_t tmp, hterm, pc, act, p1, red, ring, actb, total; };
 
-__host__ __device__ inline SegOffsets seg_layout(int C, bool has_mcf) {
+// mma-path geometry: channels padded to 16 per k-tile, rows padded by 8 bf16 so fragment loads are bank-conflict free
+__host__ __device__ inline int mma_xs(int C) { return (C + 15) / 16 * 16 + 8; }          // bf16 per ring position
+__host__ __device__ inline int mma_hs(int C) { return (4 * C + 15) / 16 * 16 + 8; }      // bf16 per act position
+
+__host__ __device__ inline SegOffsets seg_layout(int C, bool has_mcf, bool mma) {
   const int Cs = (C + 3) / 4 * 4;
   const int C2s = (2 * C + 3) / 4 * 4;
   const bool fast = C <= FAST_MAXC;
@@ -48,13 +62,15 @@ __host__ __device__ inline SegOffsets seg_layout(int C, bool has_mcf) {
   o.act = off; off += has_mcf ? (size_t)8 * ((seg_hidmax(C) + 3) / 4 * 4) : 0;
   o.p1 = off; off += has_mcf ? (fast ? (size_t)4 * 8 * 64 : (size_t)8 * C2s) : 0;
   o.red = off; off += 32;
+  const bool use_mma = has_mcf && fast && mma;
+  o.ring = off; off += use_mma ? (size_t)(2 * 3 * 10 * mma_xs(C)) / 2 : 0;      // bf16 pairs counted in floats
+  o.actb = off; off += use_mma ? (size_t)(2 * 8 * mma_hs(C)) / 2 : 0;
   o.total = off;
   return o;
 }
 
-size_t flow_segment_smem_bytes(int C, int h_ch, bool has_mcf) {
-  (void)h_ch;
-  return seg_layout(C, has_mcf).total * sizeof(float);
+size_t flow_segment_smem_bytes(int C, bool has_mcf, bool mma) {
+  return seg_layout(C, has_mcf, mma).total * sizeof(float);
 }
 
 __device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) {
@@ -223,6 +239,169 @@ __device__ __forceinline__ void mcf_fast(const MicroOp& op, const MicroOp* next,
   }
 }
 
+// ---------------------------------------------------------------------------------------------- mma MCF (C <= 32)
+struct McfMmaRegs {
+  uint4 wa_hi[12], wa_lo[12];   // conv A fragments of m-tile = warp, k-tile kt = (tap row r, dv, channel tile)
+  uint4 w1_hi[8], w1_lo[8];     // 1x1 A fragments of m-tile = warp (rows g: mu of channel 8*mt+g, rows g+8: its log-scale)
+};
+
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint4& a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
+}
+
+// packed fragment arrays: [m-tile][k-tile][lane] uint4, hi plane then lo plane
+__device__ __forceinline__ void mma_load_wa(const MicroOp& op, McfMmaRegs& r) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C = op.i1, hid = op.i3;
+  const int nmt = (hid + 15) >> 4, nct = (C + 15) >> 4, nkt = 6 * nct;
+  const uint4* W = (const uint4*)op.p0;
+  const size_t plane = (size_t)nmt * nkt * 32;
+  // register slot (tap, ct) = tap*2 + ct holds packed k-tile tap*nct + ct  (tap = tap row * 3 + dv)
+#pragma unroll
+  for (int tap = 0; tap < 6; ++tap)
+#pragma unroll
+    for (int ct = 0; ct < 2; ++ct) {
+      if (warp < nmt && ct < nct) {
+        const size_t i = ((size_t)warp * nkt + tap * nct + ct) * 32 + lane;
+        r.wa_hi[tap * 2 + ct] = __ldg(W + i);
+        r.wa_lo[tap * 2 + ct] = __ldg(W + plane + i);
+      }
+    }
+}
+__device__ __forceinline__ void mma_load_w1(const MicroOp& op, McfMmaRegs& r) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C = op.i1, hid = op.i3;
+  const int nmt1 = (C + 7) >> 3, nkt1 = (hid + 15) >> 4;
+  const uint4* W = (const uint4*)op.p1;
+  const size_t plane = (size_t)nmt1 * nkt1 * 32;
+#pragma unroll
+  for (int kt = 0; kt < 8; ++kt) {
+    if (warp < nmt1 && kt < nkt1) {
+      r.w1_hi[kt] = __ldg(W + ((size_t)warp * nkt1 + kt) * 32 + lane);
+      r.w1_lo[kt] = __ldg(W + plane + ((size_t)warp * nkt1 + kt) * 32 + lane);
+    }
+  }
+}
+
+template <bool FWD>
+__device__ __forceinline__ void mcf_mma(const MicroOp& op, const MicroOp* next, McfMmaRegs& r, const SegSmem& sm, const float* hterm,
+                                        int Cs, float& ld) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int order = op.i0, C = op.i1, hid = op.i3;
+  const int nct = (C + 15) >> 4;
+  const int nmt = (hid + 15) >> 4, nkt1 = nmt, nmt1 = (C + 7) >> 3;
+  const int XS = mma_xs(C), HS = mma_hs(C);
+  const int C2s = (2 * C + 3) / 4 * 4;
+  const int ring_plane = 3 * 10 * XS, act_plane = 8 * HS;
+
+  if (FWD) {  // snapshot x: all lines are computed from the un-transformed input (macow2.py:113-116)
+    for (int i = tid; i < 64 * Cs; i += SEG_THREADS) sm.tmp[i] = sm.s[i];
+    __syncthreads();
+  }
+
+  int slot2 = 1, slot1 = 2, slot0 = 0;   // ring slots of lines u-2, u-1, u
+  for (int u = 0; u < 8; ++u) {
+    if (u > 0) {   // line 0 sees only zero padding: hidden = 0, ELU(0) = 0, params = conditioning term
+      // ---- phase A: hidden^T[n][pos] = sum_k Wc^T[n][k] * X^T[k][pos], k = (tap row, dv, channel); then ELU -> act (bf16 hi/lo)
+      if (warp < nmt) {
+        float d[6][4];
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) d[i][j] = 0.f;
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          const int uu = u - 2 + rr;
+          if (uu >= 0) {          // warp-uniform; earlier lines are zero padding
+            const int rowoff = ((rr == 0 ? slot2 : slot1) * 10 + g) * XS + t * 2;
+#pragma unroll
+            for (int dvi = 0; dvi < 3; ++dvi)
+#pragma unroll
+              for (int ct = 0; ct < 2; ++ct) {
+                if (ct < nct) {
+                  const int kt = (rr * 3 + dvi) * 2 + ct;
+                  const int off = rowoff + dvi * XS + ct * 16;
+                  const uint32_t b0h = *(const uint32_t*)(sm.ring + off), b1h = *(const uint32_t*)(sm.ring + off + 8);
+                  const uint32_t b0l = *(const uint32_t*)(sm.ring + ring_plane + off), b1l = *(const uint32_t*)(sm.ring + ring_plane + off + 8);
+                  const int ch = (dvi & 1) * 3;
+                  mma_bf16(d[ch + 0], r.wa_hi[kt], b0h, b1h);
+                  mma_bf16(d[ch + 1], r.wa_lo[kt], b0h, b1h);
+                  mma_bf16(d[ch + 2], r.wa_hi[kt], b0l, b1l);
+                }
+              }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float h = ((d[0][j] + d[3][j]) + (d[1][j] + d[4][j])) + (d[2][j] + d[5][j]);
+          h = h > 0.f ? h : expm1f(h);
+          const int n = warp * 16 + g + (j >> 1) * 8, pos = t * 2 + (j & 1);
+          if (n < hid) {
+            const __nv_bfloat16 hi = __float2bfloat16_rn(h);
+            sm.actb[pos * HS + n] = hi;
+            sm.actb[act_plane + pos * HS + n] = __float2bfloat16_rn(h - __bfloat162float(hi));
+          }
+        }
+      }
+      __syncthreads();
+      if (u == 7 && next) mma_load_wa(*next, r);     // conv fragments are dead: fetch the next MCF's while this line finishes
+    }
+    // ---- phase C + D: params^T[o][pos] = sum_k W1x^T[o][k] * act^T[k][pos] + conditioning term; affine transform of line u
+    if (warp < nmt1) {
+      float d[6][4];
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) d[i][j] = 0.f;
+      if (u > 0) {
+#pragma unroll
+        for (int kt = 0; kt < 8; ++kt) {
+          if (kt < nkt1) {
+            const int off = g * HS + kt * 16 + t * 2;
+            const uint32_t b0h = *(const uint32_t*)(sm.actb + off), b1h = *(const uint32_t*)(sm.actb + off + 8);
+            const uint32_t b0l = *(const uint32_t*)(sm.actb + act_plane + off), b1l = *(const uint32_t*)(sm.actb + act_plane + off + 8);
+            const int ch = (kt & 1) * 3;
+            mma_bf16(d[ch + 0], r.w1_hi[kt], b0h, b1h);
+            mma_bf16(d[ch + 1], r.w1_lo[kt], b0h, b1h);
+            mma_bf16(d[ch + 2], r.w1_hi[kt], b0l, b1l);
+          }
+        }
+      }
+      const int c = warp * 8 + g;
+      if (c < C) {
+#pragma unroll
+        for (int jp = 0; jp < 2; ++jp) {
+          const int pos = t * 2 + jp;
+          const int pix = mcf_pix(order, u, pos);
+          const float mu = ((d[0][jp] + d[3][jp]) + (d[1][jp] + d[4][jp])) + (d[2][jp] + d[5][jp]) + hterm[pix * C2s + c];
+          const float ls = ((d[0][2 + jp] + d[3][2 + jp]) + (d[1][2 + jp] + d[4][2 + jp])) + (d[2][2 + jp] + d[5][2 + jp]) + hterm[pix * C2s + C + c];
+          const float sc = 1.0f + tanhf(0.5f * ls);
+          float xin;       // value of this element in the un-transformed domain: conv input of the following lines
+          if (FWD) {
+            xin = sm.tmp[pix * Cs + c];
+            sm.s[pix * Cs + c] = sc * xin + mu;
+            ld += logf(sc);
+          } else {
+            xin = (sm.s[pix * Cs + c] - mu) / (sc + 1e-12f);
+            sm.s[pix * Cs + c] = xin;
+          }
+          const int ro = (slot0 * 10 + pos + 1) * XS + c;
+          const __nv_bfloat16 hi = __float2bfloat16_rn(xin);
+          sm.ring[ro] = hi;
+          sm.ring[ring_plane + ro] = __float2bfloat16_rn(xin - __bfloat162float(hi));
+        }
+      }
+    }
+    if (u == 7 && next) mma_load_w1(*next, r);
+    __syncthreads();
+    { const int tmp = slot2; slot2 = slot1; slot1 = slot0; slot0 = tmp; }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- generic MCF (C > 32)
 template <bool FWD>
 __device__ void mcf_generic(const MicroOp& op, const SegSmem& sm, int Cs, int b, float& ld) {
@@ -332,7 +511,7 @@ __device__ __forceinline__ int next_mcf(const MicroOp* __restrict__ ops, int fro
   return -1;
 }
 
-template <bool FWD>
+template <bool FWD, bool MMA>
 __global__ void __launch_bounds__(SEG_THREADS, 1) flow_segment_kernel(const MicroOp* __restrict__ ops, int nops, int C, int has_mcf,
                                                                        float* __restrict__ state, int C0,
                                                                        float* __restrict__ logdet) {
@@ -343,12 +522,13 @@ __global__ void __launch_bounds__(SEG_THREADS, 1) flow_segment_kernel(const Micr
   const int C2s = (2 * C + 3) / 4 * 4;
   const bool fast = C <= FAST_MAXC;
   SegSmem sm;
-  const SegOffsets lo = seg_layout(C, has_mcf != 0);
+  const SegOffsets lo = seg_layout(C, has_mcf != 0, MMA);
   sm.s = smem; sm.tmp = smem + lo.tmp; sm.hterm = smem + lo.hterm; sm.pc = smem + lo.pc; sm.act = smem + lo.act;
   sm.p1 = smem + lo.p1; sm.red = smem + lo.red;
+  sm.ring = (__nv_bfloat16*)(smem + lo.ring); sm.actb = (__nv_bfloat16*)(smem + lo.actb);
 
   // first MCF of the segment: start fetching its weights / conditioning term before anything else
-  McfRegs regs;
+  typename std::conditional<MMA, McfMmaRegs, McfRegs>::type regs;
   int hbuf = 0;
   MicroOp nxt;
   int nxt_i = (has_mcf && fast) ? next_mcf(ops, 0, nops) : -1;
@@ -356,15 +536,24 @@ __global__ void __launch_bounds__(SEG_THREADS, 1) flow_segment_kernel(const Micr
     nxt = ops[nxt_i];
     mcf_prefetch_hterm(nxt, b, sm.hterm);
     cp_async_commit();
-    mcf_load_wc(nxt, regs);
-    mcf_load_w1(nxt, regs);
+    if constexpr (MMA) {
+      mma_load_wa(nxt, regs);
+      mma_load_w1(nxt, regs);
+      // zero the operand ring (halo positions and channel padding stay zero for the whole segment) and the act rows
+      uint32_t* z = (uint32_t*)sm.ring;
+      const int nz = (int)(lo.total - lo.ring);
+      for (int i = tid; i < nz; i += SEG_THREADS) z[i] = 0u;
+    } else {
+      mcf_load_wc(nxt, regs);
+      mcf_load_w1(nxt, regs);
+    }
   }
 
+  const int warp = tid >> 5, lane = tid & 31;
   float* gs = state + (size_t)b * 64 * C0;
-  for (int i = tid; i < 64 * Cs; i += SEG_THREADS) {
-    int p = i / Cs, c = i % Cs;
-    sm.s[i] = c < C ? gs[p * C0 + c] : 0.f;
-  }
+  // (pixel by warp, channel by lane) loops everywhere below: no integer divisions on the latency chain
+  for (int p = warp; p < 64; p += SEG_THREADS / 32)
+    for (int c = lane; c < Cs; c += 32) sm.s[p * Cs + c] = c < C ? gs[p * C0 + c] : 0.f;
   __syncthreads();
 
   float ld = 0.f;
@@ -373,15 +562,17 @@ __global__ void __launch_bounds__(SEG_THREADS, 1) flow_segment_kernel(const Micr
     switch (op.kind) {
       case MK_ACTNORM: {
         const int coff = op.i0, cnt = op.i1;
-        for (int i = tid; i < 64 * cnt; i += SEG_THREADS) {
-          int p = i / cnt, c = i % cnt;
-          float ls = __ldg(op.p0 + c), bb = __ldg(op.p1 + c);
-          float x = sm.s[p * Cs + coff + c];
-          if (FWD) {
-            sm.s[p * Cs + coff + c] = x * expf(ls) + bb;
-            ld += ls;   // H*W*sum(log_scale): one contribution per (pixel, channel)
-          } else {
-            sm.s[p * Cs + coff + c] = (x - bb) / (expf(ls) + 1e-8f);
+        for (int c = lane; c < cnt; c += 32) {
+          const float ls = __ldg(op.p0 + c), bb = __ldg(op.p1 + c);
+          const float e = expf(ls);
+          for (int p = warp; p < 64; p += SEG_THREADS / 32) {
+            const float x = sm.s[p * Cs + coff + c];
+            if (FWD) {
+              sm.s[p * Cs + coff + c] = x * e + bb;
+              ld += ls;   // H*W*sum(log_scale): one contribution per (pixel, channel)
+            } else {
+              sm.s[p * Cs + coff + c] = (x - bb) / (e + 1e-8f);
+            }
           }
         }
         __syncthreads();
@@ -389,15 +580,13 @@ __global__ void __launch_bounds__(SEG_THREADS, 1) flow_segment_kernel(const Micr
       }
       case MK_SHUFFLE: {
         const int Cn = op.i0;
-        for (int i = tid; i < 64 * Cn; i += SEG_THREADS) {
-          int p = i / Cn, c = i % Cn;
-          sm.tmp[p * Cs + c] = sm.s[p * Cs + op.idx[c]];
+        for (int c = lane; c < Cn; c += 32) {
+          const int src = op.idx[c];
+          for (int p = warp; p < 64; p += SEG_THREADS / 32) sm.tmp[p * Cs + c] = sm.s[p * Cs + src];
         }
         __syncthreads();
-        for (int i = tid; i < 64 * Cn; i += SEG_THREADS) {
-          int p = i / Cn, c = i % Cn;
-          sm.s[p * Cs + c] = sm.tmp[p * Cs + c];
-        }
+        for (int c = lane; c < Cn; c += 32)
+          for (int p = warp; p < 64; p += SEG_THREADS / 32) sm.s[p * Cs + c] = sm.tmp[p * Cs + c];
         __syncthreads();
         break;
       }
@@ -415,7 +604,8 @@ __global__ void __launch_bounds__(SEG_THREADS, 1) flow_segment_kernel(const Micr
             cp_async_wait0();
           }
           __syncthreads();
-          mcf_fast<FWD>(op, nn >= 0 ? &nxt : nullptr, regs, sm, sm.hterm + hbuf * 64 * C2s, Cs, ld);
+          if constexpr (MMA) mcf_mma<FWD>(op, nn >= 0 ? &nxt : nullptr, regs, sm, sm.hterm + hbuf * 64 * C2s, Cs, ld);
+          else mcf_fast<FWD>(op, nn >= 0 ? &nxt : nullptr, regs, sm, sm.hterm + hbuf * 64 * C2s, Cs, ld);
           hbuf ^= 1;
         } else {
           mcf_generic<FWD>(op, sm, Cs, b, ld);
@@ -424,60 +614,85 @@ __global__ void __launch_bounds__(SEG_THREADS, 1) flow_segment_kernel(const Micr
       }
       case MK_AFFINE: {
         // finishes a NICE coupling: params[p] = bias + sum over taps t and split-K slices of T[p + delta_t][t]  (the 3x3
-        // gather of conv3 with zero padding), then Affine.fwd / bwd on the transformed channels
+        // gather of conv3 with zero padding), then Affine.fwd / bwd on the transformed channels.
+        // Step 1 (lane = parameter index e: mu of element e, or log-scale of element e - n_p): a warp reads 2*n_p contiguous
+        // floats per (pixel, tap, slice); two pixels x nine taps of loads are in flight per lane.  Step 2 (lane = element).
         const int nsplit = op.i0, Npad = op.i1, n_p = op.i2, N3p = op.i3;
-        for (int i = tid; i < 64 * n_p; i += SEG_THREADS) {
-          const int p = i / n_p, j = i - p * n_p;
-          const int y = p >> 3, x = p & 7;
-          float mu = __ldg(op.p1 + j), ls = __ldg(op.p1 + n_p + j);
-          for (int s = 0; s < nsplit; ++s) {
-            const float* T = op.p0 + (size_t)s * op.l0 + (size_t)b * 64 * Npad;
-            float pm[9], pl[9];
+        const float* Tb = op.p0 + (size_t)b * 64 * Npad;
+        constexpr int NW = SEG_THREADS / 32;
+        for (int e = lane; e < 2 * n_p; e += 32) {
+          const float bias = __ldg(op.p1 + e);
+#pragma unroll 1
+          for (int pg = 0; pg < 64 / NW; pg += 2) {
+            float v[2];
 #pragma unroll
-            for (int t = 0; t < 9; ++t) {           // nine independent loads in flight
-              const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
-              const bool ok = yy >= 0 && yy < 8 && xx >= 0 && xx < 8;
-              const float* r = T + (size_t)(ok ? yy * 8 + xx : 0) * Npad + t * N3p;
-              pm[t] = ok ? r[j] : 0.f;
-              pl[t] = ok ? r[n_p + j] : 0.f;
+            for (int q = 0; q < 2; ++q) v[q] = bias;
+            for (int sidx = 0; sidx < nsplit; ++sidx) {
+              const float* T = Tb + (size_t)sidx * op.l0 + e;
+              float pv[2][9];
+#pragma unroll
+              for (int q = 0; q < 2; ++q) {
+                const int pp = warp + (pg + q) * NW;
+                const int y = pp >> 3, x = pp & 7;
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                  const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+                  const bool ok = yy >= 0 && yy < 8 && xx >= 0 && xx < 8;
+                  pv[q][t] = ok ? T[(size_t)(yy * 8 + xx) * Npad + t * N3p] : 0.f;
+                }
+              }
+#pragma unroll
+              for (int q = 0; q < 2; ++q)
+#pragma unroll
+                for (int t = 0; t < 9; ++t) v[q] += pv[q][t];
             }
 #pragma unroll
-            for (int t = 0; t < 9; ++t) { mu += pm[t]; ls += pl[t]; }
+            for (int q = 0; q < 2; ++q) sm.tmp[(warp + (pg + q) * NW) * Cs + e] = v[q];
           }
-          float sc = 1.0f + tanhf(0.5f * ls);
-          int c = op.idx[j];
-          float xv = sm.s[p * Cs + c];
-          if (FWD) {
-            sm.s[p * Cs + c] = sc * xv + mu;
-            ld += logf(sc);
-          } else {
-            sm.s[p * Cs + c] = (xv - mu) / (sc + 1e-12f);
+        }
+        __syncwarp();
+        for (int j = lane; j < n_p; j += 32) {
+          const int c = op.idx[j];
+          for (int pp = warp; pp < 64; pp += NW) {
+            const float mu = sm.tmp[pp * Cs + j], ls = sm.tmp[pp * Cs + n_p + j];
+            const float sc = 1.0f + tanhf(0.5f * ls);
+            const float xv = sm.s[pp * Cs + c];
+            if (FWD) {
+              sm.s[pp * Cs + c] = sc * xv + mu;
+              ld += logf(sc);
+            } else {
+              sm.s[pp * Cs + c] = (xv - mu) / (sc + 1e-12f);
+            }
           }
         }
         __syncthreads();
         break;
       }
       case MK_IM2COL: {
+        // operand rows of the next coupling's conv1: A1[b*64 + p][k = tap*n_z + j] = z-part of the state at pixel p + delta_tap
         const int n_z = op.i0, K1 = op.i1, mode = op.i2;
         const int kv = 9 * n_z;
-        for (int i = tid; i < 64 * K1; i += SEG_THREADS) {
-          int p = i / K1, k = i % K1;
-          float v = 0.f;
-          if (k < kv) {
-            int t = k / n_z, j = k % n_z;
-            int yy = (p >> 3) + t / 3 - 1, xx = (p & 7) + t % 3 - 1;
-            if (yy >= 0 && yy < 8 && xx >= 0 && xx < 8) v = sm.s[(yy * 8 + xx) * Cs + op.idx[j]];
-          }
-          size_t di = ((size_t)b * 64 + p) * K1 + k;
-          if (mode == OUT_F32_NHWC) {
-            ((float*)op.out0)[di] = v;
-          } else if (mode == OUT_BF16_SPLIT) {
-            __nv_bfloat16 hi, lo;
-            split_bf16(v, hi, lo);
-            ((__nv_bfloat16*)op.out0)[di] = hi;
-            ((__nv_bfloat16*)op.out1)[di] = lo;
-          } else {
-            ((__nv_bfloat16*)op.out0)[di] = __float2bfloat16_rn(v);
+        constexpr int NW = SEG_THREADS / 32;
+        for (int k = lane; k < K1; k += 32) {
+          const bool kvalid = k < kv;
+          const int t = kvalid ? k / n_z : 0;
+          const int ch = kvalid ? op.idx[k - t * n_z] : 0;
+          const int dy = t / 3 - 1, dx = t % 3 - 1;
+          for (int pp = warp; pp < 64; pp += NW) {
+            const int yy = (pp >> 3) + dy, xx = (pp & 7) + dx;
+            float v = 0.f;
+            if (kvalid && yy >= 0 && yy < 8 && xx >= 0 && xx < 8) v = sm.s[(yy * 8 + xx) * Cs + ch];
+            const size_t di = ((size_t)b * 64 + pp) * K1 + k;
+            if (mode == OUT_F32_NHWC) {
+              ((float*)op.out0)[di] = v;
+            } else if (mode == OUT_BF16_SPLIT) {
+              __nv_bfloat16 hi, lo;
+              split_bf16(v, hi, lo);
+              ((__nv_bfloat16*)op.out0)[di] = hi;
+              ((__nv_bfloat16*)op.out1)[di] = lo;
+            } else {
+              ((__nv_bfloat16*)op.out0)[di] = __float2bfloat16_rn(v);
+            }
           }
         }
         __syncthreads();
@@ -487,10 +702,8 @@ __global__ void __launch_bounds__(SEG_THREADS, 1) flow_segment_kernel(const Micr
     }
   }
   __syncthreads();
-  for (int i = tid; i < 64 * C; i += SEG_THREADS) {
-    int p = i / C, c = i % C;
-    gs[p * C0 + c] = sm.s[p * Cs + c];
-  }
+  for (int p = warp; p < 64; p += SEG_THREADS / 32)
+    for (int c = lane; c < C; c += 32) gs[p * C0 + c] = sm.s[p * Cs + c];
   if (FWD) {
     // block reduction of the log-det contributions (warp shuffles + one smem pass)
 #pragma unroll
@@ -507,18 +720,93 @@ __global__ void __launch_bounds__(SEG_THREADS, 1) flow_segment_kernel(const Micr
 }
 
 void flow_segment_init() {
-  IPK_CUDA(cudaFuncSetAttribute(flow_segment_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  IPK_CUDA(cudaFuncSetAttribute(flow_segment_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  IPK_CUDA(cudaFuncSetAttribute(flow_segment_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  IPK_CUDA(cudaFuncSetAttribute(flow_segment_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  IPK_CUDA(cudaFuncSetAttribute(flow_segment_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  IPK_CUDA(cudaFuncSetAttribute(flow_segment_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 }
 
 void flow_segment_run(const SegmentLaunch& s, bool forward, float* state, int C0, float* logdet, int B, cudaStream_t st) {
   if (s.nops == 0 || B == 0) return;
-  size_t smem = flow_segment_smem_bytes(s.C, 0, s.has_mcf);
+  const bool mma = s.mma && s.has_mcf && s.C <= FAST_MAXC;
+  size_t smem = flow_segment_smem_bytes(s.C, s.has_mcf, mma);
   IPK_CHECK(smem <= 200 * 1024, IPK_ERR_UNSUPPORTED, "flow segment needs %zu bytes of shared memory (C=%d)", smem, s.C);
-  if (forward)
-    flow_segment_kernel<true><<<B, SEG_THREADS, smem, st>>>(s.ops, s.nops, s.C, s.has_mcf ? 1 : 0, state, C0, logdet);
-  else
-    flow_segment_kernel<false><<<B, SEG_THREADS, smem, st>>>(s.ops, s.nops, s.C, s.has_mcf ? 1 : 0, state, C0, logdet);
+  const int hm = s.has_mcf ? 1 : 0;
+  if (forward) {
+    if (mma) flow_segment_kernel<true, true><<<B, SEG_THREADS, smem, st>>>(s.ops, s.nops, s.C, hm, state, C0, logdet);
+    else flow_segment_kernel<true, false><<<B, SEG_THREADS, smem, st>>>(s.ops, s.nops, s.C, hm, state, C0, logdet);
+  } else {
+    if (mma) flow_segment_kernel<false, true><<<B, SEG_THREADS, smem, st>>>(s.ops, s.nops, s.C, hm, state, C0, logdet);
+    else flow_segment_kernel<false, false><<<B, SEG_THREADS, smem, st>>>(s.ops, s.nops, s.C, hm, state, C0, logdet);
+  }
+  IPK_LAUNCH_CHECK();
+}
+
+// ---------------------------------------------------------------------------------------------- mma fragment packing
+// A fragment of mma.m16n8k16 (row-major 16x16 bf16): lane (g = lane/4, t = lane%4) holds a0 = (row g, k 2t..2t+1),
+// a1 = (row g+8, same k), a2 = (row g, k 2t+8..2t+9), a3 = (row g+8, k 2t+8..2t+9); low half = lower k.
+__device__ __forceinline__ void pack_pair(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+  const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
+  hi = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+  lo = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+}
+
+// shifted-conv weights w[hid][C][kh][kw] -> fragments [m-tile][k-tile][lane][4] (hi plane, then lo plane);
+// k-tile kt = (tap row r in {u-2, u-1}, dv in {-1,0,1}, channel tile ct), element kk -> channel ct*16 + kk
+__global__ void pack_mcf_mma_conv_kernel(const float* __restrict__ w, uint32_t* __restrict__ dst, int hid, int C, int kh, int kw, int order) {
+  const int nct = (C + 15) / 16, nkt = 6 * nct, nmt = (hid + 15) / 16;
+  const int total = nmt * nkt * 32 * 4;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int j = e & 3, lane = (e >> 2) & 31, kt = (e >> 7) % nkt, mt = (e >> 7) / nkt;
+    const int g = lane >> 2, t = lane & 3;
+    const int n = mt * 16 + g + (j & 1) * 8;
+    const int kk = t * 2 + (j >> 1) * 8;
+    const int rr = kt / (3 * nct), rem = kt - rr * 3 * nct, dvi = rem / nct, ct = rem - dvi * nct;
+    int ky, kx;
+    switch (order) {
+      case 0: ky = rr; kx = dvi; break;          // A (2x3)
+      case 1: ky = 1 - rr; kx = dvi; break;      // B (2x3)
+      case 2: kx = rr; ky = dvi; break;          // C (3x2)
+      default: kx = 1 - rr; ky = dvi; break;     // D (3x2)
+    }
+    float v[2];
+    for (int q = 0; q < 2; ++q) {
+      const int c = ct * 16 + kk + q;
+      v[q] = (n < hid && c < C) ? w[(((size_t)n * C + c) * kh + ky) * kw + kx] : 0.f;
+    }
+    uint32_t hi, lo;
+    pack_pair(v[0], v[1], hi, lo);
+    dst[e] = hi;
+    dst[(size_t)total + e] = lo;
+  }
+}
+// 1x1 weights v[2C][row] (weight-norm scale os[2C]) columns [0, hid) -> fragments [m-tile][k-tile][lane][4]:
+// m-tile mt rows g -> output mt*8+g (mu of that channel), rows g+8 -> output C + mt*8+g (its log-scale)
+__global__ void pack_mcf_mma_1x1_kernel(const float* __restrict__ v, const float* __restrict__ os, uint32_t* __restrict__ dst, int hid, int C, int row) {
+  const int nmt1 = (C + 7) / 8, nkt1 = (hid + 15) / 16;
+  const int total = nmt1 * nkt1 * 32 * 4;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int j = e & 3, lane = (e >> 2) & 31, kt = (e >> 7) % nkt1, mt = (e >> 7) / nkt1;
+    const int g = lane >> 2, t = lane & 3;
+    const int c = mt * 8 + g;
+    const int o = (j & 1) ? C + c : c;
+    const int kk = kt * 16 + t * 2 + (j >> 1) * 8;
+    float x[2];
+    for (int q = 0; q < 2; ++q) x[q] = (c < C && kk + q < hid) ? v[(size_t)o * row + kk + q] * os[o] : 0.f;
+    uint32_t hi, lo;
+    pack_pair(x[0], x[1], hi, lo);
+    dst[e] = hi;
+    dst[(size_t)total + e] = lo;
+  }
+}
+size_t mcf_mma_conv_words(int C) { return (size_t)((4 * C + 15) / 16) * (6 * ((C + 15) / 16)) * 128 * 2; }
+size_t mcf_mma_1x1_words(int C) { return (size_t)((C + 7) / 8) * ((4 * C + 15) / 16) * 128 * 2; }
+void pack_mcf_mma(const float* shift_w, const float* v, const float* os, uint32_t* conv_dst, uint32_t* x1_dst, int hid, int C,
+                  int kh, int kw, int order, int row, cudaStream_t st) {
+  pack_mcf_mma_conv_kernel<<<std::max(1, std::min(64, (int)(mcf_mma_conv_words(C) / 2 + 255) / 256)), 256, 0, st>>>(shift_w, conv_dst, hid, C, kh, kw, order);
+  IPK_LAUNCH_CHECK();
+  pack_mcf_mma_1x1_kernel<<<std::max(1, std::min(64, (int)(mcf_mma_1x1_words(C) / 2 + 255) / 256)), 256, 0, st>>>(v, os, x1_dst, hid, C, row);
   IPK_LAUNCH_CHECK();
 }
 

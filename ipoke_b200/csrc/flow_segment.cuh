@@ -25,7 +25,8 @@ struct MicroOp {
    MK_ACTNORM : i0 = channel offset, i1 = channel count, p0 = log_scale, p1 = bias
    MK_SHUFFLE : i0 = C, idx = gather index (new[c] = old[idx[c]])
    MK_MCF     : i0 = order (0 A,1 B,2 C,3 D), i1 = C, i2 = Cp (C rounded up to 4), i3 = hid,
-                p0 = Wc [6][Cp/4][hid][4], p1 = W1x [hid/4][2C][4],
+                p0 = Wc [6][Cp/4][hid][4], p1 = W1x [hid/4][2C][4]   (fp32 paths)
+                     or the mma.sync A-fragment arrays of pack_mcf_mma (tensor-core precisions, C <= 32),
                 p2 = conditioning term of this MCF: column block of the precomputed matrix
                      Hterm[M = B*64][l0] = b + W1h * ELU(cond)  (round_up(2C, 4) columns, 16-byte aligned), l0 = row stride
    MK_AFFINE  : i0 = nsplit, i1 = Npad (row length of the tap-response matrix), i2 = n_p, i3 = N3p (columns per tap),
@@ -40,13 +41,20 @@ struct SegmentLaunch {
   int nops;
   int C;                // active channels of this level
   bool has_mcf;
+  bool mma;             // masked-conv flows on mma.sync bf16x3 (tensor-core precisions, C <= 32)
 };
 
 constexpr int MAX_NSPLIT = 9;   // upper bound on the split-K slices of a NICE conv3
 
 // state: [B][64][C0] fp32 NHWC (in place); logdet: [B] (forward only, accumulated)
 void flow_segment_run(const SegmentLaunch& s, bool forward, float* state, int C0, float* logdet, int B, cudaStream_t st);
-size_t flow_segment_smem_bytes(int C, int h_ch, bool has_mcf);
+size_t flow_segment_smem_bytes(int C, bool has_mcf, bool mma);
+// mma.sync A-fragment packing of one MCF (see flow_segment.cu); sizes in 32-bit words (hi + lo planes)
+size_t mcf_mma_conv_words(int C);
+size_t mcf_mma_1x1_words(int C);
+void pack_mcf_mma(const float* shift_w, const float* v, const float* os, uint32_t* conv_dst, uint32_t* x1_dst, int hid, int C,
+                  int kh, int kw, int order, int row, cudaStream_t st);
+constexpr int MCF_MMA_MAXC = 32;
 void flow_segment_init();
 
 }  // namespace ipk
