@@ -338,7 +338,7 @@ __device__ __forceinline__ void mcf_mma(const MicroOp& op, const MicroOp* next, 
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float h = ((d[0][j] + d[3][j]) + (d[1][j] + d[4][j])) + (d[2][j] + d[5][j]);
-          h = h > 0.f ? h : expm1f(h);
+          h = h > 0.f ? h : (exp2f(h * 1.4426950408889634f) - 1.0f);     // ELU; abs error ~1e-7, below the bf16x3 operand split
           const int n = warp * 16 + g + (j >> 1) * 8, pos = t * 2 + (j & 1);
           if (n < hid) {
             const __nv_bfloat16 hi = __float2bfloat16_rn(h);
@@ -379,14 +379,16 @@ __device__ __forceinline__ void mcf_mma(const MicroOp& op, const MicroOp* next, 
           const int pix = mcf_pix(order, u, pos);
           const float mu = ((d[0][jp] + d[3][jp]) + (d[1][jp] + d[4][jp])) + (d[2][jp] + d[5][jp]) + hterm[pix * C2s + c];
           const float ls = ((d[0][2 + jp] + d[3][2 + jp]) + (d[1][2 + jp] + d[4][2 + jp])) + (d[2][2 + jp] + d[5][2 + jp]) + hterm[pix * C2s + C + c];
-          const float sc = 1.0f + tanhf(0.5f * ls);
+          // density direction: the reference's own formulation, so the log-det rounding stays correlated with it.
+          // sampling direction (latency-critical): 1 + tanh(ls/2) == 2 / (1 + exp(-ls)) on the SFU.
+          const float sc = FWD ? 1.0f + tanhf(0.5f * ls) : 2.0f * __frcp_rn(1.0f + exp2f(-1.4426950408889634f * ls));
           float xin;       // value of this element in the un-transformed domain: conv input of the following lines
           if (FWD) {
             xin = sm.tmp[pix * Cs + c];
             sm.s[pix * Cs + c] = sc * xin + mu;
             ld += logf(sc);
           } else {
-            xin = (sm.s[pix * Cs + c] - mu) / (sc + 1e-12f);
+            xin = (sm.s[pix * Cs + c] - mu) * __frcp_rn(sc + 1e-12f);
             sm.s[pix * Cs + c] = xin;
           }
           const int ro = (slot0 * 10 + pos + 1) * XS + c;
@@ -505,6 +507,64 @@ __device__ void mcf_generic(const MicroOp& op, const SegSmem& sm, int Cs, int b,
   }
 }
 
+// Finishes a NICE coupling: params[p] = bias + sum over taps t and split-K slices of T[p + delta_t][t]  (the 3x3 gather of
+// conv3 with zero padding), then Affine.fwd / bwd on the transformed channels.
+// Step 1 (lane = parameter index e: mu of element e, or log-scale of element e - n_p): a warp reads 2*n_p contiguous floats
+// per (pixel, tap, slice); PB pixels x nine taps of loads are in flight per lane.  Step 2 (lane = element).
+template <bool FWD, int PB>
+__device__ __forceinline__ void affine_op(const MicroOp& op, const SegSmem& sm, int Cs, int b, float& ld) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nsplit = op.i0, Npad = op.i1, n_p = op.i2, N3p = op.i3;
+  const float* Tb = op.p0 + (size_t)b * 64 * Npad;
+  constexpr int NW = SEG_THREADS / 32;
+  for (int e = lane; e < 2 * n_p; e += 32) {
+    const float bias = __ldg(op.p1 + e);
+#pragma unroll 1
+    for (int pg = 0; pg < 64 / NW; pg += PB) {
+      float v[PB];
+#pragma unroll
+      for (int q = 0; q < PB; ++q) v[q] = bias;
+      for (int sidx = 0; sidx < nsplit; ++sidx) {
+        const float* T = Tb + (size_t)sidx * op.l0 + e;
+        float pv[PB][9];
+#pragma unroll
+        for (int q = 0; q < PB; ++q) {
+          const int pp = warp + (pg + q) * NW;
+          const int y = pp >> 3, x = pp & 7;
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+            const bool ok = yy >= 0 && yy < 8 && xx >= 0 && xx < 8;
+            pv[q][t] = ok ? T[(size_t)(yy * 8 + xx) * Npad + t * N3p] : 0.f;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < PB; ++q)
+#pragma unroll
+          for (int t = 0; t < 9; ++t) v[q] += pv[q][t];
+      }
+#pragma unroll
+      for (int q = 0; q < PB; ++q) sm.tmp[(warp + (pg + q) * NW) * Cs + e] = v[q];
+    }
+  }
+  __syncwarp();
+  for (int j = lane; j < n_p; j += 32) {
+    const int c = op.idx[j];
+    for (int pp = warp; pp < 64; pp += NW) {
+      const float mu = sm.tmp[pp * Cs + j], ls = sm.tmp[pp * Cs + n_p + j];
+      const float sc = 1.0f + tanhf(0.5f * ls);
+      const float xv = sm.s[pp * Cs + c];
+      if (FWD) {
+        sm.s[pp * Cs + c] = sc * xv + mu;
+        ld += logf(sc);
+      } else {
+        sm.s[pp * Cs + c] = (xv - mu) / (sc + 1e-12f);
+      }
+    }
+  }
+  __syncthreads();
+}
+
 __device__ __forceinline__ int next_mcf(const MicroOp* __restrict__ ops, int from, int nops) {
   for (int i = from; i < nops; ++i)
     if (ops[i].kind == MK_MCF) return i;
@@ -527,11 +587,28 @@ __global__ void __launch_bounds__(SEG_THREADS, 1) flow_segment_kernel(const Micr
   sm.p1 = smem + lo.p1; sm.red = smem + lo.red;
   sm.ring = (__nv_bfloat16*)(smem + lo.ring); sm.actb = (__nv_bfloat16*)(smem + lo.actb);
 
-  // first MCF of the segment: start fetching its weights / conditioning term before anything else
+  const int warp = tid >> 5, lane = tid & 31;
+  float* gs = state + (size_t)b * 64 * C0;
+  // (pixel by warp, channel by lane) loops everywhere below: no integer divisions on the latency chain
+  for (int p = warp; p < 64; p += SEG_THREADS / 32)
+    for (int c = lane; c < Cs; c += 32) sm.s[p * Cs + c] = c < C ? gs[p * C0 + c] : 0.f;
+  __syncthreads();
+
+  float ld = 0.f;
+  // A segment that follows a coupling network starts with that coupling's affine update.  Run it before the MCF weight
+  // registers become live: the whole 8-pixel x 9-tap gather of a warp is then in flight at once.
+  int op_begin = 0;
+  if (nops > 0 && ops[0].kind == MK_AFFINE) {
+    const MicroOp op0 = ops[0];
+    affine_op<FWD, 8>(op0, sm, Cs, b, ld);
+    op_begin = 1;
+  }
+
+  // first MCF of the segment: start fetching its weights / conditioning term
   typename std::conditional<MMA, McfMmaRegs, McfRegs>::type regs;
   int hbuf = 0;
   MicroOp nxt;
-  int nxt_i = (has_mcf && fast) ? next_mcf(ops, 0, nops) : -1;
+  int nxt_i = (has_mcf && fast) ? next_mcf(ops, op_begin, nops) : -1;
   if (nxt_i >= 0) {
     nxt = ops[nxt_i];
     mcf_prefetch_hterm(nxt, b, sm.hterm);
@@ -543,21 +620,14 @@ __global__ void __launch_bounds__(SEG_THREADS, 1) flow_segment_kernel(const Micr
       uint32_t* z = (uint32_t*)sm.ring;
       const int nz = (int)(lo.total - lo.ring);
       for (int i = tid; i < nz; i += SEG_THREADS) z[i] = 0u;
+      __syncthreads();
     } else {
       mcf_load_wc(nxt, regs);
       mcf_load_w1(nxt, regs);
     }
   }
 
-  const int warp = tid >> 5, lane = tid & 31;
-  float* gs = state + (size_t)b * 64 * C0;
-  // (pixel by warp, channel by lane) loops everywhere below: no integer divisions on the latency chain
-  for (int p = warp; p < 64; p += SEG_THREADS / 32)
-    for (int c = lane; c < Cs; c += 32) sm.s[p * Cs + c] = c < C ? gs[p * C0 + c] : 0.f;
-  __syncthreads();
-
-  float ld = 0.f;
-  for (int oi = 0; oi < nops; ++oi) {
+  for (int oi = op_begin; oi < nops; ++oi) {
     const MicroOp op = ops[oi];
     switch (op.kind) {
       case MK_ACTNORM: {
@@ -612,62 +682,9 @@ __global__ void __launch_bounds__(SEG_THREADS, 1) flow_segment_kernel(const Micr
         }
         break;
       }
-      case MK_AFFINE: {
-        // finishes a NICE coupling: params[p] = bias + sum over taps t and split-K slices of T[p + delta_t][t]  (the 3x3
-        // gather of conv3 with zero padding), then Affine.fwd / bwd on the transformed channels.
-        // Step 1 (lane = parameter index e: mu of element e, or log-scale of element e - n_p): a warp reads 2*n_p contiguous
-        // floats per (pixel, tap, slice); two pixels x nine taps of loads are in flight per lane.  Step 2 (lane = element).
-        const int nsplit = op.i0, Npad = op.i1, n_p = op.i2, N3p = op.i3;
-        const float* Tb = op.p0 + (size_t)b * 64 * Npad;
-        constexpr int NW = SEG_THREADS / 32;
-        for (int e = lane; e < 2 * n_p; e += 32) {
-          const float bias = __ldg(op.p1 + e);
-#pragma unroll 1
-          for (int pg = 0; pg < 64 / NW; pg += 2) {
-            float v[2];
-#pragma unroll
-            for (int q = 0; q < 2; ++q) v[q] = bias;
-            for (int sidx = 0; sidx < nsplit; ++sidx) {
-              const float* T = Tb + (size_t)sidx * op.l0 + e;
-              float pv[2][9];
-#pragma unroll
-              for (int q = 0; q < 2; ++q) {
-                const int pp = warp + (pg + q) * NW;
-                const int y = pp >> 3, x = pp & 7;
-#pragma unroll
-                for (int t = 0; t < 9; ++t) {
-                  const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
-                  const bool ok = yy >= 0 && yy < 8 && xx >= 0 && xx < 8;
-                  pv[q][t] = ok ? T[(size_t)(yy * 8 + xx) * Npad + t * N3p] : 0.f;
-                }
-              }
-#pragma unroll
-              for (int q = 0; q < 2; ++q)
-#pragma unroll
-                for (int t = 0; t < 9; ++t) v[q] += pv[q][t];
-            }
-#pragma unroll
-            for (int q = 0; q < 2; ++q) sm.tmp[(warp + (pg + q) * NW) * Cs + e] = v[q];
-          }
-        }
-        __syncwarp();
-        for (int j = lane; j < n_p; j += 32) {
-          const int c = op.idx[j];
-          for (int pp = warp; pp < 64; pp += NW) {
-            const float mu = sm.tmp[pp * Cs + j], ls = sm.tmp[pp * Cs + n_p + j];
-            const float sc = 1.0f + tanhf(0.5f * ls);
-            const float xv = sm.s[pp * Cs + c];
-            if (FWD) {
-              sm.s[pp * Cs + c] = sc * xv + mu;
-              ld += logf(sc);
-            } else {
-              sm.s[pp * Cs + c] = (xv - mu) / (sc + 1e-12f);
-            }
-          }
-        }
-        __syncthreads();
+      case MK_AFFINE:
+        affine_op<FWD, 2>(op, sm, Cs, b, ld);
         break;
-      }
       case MK_IM2COL: {
         // operand rows of the next coupling's conv1: A1[b*64 + p][k = tap*n_z + j] = z-part of the state at pixel p + delta_tap
         const int n_z = op.i0, K1 = op.i1, mode = op.i2;
