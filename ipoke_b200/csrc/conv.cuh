@@ -19,6 +19,10 @@ struct ConvOut {
   int act = ACT_NONE;
   const float* bias = nullptr;        // [>=N] or null
   long long split_stride = 0;         // elements between split-K partial slices (fp32 NHWC only)
+  // optional second destination (tensor-core engine): output columns [split_col, N) go to `second` (its p / p_lo / mode /
+  // cstride / coff / act; column index rebased to n - split_col); pixel mapping and bias array are shared
+  const ConvOut* second = nullptr;
+  int split_col = 0;                  // multiple of 32
 };
 
 // Activation operand of one launch.
@@ -50,6 +54,11 @@ struct TapList {
 // slices actually written.
 int conv_simt_run(const ConvW& w, const ConvIn& in, const ConvOut& out, const TapList& taps, int nsplit, cudaStream_t st);
 int conv_tc_run(const ConvW& w, const ConvIn& in, const ConvOut& out, const TapList& taps, int nsplit, cudaStream_t st);
+
+// Tensor-core engine only: up to 4 tap lists ("sub-convolutions") over the same input and packed weights in ONE launch, each
+// writing its own output phase (yadd, xadd) -- the four parity classes of a stride-2 ConvTranspose2d.
+struct ConvSub { TapList taps; int yadd = 0, xadd = 0; };
+void conv_tc_run_multi(const ConvW& w, const ConvIn& in, const ConvOut& out, const ConvSub* subs, int nsub, cudaStream_t st);
 
 inline int conv_run(const ConvW& w, const ConvIn& in, const ConvOut& out, const TapList& taps, int nsplit, cudaStream_t st) {
   if (w.engine == IPK_PREC_FP32_SIMT) return conv_simt_run(w, in, out, taps, nsplit, st);

@@ -12,6 +12,7 @@
 // * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane), warps 2..5 = epilogue
 //   (TMEM -> registers -> bias / activation / operand split -> global).
 #include <cuda.h>
+#include <cstring>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -25,20 +26,30 @@ constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr size_t TC_SMEM_BUDGET = 200 * 1024;
 
+constexpr int TC_MAX_SUB = 4;
+struct TcSub {                    // one tap list + output phase (a parity class of a transposed conv; plain convs have one)
+  int ntaps, yadd, xadd;
+  int dy[MAX_TAPS], dx[MAX_TAPS], widx[MAX_TAPS];
+};
+struct TcOut {                    // destination of a column range
+  void* out; void* out_lo;
+  int act, mode, cstride, coff;
+};
 struct TcArgs {
   int F, H, W;
   int bw, bh, bf;                 // pixel box (bw*bh*bf == 128)
   int tiles_x, tiles_y;           // tiles along x and y
   int tiles_m, tiles_n, nsplit;   // tiles_m = tiles_x * tiles_y * tiles_f
-  int ntaps, iters_per_split, nkb; // nkb = Kpad / 64; a split covers iters_per_split consecutive (tap, k-block) iterations
-  int dy[MAX_TAPS], dx[MAX_TAPS], widx[MAX_TAPS];
+  int nsub;                       // sub-convolutions in this launch (nsplit == 1 when > 1)
+  int iters_per_split, nkb;       // nkb = Kpad / 64; a split covers iters_per_split consecutive (tap, k-block) iterations
+  TcSub sub[TC_MAX_SUB];
   int Npad, N;
   int stages;
   // epilogue
   const float* bias;
-  int act, out_mode, out_cstride, out_coff, Ho, Wo, ymul, yadd, xmul, xadd;
-  void* out;
-  void* out_lo;
+  int Ho, Wo, ymul, xmul;
+  int split_col;                  // columns >= split_col (when > 0) go to o[1]
+  TcOut o[2];
   long long split_stride;
 };
 
@@ -188,7 +199,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const int stages = a.stages;
   const int txy = a.tiles_x * a.tiles_y;
   const int tiles_mn = a.tiles_m * a.tiles_n;
-  const int total_tiles = tiles_mn * a.nsplit;
+  const int total_tiles = tiles_mn * (a.nsub > 1 ? a.nsub : a.nsplit);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -210,15 +221,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       int s = 0;
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int z = tile / tiles_mn, rem = tile - z * tiles_mn;
+        const int z = tile / tiles_mn, rem = tile - z * tiles_mn;      // z: split-K slice, or sub-convolution when nsub > 1
         const int mt = rem / a.tiles_n, nt = rem - mt * a.tiles_n;
         const int tf = mt / txy, r2 = mt - tf * txy;
         const int ty = r2 / a.tiles_x, tx = r2 - ty * a.tiles_x;
         const int f0 = tf * a.bf, y0 = ty * a.bh, x0 = tx * a.bw, n0 = nt * BN;
-        const int it_begin = z * a.iters_per_split, it_end = min(a.ntaps * a.nkb, it_begin + a.iters_per_split);
+        const TcSub& sb = a.sub[a.nsub > 1 ? z : 0];
+        const int it_begin = a.nsub > 1 ? 0 : z * a.iters_per_split;
+        const int it_end = min(sb.ntaps * a.nkb, it_begin + a.iters_per_split);
         int t = it_begin / a.nkb, kb = it_begin - t * a.nkb;
         for (int it = it_begin; it < it_end; ++it) {
-          const int dy = a.dy[t], dx = a.dx[t], wrow = a.widx[t] * a.Npad + n0;
+          const int dy = sb.dy[t], dx = sb.dx[t], wrow = sb.widx[t] * a.Npad + n0;
           {
             mbar_wait(&empty_bar[s], ph ^ 1);
             uint8_t* st = smem + (size_t)s * STAGE_BYTES;
@@ -244,8 +257,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       uint32_t aph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int z = tile / tiles_mn;
-        const int it_begin = z * a.iters_per_split;
-        const int iters = min(a.ntaps * a.nkb, it_begin + a.iters_per_split) - it_begin;
+        const int it_begin = a.nsub > 1 ? 0 : z * a.iters_per_split;
+        const int iters = min(a.sub[a.nsub > 1 ? z : 0].ntaps * a.nkb, it_begin + a.iters_per_split) - it_begin;
         mbar_wait(&tmem_empty_bar[as], aph ^ 1);      // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(as * BN);
@@ -288,10 +301,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const int f = tf * a.bf + fl, y = ty * a.bh + yl, x = tx * a.bw + xl;
       const int n0 = nt * BN;
       const bool valid = (f < a.F) && (y < a.H) && (x < a.W);
-      const int oy = y * a.ymul + a.yadd, ox = x * a.xmul + a.xadd;
+      const TcSub& sb = a.sub[a.nsub > 1 ? z : 0];
+      const int oy = y * a.ymul + sb.yadd, ox = x * a.xmul + sb.xadd;
       const size_t opix = ((size_t)f * a.Ho + (size_t)oy) * a.Wo + (size_t)ox;
-      const size_t obase = opix * a.out_cstride + a.out_coff;
-      float* outf = (float*)a.out + (size_t)z * a.split_stride;
+      const size_t zoff = a.nsub > 1 ? 0 : (size_t)z * a.split_stride;
 
       mbar_wait(&tmem_full_bar[as], aph);
       tc_fence_after();
@@ -310,6 +323,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           for (int j = 0; j < EPI_CHUNK; ++j) v[j] = __uint_as_float(rr[j]);
         }
         if (!valid) continue;
+        const int oi = (a.split_col > 0 && n0 + c >= a.split_col) ? 1 : 0;     // warp-uniform: destination of this chunk
+        const TcOut& od = a.o[oi];
+        const size_t ocol = opix * od.cstride + od.coff + (size_t)(n0 + c - (oi ? a.split_col : 0));
         if (a.bias) {
           const float4* b4 = (const float4*)(a.bias + n0 + c);
 #pragma unroll
@@ -319,18 +335,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
           }
         }
-        act_tile<EPI_CHUNK>(v, a.act);
-        if (a.out_mode == OUT_F32_NHWC) {
-          float4* p = (float4*)(outf + obase + n0 + c);
+        act_tile<EPI_CHUNK>(v, od.act);
+        if (od.mode == OUT_F32_NHWC) {
+          float4* p = (float4*)((float*)od.out + zoff + ocol);
 #pragma unroll
           for (int j = 0; j < EPI_CHUNK / 4; ++j)
             if (4 * j < ncols) p[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        } else if (a.out_mode == OUT_F32_NCHW) {
+        } else if (od.mode == OUT_F32_NCHW) {
           // frames at the ABI edge: [f][N][Ho][Wo]; consecutive lanes are consecutive x -> coalesced per channel
 #pragma unroll
           for (int j = 0; j < EPI_CHUNK; ++j) {
             const int n = n0 + c + j;
-            if (n < a.N) ((float*)a.out)[(((size_t)f * a.N + n) * a.Ho + oy) * a.Wo + ox] = v[j];
+            if (n < a.N) ((float*)od.out)[(((size_t)f * a.N + n) * a.Ho + oy) * a.Wo + ox] = v[j];
           }
         } else {
           uint32_t hi[EPI_CHUNK / 2], lo[EPI_CHUNK / 2];
@@ -342,12 +358,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             hi[j] = *(const uint32_t*)&hh;
             lo[j] = *(const uint32_t*)&ll;
           }
-          uint4* ph4 = (uint4*)((__nv_bfloat16*)a.out + obase + n0 + c);
+          uint4* ph4 = (uint4*)((__nv_bfloat16*)od.out + ocol);
 #pragma unroll
           for (int j = 0; j < EPI_CHUNK / 8; ++j)
             if (8 * j < ncols) ph4[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-          if (a.out_mode == OUT_BF16_SPLIT) {
-            uint4* pl4 = (uint4*)((__nv_bfloat16*)a.out_lo + obase + n0 + c);
+          if (od.mode == OUT_BF16_SPLIT) {
+            uint4* pl4 = (uint4*)((__nv_bfloat16*)od.out_lo + ocol);
 #pragma unroll
             for (int j = 0; j < EPI_CHUNK / 8; ++j)
               if (8 * j < ncols) pl4[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
@@ -439,24 +455,34 @@ static void launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CU
     IPK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TC_SMEM_BUDGET + 1024)));
     attr_set = true;
   }
-  const long long total = (long long)a.tiles_m * a.tiles_n * a.nsplit;
+  const long long total = (long long)a.tiles_m * a.tiles_n * (a.nsub > 1 ? a.nsub : a.nsplit);
   const unsigned grid = (unsigned)std::min<long long>(total, sm_count());     // persistent: one CTA per SM
   conv_tc_kernel<BN, NSPLIT><<<grid, TC_THREADS, smem, st>>>(a_hi, a_lo, w_hi, w_lo, a);
   IPK_LAUNCH_CHECK();
 }
 
-int conv_tc_run(const ConvW& w, const ConvIn& in, const ConvOut& out, const TapList& taps, int nsplit, cudaStream_t st) {
+static int conv_tc_impl(const ConvW& w, const ConvIn& in, const ConvOut& out, const ConvSub* subs, int nsub, int nsplit, cudaStream_t st) {
   IPK_CHECK(w.w_hi != nullptr, IPK_ERR_STATE, "conv_tc_run: layer was not packed for the tensor-core engine");
+  IPK_CHECK(nsub >= 1 && nsub <= TC_MAX_SUB, IPK_ERR_INVALID, "conv_tc_run: bad sub-convolution count %d", nsub);
   const bool split = w.engine == IPK_PREC_FP32_SPLIT;
   IPK_CHECK(!split || (in.p_lo && w.w_lo), IPK_ERR_STATE, "conv_tc_run: split precision needs hi and lo operand planes");
   IPK_CHECK(in.cstride % 8 == 0 && in.coff % 8 == 0, IPK_ERR_UNSUPPORTED, "conv_tc_run: activation rows must be 16-byte aligned (cstride %d, coff %d)", in.cstride, in.coff);
-  if (out.mode != OUT_F32_NCHW)
-    IPK_CHECK((out.cstride % 4 == 0) && (out.coff % 4 == 0) && out.coff + w.Npad <= out.cstride, IPK_ERR_UNSUPPORTED,
-              "conv_tc_run: output row (cstride %d, coff %d) cannot hold Npad %d", out.cstride, out.coff, w.Npad);
-  if (out.mode == OUT_BF16_SPLIT || out.mode == OUT_BF16) IPK_CHECK(out.cstride % 8 == 0 && out.coff % 8 == 0, IPK_ERR_UNSUPPORTED, "conv_tc_run: bf16 output rows must be 16-byte aligned");
+  const ConvOut* outs[2] = {&out, out.second};
+  const int ncol[2] = {out.second ? out.split_col : w.Npad, out.second ? w.Npad - out.split_col : 0};
+  if (out.second) IPK_CHECK(out.split_col > 0 && out.split_col % 32 == 0 && out.split_col < w.Npad, IPK_ERR_INVALID, "conv_tc_run: bad split_col %d", out.split_col);
+  for (int i = 0; i < 2; ++i) {
+    const ConvOut* o = outs[i];
+    if (!o) continue;
+    if (o->mode != OUT_F32_NCHW)
+      IPK_CHECK((o->cstride % 4 == 0) && (o->coff % 4 == 0) && o->coff + ncol[i] <= o->cstride, IPK_ERR_UNSUPPORTED,
+                "conv_tc_run: output row (cstride %d, coff %d) cannot hold %d columns", o->cstride, o->coff, ncol[i]);
+    if (o->mode == OUT_BF16_SPLIT || o->mode == OUT_BF16)
+      IPK_CHECK(o->cstride % 8 == 0 && o->coff % 8 == 0, IPK_ERR_UNSUPPORTED, "conv_tc_run: bf16 output rows must be 16-byte aligned");
+  }
   long long M = (long long)in.F * in.H * in.W;
   if (M == 0) return 0;
   TcArgs a;
+  memset(&a, 0, sizeof(a));
   a.F = in.F; a.H = in.H; a.W = in.W;
   if ((long long)in.H * in.W <= TC_BM) {
     IPK_CHECK(TC_BM % (in.H * in.W) == 0, IPK_ERR_UNSUPPORTED, "conv_tc_run: grid %dx%d does not tile 128 rows", in.H, in.W);
@@ -469,18 +495,30 @@ int conv_tc_run(const ConvW& w, const ConvIn& in, const ConvOut& out, const TapL
   }
   a.tiles_x = cdiv(in.W, a.bw); a.tiles_y = cdiv(in.H, a.bh);
   const int tiles_f = cdiv(in.F, a.bf);
-  a.ntaps = taps.n;
   a.nkb = w.Kpad / TC_BK;
-  const int total_iters = taps.n * a.nkb;
+  a.nsub = nsub;
+  int max_taps = 0;
+  for (int i = 0; i < nsub; ++i) {
+    const TapList& t = subs[i].taps;
+    a.sub[i].ntaps = t.n; a.sub[i].yadd = subs[i].yadd; a.sub[i].xadd = subs[i].xadd;
+    for (int j = 0; j < MAX_TAPS; ++j) { a.sub[i].dy[j] = t.dy[j]; a.sub[i].dx[j] = t.dx[j]; a.sub[i].widx[j] = t.widx[j]; }
+    max_taps = std::max(max_taps, t.n);
+  }
+  const int total_iters = max_taps * a.nkb;
+  if (nsub > 1) nsplit = 1;
   nsplit = std::max(1, std::min(nsplit, total_iters));
   a.iters_per_split = cdiv(total_iters, nsplit);
   nsplit = cdiv(total_iters, a.iters_per_split);
-  IPK_CHECK(nsplit == 1 || (out.mode == OUT_F32_NHWC && out.split_stride > 0), IPK_ERR_INVALID, "split-K needs fp32 partial slices");
-  for (int i = 0; i < MAX_TAPS; ++i) { a.dy[i] = taps.dy[i]; a.dx[i] = taps.dx[i]; a.widx[i] = taps.widx[i]; }
+  IPK_CHECK(nsplit == 1 || (out.mode == OUT_F32_NHWC && out.split_stride > 0 && !out.second), IPK_ERR_INVALID, "split-K needs fp32 partial slices");
   a.Npad = w.Npad; a.N = w.N;
-  a.bias = out.bias; a.act = out.act; a.out_mode = out.mode; a.out_cstride = out.cstride; a.out_coff = out.coff;
-  a.Ho = out.Ho; a.Wo = out.Wo; a.ymul = out.ymul; a.yadd = out.yadd; a.xmul = out.xmul; a.xadd = out.xadd;
-  a.out = out.p; a.out_lo = out.p_lo; a.split_stride = out.split_stride;
+  a.bias = out.bias;
+  a.Ho = out.Ho; a.Wo = out.Wo; a.ymul = out.ymul; a.xmul = out.xmul;
+  a.split_col = out.second ? out.split_col : 0;
+  for (int i = 0; i < 2; ++i) {
+    const ConvOut* o = outs[i] ? outs[i] : &out;
+    a.o[i].out = o->p; a.o[i].out_lo = o->p_lo; a.o[i].act = o->act; a.o[i].mode = o->mode; a.o[i].cstride = o->cstride; a.o[i].coff = o->coff;
+  }
+  a.split_stride = out.split_stride;
   a.stages = 2;
 
   // activation maps: dims (C, W, H, F); the C extent is the true channel count so the K tail is zero-filled
@@ -521,6 +559,16 @@ int conv_tc_run(const ConvW& w, const ConvIn& in, const ConvOut& out, const TapL
   }
 #undef IPK_TC_CASE
   return nsplit;
+}
+
+int conv_tc_run(const ConvW& w, const ConvIn& in, const ConvOut& out, const TapList& taps, int nsplit, cudaStream_t st) {
+  ConvSub sub;
+  sub.taps = taps; sub.yadd = out.yadd; sub.xadd = out.xadd;
+  return conv_tc_impl(w, in, out, &sub, 1, nsplit, st);
+}
+
+void conv_tc_run_multi(const ConvW& w, const ConvIn& in, const ConvOut& out, const ConvSub* subs, int nsub, cudaStream_t st) {
+  conv_tc_impl(w, in, out, subs, nsub, 1, st);
 }
 
 }  // namespace ipk

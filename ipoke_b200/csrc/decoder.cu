@@ -18,6 +18,7 @@ struct FsTensor { const void* p; int64_t numel; int dtype; };
 struct UpBlock {
   int Cin, Cout, s_in;       // input grid s_in x s_in -> output 2 s_in
   ConvW ct1, ctr, c2;        // conv1 (ConvT), res_conv (ConvT), conv2 (3x3)
+  ConvW ctf;                 // tensor-core engines: conv1 | res_conv fused along N (one read of the input per tap)
   ConvW sp1, spgb;           // SPADE: 3->128, 128->(1+gamma | beta)
   float* SP = nullptr;       // [max_batch][(2 s_in)^2][2 Cout]
   int groups = 16;
@@ -78,9 +79,9 @@ static float* dev_copy(ipk_fs* d, const void* src, size_t n, cudaStream_t st) {
 
 static const std::vector<int> ALL9 = {0, 1, 2, 3, 4, 5, 6, 7, 8};
 
-// a 3x3 conv (or ConvTranspose) whose weight may carry legacy spectral norm (weight_orig / weight_u / weight_v)
-static ConvW build_conv3(ipk_fs* d, const std::string& p, int engine, int Cout, int Cin, bool transposed, float bias_add, cudaStream_t st) {
-  ConvW w = conv_alloc(d->pool, engine, 9, Cin, Cout, true);
+// pack a 3x3 conv (or ConvTranspose) whose weight may carry legacy spectral norm (weight_orig / weight_u / weight_v) into
+// output columns [n_off, n_off + Cout) of `w`
+static void pack_conv3_into(ipk_fs* d, ConvW& w, int n_off, const std::string& p, int Cout, int Cin, bool transposed, float bias_add, cudaStream_t st) {
   PackSrc s;
   s.N = Cout; s.Ksrc = Cin; s.kh = 3; s.kw = 3; s.transposed = transposed;
   const int64_t numel = (int64_t)Cout * Cin * 9;
@@ -97,8 +98,12 @@ static ConvW build_conv3(ipk_fs* d, const std::string& p, int engine, int Cout, 
   } else {
     s.w = (const float*)fneed(d, p + "weight", numel).p;
   }
-  conv_pack_into(w, 0, s, ALL9, st);
-  conv_pack_bias(w, 0, (const float*)fneed(d, p + "bias", Cout).p, Cout, bias_add, st);
+  conv_pack_into(w, n_off, s, ALL9, st);
+  conv_pack_bias(w, n_off, (const float*)fneed(d, p + "bias", Cout).p, Cout, bias_add, st);
+}
+static ConvW build_conv3(ipk_fs* d, const std::string& p, int engine, int Cout, int Cin, bool transposed, float bias_add, cudaStream_t st) {
+  ConvW w = conv_alloc(d->pool, engine, 9, Cin, Cout, true);
+  pack_conv3_into(d, w, 0, p, Cout, Cin, transposed, bias_add, st);
   return w;
 }
 
@@ -110,7 +115,8 @@ static int gn_groups(int C) {
 
 static void stats_norm(ipk_fs* d, const float* x, int F, long long P, int C, int groups, cudaStream_t st) {
   IPK_CUDA(cudaMemsetAsync(d->sums, 0, (size_t)F * C * 2 * sizeof(double), st));
-  channel_stats(x, F, P, C, d->sums, st);
+  NormApply n; n.x = x; n.F = F; n.C = C; n.P = P; n.stats_out = d->sums;     // pure statistics pass
+  norm_apply(n, st);
   finalize_stats(d->sums, d->mr, F, P, C, groups, 1e-5f, st);
 }
 
@@ -194,22 +200,38 @@ static void decode_frames(ipk_fs* d, const float* h, int nv, int T, int v0, floa
     const long long P = (long long)so * so;
     ConvIn in; in.p = d->bufA; in.p_lo = d->bufA_lo; in.cstride = ub.Cin; in.F = F; in.H = s; in.W = s;
     // conv1: ConvT + ReLU ("elu" maps to nn.ReLU in Conv2dTransposeBlock, util.py:41-42)
-    ConvOut o1; o1.p = d->bufY1; o1.p_lo = d->bufY1_lo; o1.mode = d->act_mode; o1.cstride = ub.Cout; o1.Ho = so; o1.Wo = so; o1.act = ACT_RELU; o1.bias = ub.ct1.bias;
-    { ProfScope ps("dec.up.convT1", st); run_convT(ub.ct1, in, o1, st); }
     // res_conv: ConvT (+ InstanceNorm + ReLU applied below)
-    ConvOut orr; orr.p = d->bufR; orr.cstride = ub.Cout; orr.Ho = so; orr.Wo = so; orr.bias = ub.ctr.bias;
-    { ProfScope ps("dec.up.convTres", st); run_convT(ub.ctr, in, orr, st); }
+    const std::string bi = std::to_string(i);
+    ConvOut o1; o1.p = d->bufY1; o1.p_lo = d->bufY1_lo; o1.mode = d->act_mode; o1.cstride = ub.Cout; o1.Ho = so; o1.Wo = so; o1.act = ACT_RELU;
+    ConvOut orr; orr.p = d->bufR; orr.cstride = ub.Cout; orr.Ho = so; orr.Wo = so;
+    if (d->eng == IPK_PREC_FP32_SIMT) {
+      o1.bias = ub.ct1.bias; orr.bias = ub.ctr.bias;
+      { ProfScope ps(("dec.up.convT1.b" + bi).c_str(), st); run_convT(ub.ct1, in, o1, st); }
+      { ProfScope ps(("dec.up.convTres.b" + bi).c_str(), st); run_convT(ub.ctr, in, orr, st); }
+    } else {
+      // both transposed convs and all four output parity classes in ONE launch: N = conv1 | res_conv, dual destination
+      ProfScope ps(("dec.up.convT.b" + bi).c_str(), st);
+      o1.bias = ub.ctf.bias; o1.second = &orr; o1.split_col = ub.Cout; o1.ymul = 2; o1.xmul = 2;
+      ConvSub subs[4];
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) { subs[a * 2 + b].taps = taps_convT(a, b); subs[a * 2 + b].yadd = a; subs[a * 2 + b].xadd = b; }
+      std::swap(subs[0], subs[3]);      // heaviest class (4 taps) first
+      conv_tc_run_multi(ub.ctf, in, o1, subs, 4, st);
+    }
     // conv2: ZeroPad(1) + 3x3, no norm, no activation
     ConvIn in2; in2.p = d->bufY1; in2.p_lo = d->bufY1_lo; in2.cstride = ub.Cout; in2.F = F; in2.H = so; in2.W = so;
     ConvOut o2; o2.p = d->bufY2; o2.cstride = ub.Cout; o2.Ho = so; o2.Wo = so; o2.bias = ub.c2.bias;
-    { ProfScope ps("dec.up.conv2", st); conv_run(ub.c2, in2, o2, taps_3x3(), 1, st); }
-    ProfScope pse("dec.up.norm_spade", st);
+    { ProfScope ps(("dec.up.conv2.b" + bi).c_str(), st); conv_run(ub.c2, in2, o2, taps_3x3(), 1, st); }
+    ProfScope pse(("dec.up.norm_spade.b" + bi).c_str(), st);
     // out = conv2 + ReLU(IN(res))      (ResBlock.forward, util.py:185-192)
     stats_norm(d, d->bufR, F, P, ub.Cout, 0, st);
+    // (the GroupNorm statistics of `out` needed by SPADE are accumulated by the same pass)
+    IPK_CUDA(cudaMemsetAsync(d->sums, 0, (size_t)F * ub.Cout * 2 * sizeof(double), st));
     NormApply n; n.x = d->bufR; n.F = F; n.C = ub.Cout; n.P = P; n.mr = d->mr; n.act = ACT_RELU; n.add = d->bufY2; n.out_f32 = d->bufS;
+    n.stats_out = d->sums;
     norm_apply(n, st);
     // SPADE: GroupNorm(16, affine=False)(out) * (1 + gamma) + beta
-    stats_norm(d, d->bufS, F, P, ub.Cout, ub.groups, st);
+    finalize_stats(d->sums, d->mr, F, P, ub.Cout, ub.groups, 1e-5f, st);
     NormApply sp; sp.x = d->bufS; sp.F = F; sp.C = ub.Cout; sp.P = P; sp.mr = d->mr; sp.spade = ub.SP + (size_t)v0 * P * 2 * ub.Cout; sp.T = T;
     to_operand(d, sp, d->bufA, d->bufA_lo);
     norm_apply(sp, st);
@@ -343,8 +365,14 @@ extern "C" int ipk_fs_finalize(ipk_fs* d, void* stream) {
     UpBlock ub;
     ub.Cin = dc[i]; ub.Cout = dc[i + 1]; ub.s_in = 8 << i;
     std::string p = "gen.blocks." + std::to_string(i) + ".";
-    ub.ct1 = build_conv3(d, p + "conv1.conv.", eng, ub.Cout, ub.Cin, true, 0.f, st);
-    ub.ctr = build_conv3(d, p + "res_conv.conv.", eng, ub.Cout, ub.Cin, true, 0.f, st);
+    if (eng == IPK_PREC_FP32_SIMT) {
+      ub.ct1 = build_conv3(d, p + "conv1.conv.", eng, ub.Cout, ub.Cin, true, 0.f, st);
+      ub.ctr = build_conv3(d, p + "res_conv.conv.", eng, ub.Cout, ub.Cin, true, 0.f, st);
+    } else {
+      ub.ctf = conv_alloc(d->pool, eng, 9, ub.Cin, 2 * ub.Cout, true);
+      pack_conv3_into(d, ub.ctf, 0, p + "conv1.conv.", ub.Cout, ub.Cin, true, 0.f, st);
+      pack_conv3_into(d, ub.ctf, ub.Cout, p + "res_conv.conv.", ub.Cout, ub.Cin, true, 0.f, st);
+    }
     ub.c2 = build_conv3(d, p + "conv2.conv.", eng, ub.Cout, ub.Cout, false, 0.f, st);
     std::string sp = "gen.spade_blocks." + std::to_string(i) + ".";
     if (eng == IPK_PREC_FP32_SIMT) {

@@ -123,66 +123,116 @@ void finalize_stats(const double* sums, float* mr, int F, long long P, int C, in
   IPK_LAUNCH_CHECK();
 }
 
-// ------------------------------------------------------------------ fused normalise/affine/act/residual/SPADE
+// ------------------------------------------------------------------ fused normalise/affine/act/residual/SPADE (+ output stats)
 struct NormApplyK {
   const float* x; int F, C; long long P;
   const float* mr; const float* w; const float* b; int act; const float* add; const float* spade; int T;
   float* out_f32; __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
+  double* stats_out;       // optional: per-(frame, channel) sum / sum of squares of the OUTPUT values, accumulated
+  int ppb;                 // pixels per block
 };
+// grid (pixel chunks, F): a block works on `ppb` pixels of ONE frame; thread = (channel quad c4 = tid % C4, pixel lane =
+// tid / C4).  Per-channel constants (mean, rstd, affine) sit in registers; no integer division per element.
 __global__ void __launch_bounds__(256) norm_apply_kernel(const NormApplyK a) {
-  const int C4 = a.C / 4;
-  const long long total = (long long)a.F * a.P * C4;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    int c4 = (int)(e % C4);
-    long long fp = e / C4;
-    int f = (int)(fp / a.P);
-    long long p = fp % a.P;
-    float4 v4 = ((const float4*)a.x)[e];
-    float v[4] = {v4.x, v4.y, v4.z, v4.w};
-    float ad[4] = {0.f, 0.f, 0.f, 0.f};
-    if (a.add) {
-      float4 t = ((const float4*)a.add)[e];
-      ad[0] = t.x; ad[1] = t.y; ad[2] = t.z; ad[3] = t.w;
-    }
+  const int C4 = a.C >> 2;
+  const int f = blockIdx.y;
+  const int lanes = 256 / C4;                     // pixel lanes (C4 <= 256)
+  const int c4 = threadIdx.x % C4, lane = threadIdx.x / C4;
+  const long long p0 = (long long)blockIdx.x * a.ppb;
+  const long long p1 = min(a.P, p0 + a.ppb);
+  float mean[4] = {0.f, 0.f, 0.f, 0.f}, rstd[4] = {1.f, 1.f, 1.f, 1.f}, gw[4] = {1.f, 1.f, 1.f, 1.f}, gb[4] = {0.f, 0.f, 0.f, 0.f};
+  if (lane < lanes) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      int c = c4 * 4 + i;
-      float t = v[i];
-      if (a.mr) {
-        float mean = a.mr[((size_t)f * a.C + c) * 2], rstd = a.mr[((size_t)f * a.C + c) * 2 + 1];
-        t = (t - mean) * rstd;
-      }
-      if (a.w) t = t * a.w[c] + a.b[c];
-      t = act_apply(t, a.act);
-      t += ad[i];
-      if (a.spade) {
-        size_t sp = ((size_t)(f / a.T) * a.P + p) * (2 * a.C);
-        t = t * a.spade[sp + c] + a.spade[sp + a.C + c];
-      }
-      v[i] = t;
+      const int c = c4 * 4 + i;
+      if (a.mr) { mean[i] = a.mr[((size_t)f * a.C + c) * 2]; rstd[i] = a.mr[((size_t)f * a.C + c) * 2 + 1]; }
+      if (a.w) { gw[i] = a.w[c]; gb[i] = a.b[c]; }
     }
-    if (a.out_f32) ((float4*)a.out_f32)[e] = make_float4(v[0], v[1], v[2], v[3]);
-    if (a.out_hi) {
-      __nv_bfloat16 hi[4], lo[4];
+  }
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+  if (lane < lanes) {
+    const size_t fbase = (size_t)f * a.P;
+    const size_t vbase = (size_t)(f / a.T) * a.P;
+    for (long long p = p0 + lane; p < p1; p += lanes) {
+      const size_t e = (fbase + p) * C4 + c4;
+      const float4 v4 = ((const float4*)a.x)[e];
+      float v[4] = {v4.x, v4.y, v4.z, v4.w};
+      float ad[4] = {0.f, 0.f, 0.f, 0.f};
+      if (a.add) {
+        const float4 t = ((const float4*)a.add)[e];
+        ad[0] = t.x; ad[1] = t.y; ad[2] = t.z; ad[3] = t.w;
+      }
+      float sg[4] = {1.f, 1.f, 1.f, 1.f}, sb[4] = {0.f, 0.f, 0.f, 0.f};
+      if (a.spade) {
+        const float4* sp = (const float4*)(a.spade + (vbase + p) * (2 * a.C));
+        const float4 g4 = sp[c4], b4 = sp[C4 + c4];
+        sg[0] = g4.x; sg[1] = g4.y; sg[2] = g4.z; sg[3] = g4.w;
+        sb[0] = b4.x; sb[1] = b4.y; sb[2] = b4.z; sb[3] = b4.w;
+      }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) split_bf16(v[i], hi[i], lo[i]);
-      __nv_bfloat162* oh = (__nv_bfloat162*)(a.out_hi + e * 4);
-      oh[0] = __nv_bfloat162(hi[0], hi[1]);
-      oh[1] = __nv_bfloat162(hi[2], hi[3]);
-      if (a.out_lo) {
-        __nv_bfloat162* ol = (__nv_bfloat162*)(a.out_lo + e * 4);
-        ol[0] = __nv_bfloat162(lo[0], lo[1]);
-        ol[1] = __nv_bfloat162(lo[2], lo[3]);
+      for (int i = 0; i < 4; ++i) {
+        float t = v[i];
+        if (a.mr) t = (t - mean[i]) * rstd[i];
+        if (a.w) t = t * gw[i] + gb[i];
+        t = act_apply(t, a.act);
+        t += ad[i];
+        if (a.spade) t = t * sg[i] + sb[i];
+        v[i] = t;
+        s[i] += t;
+        q[i] = fmaf(t, t, q[i]);
+      }
+      if (a.out_f32) ((float4*)a.out_f32)[e] = make_float4(v[0], v[1], v[2], v[3]);
+      if (a.out_hi) {
+        __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split_bf16(v[i], hi[i], lo[i]);
+        __nv_bfloat162* oh = (__nv_bfloat162*)(a.out_hi + e * 4);
+        oh[0] = __nv_bfloat162(hi[0], hi[1]);
+        oh[1] = __nv_bfloat162(hi[2], hi[3]);
+        if (a.out_lo) {
+          __nv_bfloat162* ol = (__nv_bfloat162*)(a.out_lo + e * 4);
+          ol[0] = __nv_bfloat162(lo[0], lo[1]);
+          ol[1] = __nv_bfloat162(lo[2], lo[3]);
+        }
+      }
+    }
+  }
+  if (a.stats_out) {      // block-uniform
+    __shared__ float red[256][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { red[threadIdx.x][i] = s[i]; red[threadIdx.x][4 + i] = q[i]; }
+    __syncthreads();
+    if (threadIdx.x < C4) {
+      double ds[4] = {0, 0, 0, 0}, dq[4] = {0, 0, 0, 0};
+      for (int l = 0; l < lanes; ++l)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { ds[i] += red[l * C4 + c4][i]; dq[i] += red[l * C4 + c4][4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        atomicAdd(&a.stats_out[((size_t)f * a.C + c4 * 4 + i) * 2 + 0], ds[i]);
+        atomicAdd(&a.stats_out[((size_t)f * a.C + c4 * 4 + i) * 2 + 1], dq[i]);
       }
     }
   }
 }
-void norm_apply(const NormApply& n, cudaStream_t st) {
-  IPK_CHECK(n.C % 4 == 0, IPK_ERR_UNSUPPORTED, "norm_apply: C must be a multiple of 4");
-  NormApplyK a{n.x, n.F, n.C, n.P, n.mr, n.w, n.b, n.act, n.add, n.spade, n.T, n.out_f32, n.out_hi, n.out_lo};
-  long long total = (long long)n.F * n.P * (n.C / 4);
-  if (total == 0) return;
-  norm_apply_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, st>>>(a);
+void norm_apply(const NormApply& n0, cudaStream_t st) {
+  NormApply n = n0;
+  // purely elementwise use on wide rows: view [P][C] as [P*k][C/k]
+  if (!n.mr && !n.w && !n.spade && !n.stats_out)
+    while (n.C > 1024 && n.C % 8 == 0) { n.C /= 2; n.P *= 2; }
+  IPK_CHECK(n.C % 4 == 0 && n.C >= 4 && n.C <= 1024, IPK_ERR_UNSUPPORTED, "norm_apply: C must be a multiple of 4 in [4, 1024] (got %d)", n.C);
+  if ((long long)n.F * n.P == 0) return;
+  const int C4 = n.C / 4;
+  const int lanes = std::max(1, 256 / C4);
+  // <= 64 fp32 accumulations per thread and enough blocks to fill the machine
+  long long ppb = (long long)lanes * 64;
+  const long long want_blocks = 148LL * 8;
+  while (ppb > lanes && (long long)n.F * ((n.P + ppb - 1) / ppb) < want_blocks) ppb /= 2;
+  ppb = std::max<long long>(ppb, lanes);
+  NormApplyK a{n.x, n.F, n.C, n.P, n.mr, n.w, n.b, n.act, n.add, n.spade, n.T, n.out_f32, n.out_hi, n.out_lo, n.stats_out, (int)ppb};
+  dim3 g((unsigned)((n.P + ppb - 1) / ppb), (unsigned)n.F);
+  IPK_CHECK(n.F <= 65535, IPK_ERR_UNSUPPORTED, "norm_apply: too many frames per launch (%d)", n.F);
+  norm_apply_kernel<<<g, 256, 0, st>>>(a);
   IPK_LAUNCH_CHECK();
 }
 

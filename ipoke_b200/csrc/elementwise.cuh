@@ -32,6 +32,8 @@ struct NormApply {
   float* out_f32 = nullptr;      // any of the three outputs may be null
   __nv_bfloat16* out_hi = nullptr;
   __nv_bfloat16* out_lo = nullptr;
+  double* stats_out = nullptr;   // optional [F][C][2]: sum / sum of squares of the values produced, accumulated (zero first);
+                                 // with no output pointer set this is a pure statistics pass
 };
 void norm_apply(const NormApply& a, cudaStream_t st);
 
