@@ -12,6 +12,15 @@ thread_local int64_t g_launches = 0;
 
 void set_last_error(const std::string& m) { g_last_error = m; }
 
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("IPK_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+
 [[noreturn]] void fail(int code, const char* fmt, ...) {
   char buf[1024];
   va_list ap;

@@ -8,6 +8,9 @@
 #include <stdexcept>
 #include <vector>
 #include <algorithm>
+#include <utility>
+#include <cstring>
+#include <cstdlib>
 
 #include "../../include/ipoke_b200.h"
 
@@ -42,6 +45,30 @@ inline void count_launch(int n = 1) { g_launches += n; }
     ::ipk::count_launch();                \
     IPK_CUDA(cudaGetLastError());         \
   } while (0)
+
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every hot kernel is launched with programmatic stream serialization: its CTAs may be scheduled while the previous kernel in
+// the stream drains, run their prologue (barrier init, TMEM allocation, index setup) and then block in pdl_wait() until the
+// previous grid has completed and its writes are visible.  pdl_trigger() lets the NEXT kernel do the same with this one.
+// Kernels launched this way MUST call pdl_wait() before their first global-memory access.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();   // IPK_PDL=0 disables (plain stream-ordered launches)
+
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+  if (e != cudaSuccess) ::ipk::fail(IPK_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  count_launch();
+}
 
 // ---------------------------------------------------------------- optional per-phase device timing
 // When enabled (ipk_prof_enable), every ProfScope brackets the launches issued inside it with CUDA events on the launch

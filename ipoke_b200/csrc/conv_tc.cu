@@ -214,6 +214,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();        // prologue above overlapped the previous kernel's tail; its outputs are visible from here on
+  pdl_trigger();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -457,8 +459,7 @@ static void launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CU
   }
   const long long total = (long long)a.tiles_m * a.tiles_n * (a.nsub > 1 ? a.nsub : a.nsplit);
   const unsigned grid = (unsigned)std::min<long long>(total, sm_count());     // persistent: one CTA per SM
-  conv_tc_kernel<BN, NSPLIT><<<grid, TC_THREADS, smem, st>>>(a_hi, a_lo, w_hi, w_lo, a);
-  IPK_LAUNCH_CHECK();
+  launch_k(conv_tc_kernel<BN, NSPLIT>, dim3(grid), dim3(TC_THREADS), smem, st, a_hi, a_lo, w_hi, w_lo, a);
 }
 
 static int conv_tc_impl(const ConvW& w, const ConvIn& in, const ConvOut& out, const ConvSub* subs, int nsub, int nsplit, cudaStream_t st) {

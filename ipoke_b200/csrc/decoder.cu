@@ -44,6 +44,7 @@ struct ipk_fs {
   float *gn1_w = nullptr, *gn1_b = nullptr, *gn2_w = nullptr, *gn2_b = nullptr;
   std::vector<UpBlock> blocks;
   ConvW out_conv;
+  OutConvPlan* out_direct = nullptr;   // fp32 halo-tile kernel when the last decoder width is 64 (out_conv.cu)
   // workspace
   std::vector<char*> XH, XRH;    // [L] conv-input operands (x | h), (x | r*h): [Mmax][2z] in the engine's storage mode
   std::vector<float*> Hf;        // [L] fp32 hidden state [Mmax][z]
@@ -233,16 +234,21 @@ static void decode_frames(ipk_fs* d, const float* h, int nv, int T, int v0, floa
     // SPADE: GroupNorm(16, affine=False)(out) * (1 + gamma) + beta
     finalize_stats(d->sums, d->mr, F, P, ub.Cout, ub.groups, 1e-5f, st);
     NormApply sp; sp.x = d->bufS; sp.F = F; sp.C = ub.Cout; sp.P = P; sp.mr = d->mr; sp.spade = ub.SP + (size_t)v0 * P * 2 * ub.Cout; sp.T = T;
-    to_operand(d, sp, d->bufA, d->bufA_lo);
+    if (last && d->out_direct) sp.out_f32 = (float*)d->bufA;      // the final conv reads fp32
+    else to_operand(d, sp, d->bufA, d->bufA_lo);
     norm_apply(sp, st);
   }
   // ---- out_conv: 3x3 -> 3 channels + tanh, written straight into the NCHW frame tensor
   {
-    const int Cl = d->cfg.dec_channels[d->nd - 1];
-    ConvIn in; in.p = d->bufA; in.p_lo = d->bufA_lo; in.cstride = Cl; in.F = F; in.H = d->S; in.W = d->S;
-    ConvOut o; o.p = frames; o.mode = OUT_F32_NCHW; o.Ho = d->S; o.Wo = d->S; o.act = ACT_TANH; o.bias = d->out_conv.bias;
     ProfScope ps("dec.out_conv", st);
-    conv_run(d->out_conv, in, o, taps_3x3(), 1, st);
+    if (d->out_direct) {
+      out_conv_run(d->out_direct, (const float*)d->bufA, frames, F, d->S, st);
+    } else {
+      const int Cl = d->cfg.dec_channels[d->nd - 1];
+      ConvIn in; in.p = d->bufA; in.p_lo = d->bufA_lo; in.cstride = Cl; in.F = F; in.H = d->S; in.W = d->S;
+      ConvOut o; o.p = frames; o.mode = OUT_F32_NCHW; o.Ho = d->S; o.Wo = d->S; o.act = ACT_TANH; o.bias = d->out_conv.bias;
+      conv_run(d->out_conv, in, o, taps_3x3(), 1, st);
+    }
   }
 }
 
@@ -406,7 +412,22 @@ extern "C" int ipk_fs_finalize(ipk_fs* d, void* stream) {
     fe = std::max(fe, (size_t)ub.s_in * ub.s_in * ub.Cin);
     d->blocks.push_back(ub);
   }
-  d->out_conv = build_conv3(d, "gen.out_conv.conv.", eng, 3, dc[d->nd - 1], false, 0.f, st);
+  if (dc[d->nd - 1] == OUT_CONV_CIN) {
+    const std::string p = "gen.out_conv.conv.";
+    float* packed = d->pool.alloc<float>(OUT_CONV_PACKED_FLOATS);
+    const float* bias = (const float*)fneed(d, p + "bias", 3).p;
+    if (fhas(d, p + "weight_orig")) {
+      const FsTensor& wo = fneed(d, p + "weight_orig", 3 * 64 * 9);
+      float* sigma = d->pool.alloc<float>(1);
+      spectral_sigma((const float*)wo.p, (const float*)fneed(d, p + "weight_u", 3).p, (const float*)fneed(d, p + "weight_v", 64 * 9).p, sigma, 3, 64, 9, false, st);
+      out_conv_pack((const float*)wo.p, sigma, bias, packed, st);
+    } else {
+      out_conv_pack((const float*)fneed(d, p + "weight", 3 * 64 * 9).p, nullptr, bias, packed, st);
+    }
+    d->out_direct = out_conv_plan_create(packed, st);
+  } else {
+    d->out_conv = build_conv3(d, "gen.out_conv.conv.", eng, 3, dc[d->nd - 1], false, 0.f, st);
+  }
   d->frame_elems = fe;
   // ---- workspace
   const size_t Mmax = (size_t)d->cfg.max_batch * 64;
@@ -532,6 +553,7 @@ extern "C" int ipk_fs_destroy(ipk_fs* d) {
   if (!d) return IPK_OK;
   d->pool.release();
   d->ws.release();
+  if (d->out_direct) out_conv_plan_destroy(d->out_direct);
   delete d;
   return IPK_OK;
 }

@@ -95,6 +95,8 @@ void channel_stats(const float* x, int F, long long P, int C, double* sums, cuda
   IPK_LAUNCH_CHECK();
 }
 __global__ void finalize_stats_kernel(const double* __restrict__ sums, float* __restrict__ mr, int F, long long P, int C, int groups, float eps) {
+  pdl_wait();
+  pdl_trigger();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= F * C) return;
   int f = i / C, c = i % C;
@@ -119,8 +121,7 @@ __global__ void finalize_stats_kernel(const double* __restrict__ sums, float* __
   mr[(size_t)i * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
 }
 void finalize_stats(const double* sums, float* mr, int F, long long P, int C, int groups, float eps, cudaStream_t st) {
-  finalize_stats_kernel<<<cdiv(F * C, 256), 256, 0, st>>>(sums, mr, F, P, C, groups, eps);
-  IPK_LAUNCH_CHECK();
+  launch_k(finalize_stats_kernel, dim3(cdiv(F * C, 256)), dim3(256), 0, st, sums, mr, F, P, C, groups, eps);
 }
 
 // ------------------------------------------------------------------ fused normalise/affine/act/residual/SPADE (+ output stats)
@@ -134,6 +135,8 @@ struct NormApplyK {
 // grid (pixel chunks, F): a block works on `ppb` pixels of ONE frame; thread = (channel quad c4 = tid % C4, pixel lane =
 // tid / C4).  Per-channel constants (mean, rstd, affine) sit in registers; no integer division per element.
 __global__ void __launch_bounds__(256) norm_apply_kernel(const NormApplyK a) {
+  pdl_wait();
+  pdl_trigger();
   const int C4 = a.C >> 2;
   const int f = blockIdx.y;
   const int lanes = 256 / C4;                     // pixel lanes (C4 <= 256)
@@ -232,8 +235,7 @@ void norm_apply(const NormApply& n0, cudaStream_t st) {
   NormApplyK a{n.x, n.F, n.C, n.P, n.mr, n.w, n.b, n.act, n.add, n.spade, n.T, n.out_f32, n.out_hi, n.out_lo, n.stats_out, (int)ppb};
   dim3 g((unsigned)((n.P + ppb - 1) / ppb), (unsigned)n.F);
   IPK_CHECK(n.F <= 65535, IPK_ERR_UNSUPPORTED, "norm_apply: too many frames per launch (%d)", n.F);
-  norm_apply_kernel<<<g, 256, 0, st>>>(a);
-  IPK_LAUNCH_CHECK();
+  launch_k(norm_apply_kernel, g, dim3(256), 0, st, a);
 }
 
 // ------------------------------------------------------------------ operand stores / ConvGRU gates
@@ -248,6 +250,8 @@ __device__ __forceinline__ void store_operand(const OperandDst& d, long long m, 
   }
 }
 __global__ void operand_copy_kernel(const float* __restrict__ src, int scs, int scoff, OperandDst dst, long long M, int C) {
+  pdl_wait();
+  pdl_trigger();
   long long total = M * C;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     int c = (int)(e % C);
@@ -257,11 +261,12 @@ __global__ void operand_copy_kernel(const float* __restrict__ src, int scs, int 
 }
 void operand_copy(const float* src, int scs, int scoff, const OperandDst& dst, long long M, int C, cudaStream_t st) {
   if (M * C == 0) return;
-  operand_copy_kernel<<<grid_for(M * C), 256, 0, st>>>(src, scs, scoff, dst, M, C);
-  IPK_LAUNCH_CHECK();
+  launch_k(operand_copy_kernel, dim3(grid_for(M * C)), dim3(256), 0, st, src, scs, scoff, dst, M, C);
 }
 __global__ void gru_gate1_kernel(const float* __restrict__ raw, const float* __restrict__ Hf, float* __restrict__ U, OperandDst xrh,
                                  long long M, int z) {
+  pdl_wait();
+  pdl_trigger();
   long long total = M * z;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     int c = (int)(e % z);
@@ -273,12 +278,13 @@ __global__ void gru_gate1_kernel(const float* __restrict__ raw, const float* __r
   }
 }
 void gru_gate1(const float* raw, const float* Hf, float* U, const OperandDst& xrh, long long M, int z, cudaStream_t st) {
-  gru_gate1_kernel<<<grid_for(M * z), 256, 0, st>>>(raw, Hf, U, xrh, M, z);
-  IPK_LAUNCH_CHECK();
+  launch_k(gru_gate1_kernel, dim3(grid_for(M * z)), dim3(256), 0, st, raw, Hf, U, xrh, M, z);
 }
 struct OperandDst3 { OperandDst d[3]; int n; };
 __global__ void gru_gate2_kernel(const float* __restrict__ raw, const float* __restrict__ U, float* __restrict__ Hf,
                                  long long M, int z, OperandDst3 dst, float* __restrict__ seq_out, int T, int t) {
+  pdl_wait();
+  pdl_trigger();
   long long total = M * z;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     int c = (int)(e % z);
@@ -300,8 +306,7 @@ void gru_gate2(const float* raw, const float* U, float* Hf, long long M, int z, 
   OperandDst3 d;
   d.n = ndst;
   for (int i = 0; i < ndst && i < 3; ++i) d.d[i] = dst[i];
-  gru_gate2_kernel<<<grid_for(M * z), 256, 0, st>>>(raw, U, Hf, M, z, d, seq_out, T, t);
-  IPK_LAUNCH_CHECK();
+  launch_k(gru_gate2_kernel, dim3(grid_for(M * z)), dim3(256), 0, st, raw, U, Hf, M, z, d, seq_out, T, t);
 }
 
 __global__ void im2col3x3_small_kernel(const float* __restrict__ src, int B, int s, int C, OperandDst dst, int Kfill) {

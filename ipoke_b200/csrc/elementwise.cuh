@@ -62,6 +62,15 @@ void im2col3x3_small(const float* src, int B, int s, int C, const OperandDst& ds
 // F.interpolate(mode='bilinear', align_corners=True): in [B][3][S][S] NCHW -> out [B][s][s][3] NHWC
 void bilinear_nchw_to_nhwc(const float* in, float* out, int B, int C, int S, int s, cudaStream_t st);
 
+// Final decoder conv (3x3, 64 -> 3, tanh, NCHW frames): out_conv.cu
+struct OutConvPlan;
+constexpr int OUT_CONV_CIN = 64;
+constexpr int OUT_CONV_PACKED_FLOATS = 9 * 64 * 3 + 3;
+void out_conv_pack(const float* w_oihw, const float* sigma, const float* bias, float* dst, cudaStream_t st);
+OutConvPlan* out_conv_plan_create(const float* w_dev_packed, cudaStream_t st);
+void out_conv_plan_destroy(OutConvPlan* p);
+void out_conv_run(const OutConvPlan* p, const float* in_nhwc, float* out_nchw, int F, int S, cudaStream_t st);
+
 // weight-norm row scale: oscale[n] = g[n] / ||v[n,:]||_2   (torch.nn.utils.weight_norm, dim=0)
 void weight_norm_scale(const float* v, const float* g, float* oscale, int N, int row, cudaStream_t st);
 // spectral-norm sigma = u^T W_mat v with W_mat = weight viewed [rows][cols] (dim 0) or permuted (dim 1, ConvTranspose)

@@ -589,6 +589,8 @@ __global__ void __launch_bounds__(SEG_THREADS, 1) flow_segment_kernel(const Micr
 
   const int warp = tid >> 5, lane = tid & 31;
   float* gs = state + (size_t)b * 64 * C0;
+  pdl_wait();
+  pdl_trigger();
   // (pixel by warp, channel by lane) loops everywhere below: no integer divisions on the latency chain
   for (int p = warp; p < 64; p += SEG_THREADS / 32)
     for (int c = lane; c < Cs; c += 32) sm.s[p * Cs + c] = c < C ? gs[p * C0 + c] : 0.f;
@@ -749,14 +751,16 @@ void flow_segment_run(const SegmentLaunch& s, bool forward, float* state, int C0
   size_t smem = flow_segment_smem_bytes(s.C, s.has_mcf, mma);
   IPK_CHECK(smem <= 200 * 1024, IPK_ERR_UNSUPPORTED, "flow segment needs %zu bytes of shared memory (C=%d)", smem, s.C);
   const int hm = s.has_mcf ? 1 : 0;
+  const MicroOp* ops = s.ops;
+  const int nops = s.nops, C = s.C;
+  auto go = [&](auto kernel) { launch_k(kernel, dim3(B), dim3(SEG_THREADS), smem, st, ops, nops, C, hm, state, C0, logdet); };
   if (forward) {
-    if (mma) flow_segment_kernel<true, true><<<B, SEG_THREADS, smem, st>>>(s.ops, s.nops, s.C, hm, state, C0, logdet);
-    else flow_segment_kernel<true, false><<<B, SEG_THREADS, smem, st>>>(s.ops, s.nops, s.C, hm, state, C0, logdet);
+    if (mma) go(flow_segment_kernel<true, true>);
+    else go(flow_segment_kernel<true, false>);
   } else {
-    if (mma) flow_segment_kernel<false, true><<<B, SEG_THREADS, smem, st>>>(s.ops, s.nops, s.C, hm, state, C0, logdet);
-    else flow_segment_kernel<false, false><<<B, SEG_THREADS, smem, st>>>(s.ops, s.nops, s.C, hm, state, C0, logdet);
+    if (mma) go(flow_segment_kernel<false, true>);
+    else go(flow_segment_kernel<false, false>);
   }
-  IPK_LAUNCH_CHECK();
 }
 
 // ---------------------------------------------------------------------------------------------- mma fragment packing
