@@ -88,7 +88,8 @@ extern "C" int ipk_prof_report(char* buf, int cap) {
 // defined in flow.cu / decoder.cu
 struct ipk_flow;
 struct ipk_fs;
-int ipk_fs_decode_nhwc(ipk_fs* d, const float* motion_nhwc, const float* x0, float* frames, int B, int T, cudaStream_t st);
+int ipk_fs_decode_nhwc(ipk_fs* d, const float* motion_nhwc, const float* x0, float* frames, int B, int T, cudaStream_t st,
+                       float* frames_host = nullptr, cudaStream_t copy_st = nullptr);
 int ipk_flow_reverse_nhwc(ipk_flow* f, const float* z, const float* cond, const float** state_nhwc, int B, cudaStream_t st);
 
 extern "C" int ipk_version(void) { return IPK_VERSION; }
@@ -112,6 +113,7 @@ namespace {
 struct HostStage {
   float *z = nullptr, *cond = nullptr, *x0 = nullptr, *frames = nullptr;
   size_t nz = 0, nc = 0, nx = 0, nf = 0;
+  cudaStream_t copy_st = nullptr;
   void ensure(float** p, size_t* cap, size_t n) {
     if (*cap >= n) return;
     if (*p) cudaFree(*p);
@@ -146,8 +148,10 @@ extern "C" int ipk_sample_host(ipk_flow* f, ipk_fs* d, const float* z_host, cons
   const float* motion = nullptr;
   int rc = ipk_flow_reverse_nhwc(f, g_stage.z, g_stage.cond, &motion, B, st);
   if (rc != 0) return rc;
-  ipk_fs_decode_nhwc(d, motion, g_stage.x0, g_stage.frames, B, T, st);
-  IPK_CUDA(cudaMemcpyAsync(frames_host, g_stage.frames, nf * 4, cudaMemcpyDeviceToHost, st));
+  // frames leave chunk by chunk on a second stream while the next chunk is decoded
+  if (!g_stage.copy_st) IPK_CUDA(cudaStreamCreateWithFlags(&g_stage.copy_st, cudaStreamNonBlocking));
+  ipk_fs_decode_nhwc(d, motion, g_stage.x0, g_stage.frames, B, T, st, frames_host, g_stage.copy_st);
+  IPK_CUDA(cudaStreamSynchronize(g_stage.copy_st));
   IPK_CUDA(cudaStreamSynchronize(st));
   IPK_CATCH
 }

@@ -44,6 +44,7 @@ struct ipk_fs {
   float *gn1_w = nullptr, *gn1_b = nullptr, *gn2_w = nullptr, *gn2_b = nullptr;
   std::vector<UpBlock> blocks;
   ConvW out_conv;
+  cudaEvent_t chunk_done = nullptr;
   OutConvPlan* out_direct = nullptr;   // fp32 halo-tile kernel when the last decoder width is 64 (out_conv.cu)
   // workspace
   std::vector<char*> XH, XRH;    // [L] conv-input operands (x | h), (x | r*h): [Mmax][2z] in the engine's storage mode
@@ -478,7 +479,10 @@ extern "C" int ipk_fs_finalize(ipk_fs* d, void* stream) {
   IPK_CATCH
 }
 
-static void fs_decode_impl(ipk_fs* d, const float* motion, bool motion_is_nhwc, const float* x0, float* frames, int B, int T, cudaStream_t st) {
+// frames_host / copy_st (optional): every finished chunk of frames is copied to the host on a second stream while the next
+// chunk is being decoded; the caller synchronises copy_st.
+static void fs_decode_impl(ipk_fs* d, const float* motion, bool motion_is_nhwc, const float* x0, float* frames, int B, int T, cudaStream_t st,
+                           float* frames_host = nullptr, cudaStream_t copy_st = nullptr) {
   IPK_CHECK(d && d->finalized, IPK_ERR_STATE, "first stage not finalized");
   IPK_CHECK(B > 0 && B <= d->cfg.max_batch, IPK_ERR_INVALID, "first stage: batch %d outside (0, %d]", B, d->cfg.max_batch);
   IPK_CHECK(T > 0 && T <= d->cfg.max_frames, IPK_ERR_INVALID, "first stage: T %d outside (0, %d]", T, d->cfg.max_frames);
@@ -501,7 +505,14 @@ static void fs_decode_impl(ipk_fs* d, const float* motion, bool motion_is_nhwc, 
   }
   for (int v0 = 0; v0 < B; v0 += d->chunk_videos) {
     int nv = std::min(d->chunk_videos, B - v0);
-    decode_frames(d, d->Hseq + (size_t)v0 * T * 64 * z, nv, T, v0, frames + (size_t)v0 * T * 3 * d->S * d->S, st);
+    const size_t off = (size_t)v0 * T * 3 * d->S * d->S, cnt = (size_t)nv * T * 3 * d->S * d->S;
+    decode_frames(d, d->Hseq + (size_t)v0 * T * 64 * z, nv, T, v0, frames + off, st);
+    if (frames_host) {
+      if (!d->chunk_done) IPK_CUDA(cudaEventCreateWithFlags(&d->chunk_done, cudaEventDisableTiming));
+      IPK_CUDA(cudaEventRecord(d->chunk_done, st));
+      IPK_CUDA(cudaStreamWaitEvent(copy_st, d->chunk_done, 0));
+      IPK_CUDA(cudaMemcpyAsync(frames_host + off, frames + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, copy_st));
+    }
   }
 }
 
@@ -513,8 +524,9 @@ extern "C" int ipk_fs_decode(ipk_fs* d, const float* motion, const float* x0, fl
 }
 
 // internal entry used by ipk_sample: motion already NHWC [B][64][z] on device
-int ipk_fs_decode_nhwc(ipk_fs* d, const float* motion_nhwc, const float* x0, float* frames, int B, int T, cudaStream_t st) {
-  fs_decode_impl(d, motion_nhwc, true, x0, frames, B, T, st);
+int ipk_fs_decode_nhwc(ipk_fs* d, const float* motion_nhwc, const float* x0, float* frames, int B, int T, cudaStream_t st,
+                       float* frames_host, cudaStream_t copy_st) {
+  fs_decode_impl(d, motion_nhwc, true, x0, frames, B, T, st, frames_host, copy_st);
   return 0;
 }
 
@@ -554,6 +566,7 @@ extern "C" int ipk_fs_destroy(ipk_fs* d) {
   d->pool.release();
   d->ws.release();
   if (d->out_direct) out_conv_plan_destroy(d->out_direct);
+  if (d->chunk_done) cudaEventDestroy(d->chunk_done);
   delete d;
   return IPK_OK;
 }

@@ -55,8 +55,14 @@ class PokeMotionSampler:
         device = torch.device(device if device is not None else "cuda:0")
         B = z.shape[0]
         fs = self.first_stage_model
-        zp, cp, xp = self._pin("z", z.shape), self._pin("cond", cond.shape), self._pin("x0", x0.shape)
-        zp.copy_(z); cp.copy_(cond); xp.copy_(x0)
+        def staged(name, t):
+            # already-pinned fp32 host tensors go to the device as they are; anything else is staged through a pinned buffer
+            if t.device.type == "cpu" and t.dtype == torch.float32 and t.is_contiguous() and t.is_pinned():
+                return t
+            buf = self._pin(name, t.shape)
+            buf.copy_(t)
+            return buf
+        zp, cp, xp = staged("z", z), staged("cond", cond), staged("x0", x0)
         out = self._pin("frames", (B, int(length), 3, fs.spatial, fs.spatial))
         fplan = self.flow._ensure_plan(device, B)
         dplan = fs._ensure_plan(device, B, length)
