@@ -38,17 +38,24 @@ struct SegSmem {
   float* act;     // [8][hidS] ELU(hidden) of the current line
   float* p1;      // fast: [4][8][64] 1x1 partials        generic: [8][C2s] params of the line
   float* red;     // [32]
-  __nv_bfloat16* ring;   // mma: [2 planes][3 lines][10 positions (zero halo at 0 and 9)][XS]
-  __nv_bfloat16* actb;   // mma: [2 planes][8 positions][HS] ELU(hidden) of the current line
+  unsigned char* ring;   // mma: [3 lines][10 positions (zero halo at 0 and 9)][XSB bytes], hi/lo interleaved per k-tile
+  unsigned char* actb;   // mma: [8 positions][HSB bytes] ELU(hidden) of the current line
+  uint4* wst;            // mma: [slot][thread] conv fragments of the NEXT MCF, landed by cp.async during the current one
 };
 
 __host__ __device__ inline int seg_hidmax(int C) { return C <= 96 ? 4 * C : (2 * C < 512 ? 2 * C : 512); }
 
-struct SegOffsets { size_t tmp, hterm, pc, act, p1, red, ring, actb, total; };
+struct SegOffsets { size_t tmp, hterm, pc, act, p1, red, ring, actb, wst, total; };
 
 // mma-path geometry: channels padded to 16 per k-tile, rows padded by 8 bf16 so fragment loads are bank-conflict free
-__host__ __device__ inline int mma_xs(int C) { return (C + 15) / 16 * 16 + 8; }          // bf16 per ring position
-__host__ __device__ inline int mma_hs(int C) { return (4 * C + 15) / 16 * 16 + 8; }      // bf16 per act position
+// Operand rows of the mma path: per position, 64 bytes per 16-element k-tile = [t = 0..3][hi: k 2t, 2t+1, 2t+8, 2t+9 | lo: same],
+// so lane (g, t) fetches b0/b1 of both planes with ONE 16-byte load.  Position strides are 64 (mod 128) bytes: the two
+// positions served by one 8-lane LDS.128 phase hit disjoint bank halves.
+__host__ __device__ inline int mma_xsb(int C) { const int n = (C + 15) / 16; return n * 64 + ((n & 1) ? 0 : 64); }          // bytes per ring position
+__host__ __device__ inline int mma_hsb(int C) { const int n = (4 * C + 15) / 16; return n * 64 + ((n & 1) ? 0 : 64); }      // bytes per act position
+// byte offset of element k (0..15) of a k-tile inside its 64-byte block, hi plane (lo plane: + 8)
+__host__ __device__ inline int mma_koff(int k) { return ((k & 7) >> 1) * 16 + (((k >> 3) << 1) | (k & 1)) * 2; }
+__host__ __device__ inline int mma_wst_slots(int C) { return 2 * 6 * ((C + 15) / 16); }     // staged conv fragments (uint4) per thread
 
 __host__ __device__ inline SegOffsets seg_layout(int C, bool has_mcf, bool mma) {
   const int Cs = (C + 3) / 4 * 4;
@@ -58,13 +65,15 @@ __host__ __device__ inline SegOffsets seg_layout(int C, bool has_mcf, bool mma) 
   size_t off = (size_t)64 * Cs;                       // s
   o.tmp = off; off += (size_t)64 * Cs;
   o.hterm = off; off += has_mcf ? (size_t)(fast ? 2 : 1) * 64 * C2s : 0;
-  o.pc = off; off += (has_mcf && fast) ? (size_t)2 * 8 * 128 : 0;
-  o.act = off; off += has_mcf ? (size_t)8 * ((seg_hidmax(C) + 3) / 4 * 4) : 0;
-  o.p1 = off; off += has_mcf ? (fast ? (size_t)4 * 8 * 64 : (size_t)8 * C2s) : 0;
-  o.red = off; off += 32;
   const bool use_mma = has_mcf && fast && mma;
-  o.ring = off; off += use_mma ? (size_t)(2 * 3 * 10 * mma_xs(C)) / 2 : 0;      // bf16 pairs counted in floats
-  o.actb = off; off += use_mma ? (size_t)(2 * 8 * mma_hs(C)) / 2 : 0;
+  o.pc = off; off += (has_mcf && fast && !use_mma) ? (size_t)2 * 8 * 128 : 0;
+  o.act = off; off += (has_mcf && !use_mma) ? (size_t)8 * ((seg_hidmax(C) + 3) / 4 * 4) : 0;
+  o.p1 = off; off += (has_mcf && !use_mma) ? (fast ? (size_t)4 * 8 * 64 : (size_t)8 * C2s) : 0;
+  o.red = off; off += 32;
+  o.ring = off; off += use_mma ? (size_t)(3 * 10 * mma_xsb(C)) / 4 : 0;
+  o.actb = off; off += use_mma ? (size_t)(8 * mma_hsb(C)) / 4 : 0;
+  off = (off + 3) / 4 * 4;
+  o.wst = off; off += use_mma ? (size_t)mma_wst_slots(C) * SEG_THREADS * 4 : 0;     // [slot][thread] uint4
   o.total = off;
   return o;
 }
@@ -253,13 +262,13 @@ __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint4& a, uint32_t
 }
 
 // packed fragment arrays: [m-tile][k-tile][lane] uint4, hi plane then lo plane
+// register slot (tap, ct) = tap*2 + ct holds packed k-tile tap*nct + ct  (tap = tap row * 3 + dv)
 __device__ __forceinline__ void mma_load_wa(const MicroOp& op, McfMmaRegs& r) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int C = op.i1, hid = op.i3;
   const int nmt = (hid + 15) >> 4, nct = (C + 15) >> 4, nkt = 6 * nct;
   const uint4* W = (const uint4*)op.p0;
   const size_t plane = (size_t)nmt * nkt * 32;
-  // register slot (tap, ct) = tap*2 + ct holds packed k-tile tap*nct + ct  (tap = tap row * 3 + dv)
 #pragma unroll
   for (int tap = 0; tap < 6; ++tap)
 #pragma unroll
@@ -268,6 +277,36 @@ __device__ __forceinline__ void mma_load_wa(const MicroOp& op, McfMmaRegs& r) {
         const size_t i = ((size_t)warp * nkt + tap * nct + ct) * 32 + lane;
         r.wa_hi[tap * 2 + ct] = __ldg(W + i);
         r.wa_lo[tap * 2 + ct] = __ldg(W + plane + i);
+      }
+    }
+}
+// the same fragments, global -> this thread's private staging slots (cp.async; joins the caller's commit group)
+__device__ __forceinline__ void mma_stage_wa(const MicroOp& op, uint4* wst) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int C = op.i1, hid = op.i3;
+  const int nmt = (hid + 15) >> 4, nct = (C + 15) >> 4, nkt = 6 * nct;
+  const uint4* W = (const uint4*)op.p0;
+  const size_t plane = (size_t)nmt * nkt * 32;
+  if (warp < nmt) {
+    for (int kt = 0; kt < nkt; ++kt) {
+      const size_t i = ((size_t)warp * nkt + kt) * 32 + lane;
+      cp_async16(wst + (size_t)(2 * kt) * SEG_THREADS + tid, W + i);
+      cp_async16(wst + (size_t)(2 * kt + 1) * SEG_THREADS + tid, W + plane + i);
+    }
+  }
+}
+__device__ __forceinline__ void mma_unstage_wa(const MicroOp& op, const uint4* wst, McfMmaRegs& r) {
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int C = op.i1, hid = op.i3;
+  const int nmt = (hid + 15) >> 4, nct = (C + 15) >> 4;
+#pragma unroll
+  for (int tap = 0; tap < 6; ++tap)
+#pragma unroll
+    for (int ct = 0; ct < 2; ++ct) {
+      if (warp < nmt && ct < nct) {
+        const int kt = tap * nct + ct;
+        r.wa_hi[tap * 2 + ct] = wst[(size_t)(2 * kt) * SEG_THREADS + tid];
+        r.wa_lo[tap * 2 + ct] = wst[(size_t)(2 * kt + 1) * SEG_THREADS + tid];
       }
     }
 }
@@ -294,14 +333,23 @@ __device__ __forceinline__ void mcf_mma(const MicroOp& op, const MicroOp* next, 
   const int order = op.i0, C = op.i1, hid = op.i3;
   const int nct = (C + 15) >> 4;
   const int nmt = (hid + 15) >> 4, nkt1 = nmt, nmt1 = (C + 7) >> 3;
-  const int XS = mma_xs(C), HS = mma_hs(C);
+  const int XSB = mma_xsb(C), HSB = mma_hsb(C);
   const int C2s = (2 * C + 3) / 4 * 4;
-  const int ring_plane = 3 * 10 * XS, act_plane = 8 * HS;
+  // pixel of (line u, position v) = pb + u*pu + v*pv
+  const int pb = order == 1 ? 56 : (order == 3 ? 7 : 0);
+  const int pu = order == 0 ? 8 : (order == 1 ? -8 : (order == 2 ? 1 : -1));
+  const int pv = order < 2 ? 1 : 8;
 
   if (FWD) {  // snapshot x: all lines are computed from the un-transformed input (macow2.py:113-116)
     for (int i = tid; i < 64 * Cs; i += SEG_THREADS) sm.tmp[i] = sm.s[i];
     __syncthreads();
   }
+
+  // phase D constants of this thread: channel c = 8*warp + g, operand slot of c inside its 16-channel k-tile
+  const int c = warp * 8 + g;
+  const int c_ring = (c >> 4) * 64 + mma_koff(c & 15);
+  // phase A epilogue: hidden units n0 = 16*warp + g and n0 + 8 -> act offsets
+  const int a_off0 = warp * 64 + mma_koff(g), a_off1 = warp * 64 + mma_koff(g + 8);
 
   int slot2 = 1, slot1 = 2, slot0 = 0;   // ring slots of lines u-2, u-1, u
   for (int u = 0; u < 8; ++u) {
@@ -317,20 +365,18 @@ __device__ __forceinline__ void mcf_mma(const MicroOp& op, const MicroOp* next, 
         for (int rr = 0; rr < 2; ++rr) {
           const int uu = u - 2 + rr;
           if (uu >= 0) {          // warp-uniform; earlier lines are zero padding
-            const int rowoff = ((rr == 0 ? slot2 : slot1) * 10 + g) * XS + t * 2;
+            const unsigned char* rowp = sm.ring + ((rr == 0 ? slot2 : slot1) * 10 + g) * XSB + t * 16;
 #pragma unroll
             for (int dvi = 0; dvi < 3; ++dvi)
 #pragma unroll
               for (int ct = 0; ct < 2; ++ct) {
                 if (ct < nct) {
                   const int kt = (rr * 3 + dvi) * 2 + ct;
-                  const int off = rowoff + dvi * XS + ct * 16;
-                  const uint32_t b0h = *(const uint32_t*)(sm.ring + off), b1h = *(const uint32_t*)(sm.ring + off + 8);
-                  const uint32_t b0l = *(const uint32_t*)(sm.ring + ring_plane + off), b1l = *(const uint32_t*)(sm.ring + ring_plane + off + 8);
+                  const uint4 bq = *(const uint4*)(rowp + dvi * XSB + ct * 64);     // {b0 hi, b1 hi, b0 lo, b1 lo}
                   const int ch = (dvi & 1) * 3;
-                  mma_bf16(d[ch + 0], r.wa_hi[kt], b0h, b1h);
-                  mma_bf16(d[ch + 1], r.wa_lo[kt], b0h, b1h);
-                  mma_bf16(d[ch + 2], r.wa_hi[kt], b0l, b1l);
+                  mma_bf16(d[ch + 0], r.wa_hi[kt], bq.x, bq.y);
+                  mma_bf16(d[ch + 1], r.wa_lo[kt], bq.x, bq.y);
+                  mma_bf16(d[ch + 2], r.wa_hi[kt], bq.z, bq.w);
                 }
               }
           }
@@ -339,16 +385,20 @@ __device__ __forceinline__ void mcf_mma(const MicroOp& op, const MicroOp* next, 
         for (int j = 0; j < 4; ++j) {
           float h = ((d[0][j] + d[3][j]) + (d[1][j] + d[4][j])) + (d[2][j] + d[5][j]);
           h = h > 0.f ? h : (exp2f(h * 1.4426950408889634f) - 1.0f);     // ELU; abs error ~1e-7, below the bf16x3 operand split
-          const int n = warp * 16 + g + (j >> 1) * 8, pos = t * 2 + (j & 1);
-          if (n < hid) {
+          const int pos = t * 2 + (j & 1);
+          if (warp * 16 + g + (j >> 1) * 8 < hid) {
+            unsigned char* ap = sm.actb + pos * HSB + ((j >> 1) ? a_off1 : a_off0);
             const __nv_bfloat16 hi = __float2bfloat16_rn(h);
-            sm.actb[pos * HS + n] = hi;
-            sm.actb[act_plane + pos * HS + n] = __float2bfloat16_rn(h - __bfloat162float(hi));
+            *(__nv_bfloat16*)ap = hi;
+            *(__nv_bfloat16*)(ap + 8) = __float2bfloat16_rn(h - __bfloat162float(hi));
           }
         }
       }
       __syncthreads();
-      if (u == 7 && next) mma_load_wa(*next, r);     // conv fragments are dead: fetch the next MCF's while this line finishes
+      if (u == 7 && next) {     // conv fragments are dead: take the next MCF's from the staging slots (landed during this MCF)
+        cp_async_wait0();
+        mma_unstage_wa(*next, sm.wst, r);
+      }
     }
     // ---- phase C + D: params^T[o][pos] = sum_k W1x^T[o][k] * act^T[k][pos] + conditioning term; affine transform of line u
     if (warp < nmt1) {
@@ -358,25 +408,23 @@ __device__ __forceinline__ void mcf_mma(const MicroOp& op, const MicroOp* next, 
 #pragma unroll
         for (int j = 0; j < 4; ++j) d[i][j] = 0.f;
       if (u > 0) {
+        const unsigned char* ap = sm.actb + g * HSB + t * 16;
 #pragma unroll
         for (int kt = 0; kt < 8; ++kt) {
           if (kt < nkt1) {
-            const int off = g * HS + kt * 16 + t * 2;
-            const uint32_t b0h = *(const uint32_t*)(sm.actb + off), b1h = *(const uint32_t*)(sm.actb + off + 8);
-            const uint32_t b0l = *(const uint32_t*)(sm.actb + act_plane + off), b1l = *(const uint32_t*)(sm.actb + act_plane + off + 8);
+            const uint4 bq = *(const uint4*)(ap + kt * 64);
             const int ch = (kt & 1) * 3;
-            mma_bf16(d[ch + 0], r.w1_hi[kt], b0h, b1h);
-            mma_bf16(d[ch + 1], r.w1_lo[kt], b0h, b1h);
-            mma_bf16(d[ch + 2], r.w1_hi[kt], b0l, b1l);
+            mma_bf16(d[ch + 0], r.w1_hi[kt], bq.x, bq.y);
+            mma_bf16(d[ch + 1], r.w1_lo[kt], bq.x, bq.y);
+            mma_bf16(d[ch + 2], r.w1_hi[kt], bq.z, bq.w);
           }
         }
       }
-      const int c = warp * 8 + g;
       if (c < C) {
 #pragma unroll
         for (int jp = 0; jp < 2; ++jp) {
           const int pos = t * 2 + jp;
-          const int pix = mcf_pix(order, u, pos);
+          const int pix = pb + u * pu + pos * pv;
           const float mu = ((d[0][jp] + d[3][jp]) + (d[1][jp] + d[4][jp])) + (d[2][jp] + d[5][jp]) + hterm[pix * C2s + c];
           const float ls = ((d[0][2 + jp] + d[3][2 + jp]) + (d[1][2 + jp] + d[4][2 + jp])) + (d[2][2 + jp] + d[5][2 + jp]) + hterm[pix * C2s + C + c];
           // density direction: the reference's own formulation, so the log-det rounding stays correlated with it.
@@ -391,10 +439,10 @@ __device__ __forceinline__ void mcf_mma(const MicroOp& op, const MicroOp* next, 
             xin = (sm.s[pix * Cs + c] - mu) * __frcp_rn(sc + 1e-12f);
             sm.s[pix * Cs + c] = xin;
           }
-          const int ro = (slot0 * 10 + pos + 1) * XS + c;
+          unsigned char* rp = sm.ring + (slot0 * 10 + pos + 1) * XSB + c_ring;
           const __nv_bfloat16 hi = __float2bfloat16_rn(xin);
-          sm.ring[ro] = hi;
-          sm.ring[ring_plane + ro] = __float2bfloat16_rn(xin - __bfloat162float(hi));
+          *(__nv_bfloat16*)rp = hi;
+          *(__nv_bfloat16*)(rp + 8) = __float2bfloat16_rn(xin - __bfloat162float(hi));
         }
       }
     }
@@ -585,7 +633,7 @@ __global__ void __launch_bounds__(SEG_THREADS, 1) flow_segment_kernel(const Micr
   const SegOffsets lo = seg_layout(C, has_mcf != 0, MMA);
   sm.s = smem; sm.tmp = smem + lo.tmp; sm.hterm = smem + lo.hterm; sm.pc = smem + lo.pc; sm.act = smem + lo.act;
   sm.p1 = smem + lo.p1; sm.red = smem + lo.red;
-  sm.ring = (__nv_bfloat16*)(smem + lo.ring); sm.actb = (__nv_bfloat16*)(smem + lo.actb);
+  sm.ring = (unsigned char*)(smem + lo.ring); sm.actb = (unsigned char*)(smem + lo.actb); sm.wst = (uint4*)(smem + lo.wst);
 
   const int warp = tid >> 5, lane = tid & 31;
   float* gs = state + (size_t)b * 64 * C0;
@@ -609,23 +657,23 @@ __global__ void __launch_bounds__(SEG_THREADS, 1) flow_segment_kernel(const Micr
   // first MCF of the segment: start fetching its weights / conditioning term
   typename std::conditional<MMA, McfMmaRegs, McfRegs>::type regs;
   int hbuf = 0;
-  MicroOp nxt;
+  const MicroOp* nxt = nullptr;      // next MCF micro-op (read from global on demand: keeps ~20 registers free)
   int nxt_i = (has_mcf && fast) ? next_mcf(ops, op_begin, nops) : -1;
   if (nxt_i >= 0) {
-    nxt = ops[nxt_i];
-    mcf_prefetch_hterm(nxt, b, sm.hterm);
+    nxt = ops + nxt_i;
+    mcf_prefetch_hterm(*nxt, b, sm.hterm);
     cp_async_commit();
     if constexpr (MMA) {
-      mma_load_wa(nxt, regs);
-      mma_load_w1(nxt, regs);
+      mma_load_wa(*nxt, regs);
+      mma_load_w1(*nxt, regs);
       // zero the operand ring (halo positions and channel padding stay zero for the whole segment) and the act rows
       uint32_t* z = (uint32_t*)sm.ring;
-      const int nz = (int)(lo.total - lo.ring);
+      const int nz = (int)(lo.wst - lo.ring);
       for (int i = tid; i < nz; i += SEG_THREADS) z[i] = 0u;
       __syncthreads();
     } else {
-      mcf_load_wc(nxt, regs);
-      mcf_load_w1(nxt, regs);
+      mcf_load_wc(*nxt, regs);
+      mcf_load_w1(*nxt, regs);
     }
   }
 
@@ -668,16 +716,17 @@ __global__ void __launch_bounds__(SEG_THREADS, 1) flow_segment_kernel(const Micr
           // buffer hbuf.  Queue the NEXT MCF's conditioning term into the other buffer, then wait for ours.
           const int nn = next_mcf(ops, oi + 1, nops);
           if (nn >= 0) {
-            nxt = ops[nn];
-            mcf_prefetch_hterm(nxt, b, sm.hterm + (hbuf ^ 1) * 64 * C2s);
+            nxt = ops + nn;
+            mcf_prefetch_hterm(*nxt, b, sm.hterm + (hbuf ^ 1) * 64 * C2s);
+            if constexpr (MMA) mma_stage_wa(*nxt, sm.wst);     // same commit group: lands while this MCF runs
             cp_async_commit();
             cp_async_wait1();
           } else {
             cp_async_wait0();
           }
           __syncthreads();
-          if constexpr (MMA) mcf_mma<FWD>(op, nn >= 0 ? &nxt : nullptr, regs, sm, sm.hterm + hbuf * 64 * C2s, Cs, ld);
-          else mcf_fast<FWD>(op, nn >= 0 ? &nxt : nullptr, regs, sm, sm.hterm + hbuf * 64 * C2s, Cs, ld);
+          if constexpr (MMA) mcf_mma<FWD>(op, nn >= 0 ? nxt : nullptr, regs, sm, sm.hterm + hbuf * 64 * C2s, Cs, ld);
+          else mcf_fast<FWD>(op, nn >= 0 ? nxt : nullptr, regs, sm, sm.hterm + hbuf * 64 * C2s, Cs, ld);
           hbuf ^= 1;
         } else {
           mcf_generic<FWD>(op, sm, Cs, b, ld);
