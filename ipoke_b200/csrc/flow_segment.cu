@@ -251,7 +251,8 @@ __device__ __forceinline__ void mcf_fast(const MicroOp& op, const MicroOp* next,
 // ---------------------------------------------------------------------------------------------- mma MCF (C <= 32)
 struct McfMmaRegs {
   uint4 wa_hi[12], wa_lo[12];   // conv A fragments of m-tile = warp, k-tile kt = (tap row r, dv, channel tile)
-  uint4 w1_hi[8], w1_lo[8];     // 1x1 A fragments of m-tile = warp (rows g: mu of channel 8*mt+g, rows g+8: its log-scale)
+  uint2 w1_hi[8], w1_lo[8];     // 1x1 A fragments of m-tile = warp: rows 0-3 = mu of channels 4*mt.., rows 4-7 = their
+                                // log-scales, rows 8-15 = zero (only a0 / a2 are stored)
 };
 
 __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint4& a, uint32_t b0, uint32_t b1) {
@@ -313,8 +314,8 @@ __device__ __forceinline__ void mma_unstage_wa(const MicroOp& op, const uint4* w
 __device__ __forceinline__ void mma_load_w1(const MicroOp& op, McfMmaRegs& r) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int C = op.i1, hid = op.i3;
-  const int nmt1 = (C + 7) >> 3, nkt1 = (hid + 15) >> 4;
-  const uint4* W = (const uint4*)op.p1;
+  const int nmt1 = (C + 3) >> 2, nkt1 = (hid + 15) >> 4;
+  const uint2* W = (const uint2*)op.p1;
   const size_t plane = (size_t)nmt1 * nkt1 * 32;
 #pragma unroll
   for (int kt = 0; kt < 8; ++kt) {
@@ -332,7 +333,7 @@ __device__ __forceinline__ void mcf_mma(const MicroOp& op, const MicroOp* next, 
   const int g = lane >> 2, t = lane & 3;
   const int order = op.i0, C = op.i1, hid = op.i3;
   const int nct = (C + 15) >> 4;
-  const int nmt = (hid + 15) >> 4, nkt1 = nmt, nmt1 = (C + 7) >> 3;
+  const int nmt = (hid + 15) >> 4, nkt1 = nmt, nmt1 = (C + 3) >> 2;
   const int XSB = mma_xsb(C), HSB = mma_hsb(C);
   const int C2s = (2 * C + 3) / 4 * 4;
   // pixel of (line u, position v) = pb + u*pu + v*pv
@@ -345,8 +346,9 @@ __device__ __forceinline__ void mcf_mma(const MicroOp& op, const MicroOp* next, 
     __syncthreads();
   }
 
-  // phase D constants of this thread: channel c = 8*warp + g, operand slot of c inside its 16-channel k-tile
-  const int c = warp * 8 + g;
+  // phase D: all eight warps; lane (g, t) finishes channel c = 4*warp + (g & 3) at position 2t + (g >> 2)
+  const int c = warp * 4 + (g & 3);
+  const int dpos = t * 2 + (g >> 2);
   const int c_ring = (c >> 4) * 64 + mma_koff(c & 15);
   // phase A epilogue: hidden units n0 = 16*warp + g and n0 + 8 -> act offsets
   const int a_off0 = warp * 64 + mma_koff(g), a_off1 = warp * 64 + mma_koff(g + 8);
@@ -400,7 +402,9 @@ __device__ __forceinline__ void mcf_mma(const MicroOp& op, const MicroOp* next, 
         mma_unstage_wa(*next, sm.wst, r);
       }
     }
-    // ---- phase C + D: params^T[o][pos] = sum_k W1x^T[o][k] * act^T[k][pos] + conditioning term; affine transform of line u
+    // ---- phase C + D: params^T[o][pos] = sum_k W1x^T[o][k] * act^T[k][pos] + conditioning term; affine transform of line u.
+    // m-tile of a warp: rows 0-3 = mu of its 4 channels, rows 4-7 = their log-scales -> accumulator row g of lane (g, t) holds
+    // columns (positions) 2t, 2t+1; one xor-16 shuffle pairs mu and log-scale, each lane then finishes ONE (channel, position).
     if (warp < nmt1) {
       float d[6][4];
 #pragma unroll
@@ -414,36 +418,37 @@ __device__ __forceinline__ void mcf_mma(const MicroOp& op, const MicroOp* next, 
           if (kt < nkt1) {
             const uint4 bq = *(const uint4*)(ap + kt * 64);
             const int ch = (kt & 1) * 3;
-            mma_bf16(d[ch + 0], r.w1_hi[kt], bq.x, bq.y);
-            mma_bf16(d[ch + 1], r.w1_lo[kt], bq.x, bq.y);
-            mma_bf16(d[ch + 2], r.w1_hi[kt], bq.z, bq.w);
+            const uint4 ahi = make_uint4(r.w1_hi[kt].x, 0u, r.w1_hi[kt].y, 0u), alo = make_uint4(r.w1_lo[kt].x, 0u, r.w1_lo[kt].y, 0u);
+            mma_bf16(d[ch + 0], ahi, bq.x, bq.y);
+            mma_bf16(d[ch + 1], alo, bq.x, bq.y);
+            mma_bf16(d[ch + 2], ahi, bq.z, bq.w);
           }
         }
       }
+      const float v0 = ((d[0][0] + d[3][0]) + (d[1][0] + d[4][0])) + (d[2][0] + d[5][0]);     // row g, position 2t
+      const float v1 = ((d[0][1] + d[3][1]) + (d[1][1] + d[4][1])) + (d[2][1] + d[5][1]);     // row g, position 2t+1
+      const bool is_mu = g < 4;
+      const float got = __shfl_xor_sync(0xffffffffu, is_mu ? v1 : v0, 16);
       if (c < C) {
-#pragma unroll
-        for (int jp = 0; jp < 2; ++jp) {
-          const int pos = t * 2 + jp;
-          const int pix = pb + u * pu + pos * pv;
-          const float mu = ((d[0][jp] + d[3][jp]) + (d[1][jp] + d[4][jp])) + (d[2][jp] + d[5][jp]) + hterm[pix * C2s + c];
-          const float ls = ((d[0][2 + jp] + d[3][2 + jp]) + (d[1][2 + jp] + d[4][2 + jp])) + (d[2][2 + jp] + d[5][2 + jp]) + hterm[pix * C2s + C + c];
-          // density direction: the reference's own formulation, so the log-det rounding stays correlated with it.
-          // sampling direction (latency-critical): 1 + tanh(ls/2) == 2 / (1 + exp(-ls)) on the SFU.
-          const float sc = FWD ? 1.0f + tanhf(0.5f * ls) : 2.0f * __frcp_rn(1.0f + exp2f(-1.4426950408889634f * ls));
-          float xin;       // value of this element in the un-transformed domain: conv input of the following lines
-          if (FWD) {
-            xin = sm.tmp[pix * Cs + c];
-            sm.s[pix * Cs + c] = sc * xin + mu;
-            ld += logf(sc);
-          } else {
-            xin = (sm.s[pix * Cs + c] - mu) * __frcp_rn(sc + 1e-12f);
-            sm.s[pix * Cs + c] = xin;
-          }
-          unsigned char* rp = sm.ring + (slot0 * 10 + pos + 1) * XSB + c_ring;
-          const __nv_bfloat16 hi = __float2bfloat16_rn(xin);
-          *(__nv_bfloat16*)rp = hi;
-          *(__nv_bfloat16*)(rp + 8) = __float2bfloat16_rn(xin - __bfloat162float(hi));
+        const int pix = pb + u * pu + dpos * pv;
+        const float mu = (is_mu ? v0 : got) + hterm[pix * C2s + c];
+        const float ls = (is_mu ? got : v1) + hterm[pix * C2s + C + c];
+        // density direction: the reference's own formulation, so the log-det rounding stays correlated with it.
+        // sampling direction (latency-critical): 1 + tanh(ls/2) == 2 / (1 + exp(-ls)) on the SFU.
+        const float sc = FWD ? 1.0f + tanhf(0.5f * ls) : 2.0f * __frcp_rn(1.0f + exp2f(-1.4426950408889634f * ls));
+        float xin;       // value of this element in the un-transformed domain: conv input of the following lines
+        if (FWD) {
+          xin = sm.tmp[pix * Cs + c];
+          sm.s[pix * Cs + c] = sc * xin + mu;
+          ld += logf(sc);
+        } else {
+          xin = (sm.s[pix * Cs + c] - mu) * __frcp_rn(sc + 1e-12f);
+          sm.s[pix * Cs + c] = xin;
         }
+        unsigned char* rp = sm.ring + (slot0 * 10 + dpos + 1) * XSB + c_ring;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(xin);
+        *(__nv_bfloat16*)rp = hi;
+        *(__nv_bfloat16*)(rp + 8) = __float2bfloat16_rn(xin - __bfloat162float(hi));
       }
     }
     if (u == 7 && next) mma_load_w1(*next, r);
@@ -851,17 +856,17 @@ __global__ void pack_mcf_mma_conv_kernel(const float* __restrict__ w, uint32_t* 
     dst[(size_t)total + e] = lo;
   }
 }
-// 1x1 weights v[2C][row] (weight-norm scale os[2C]) columns [0, hid) -> fragments [m-tile][k-tile][lane][4]:
-// m-tile mt rows g -> output mt*8+g (mu of that channel), rows g+8 -> output C + mt*8+g (its log-scale)
+// 1x1 weights v[2C][row] (weight-norm scale os[2C]) columns [0, hid) -> fragments [m-tile][k-tile][lane] uint2 = (a0, a2):
+// m-tile mt rows 0-3 -> outputs 4*mt + r (mu), rows 4-7 -> outputs C + 4*mt + r - 4 (log-scale); rows 8-15 are zero and not stored
 __global__ void pack_mcf_mma_1x1_kernel(const float* __restrict__ v, const float* __restrict__ os, uint32_t* __restrict__ dst, int hid, int C, int row) {
-  const int nmt1 = (C + 7) / 8, nkt1 = (hid + 15) / 16;
-  const int total = nmt1 * nkt1 * 32 * 4;
+  const int nmt1 = (C + 3) / 4, nkt1 = (hid + 15) / 16;
+  const int total = nmt1 * nkt1 * 32 * 2;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-    const int j = e & 3, lane = (e >> 2) & 31, kt = (e >> 7) % nkt1, mt = (e >> 7) / nkt1;
+    const int j = e & 1, lane = (e >> 1) & 31, kt = (e >> 6) % nkt1, mt = (e >> 6) / nkt1;
     const int g = lane >> 2, t = lane & 3;
-    const int c = mt * 8 + g;
-    const int o = (j & 1) ? C + c : c;
-    const int kk = kt * 16 + t * 2 + (j >> 1) * 8;
+    const int c = mt * 4 + (g & 3);
+    const int o = (g >= 4) ? C + c : c;
+    const int kk = kt * 16 + t * 2 + j * 8;
     float x[2];
     for (int q = 0; q < 2; ++q) x[q] = (c < C && kk + q < hid) ? v[(size_t)o * row + kk + q] * os[o] : 0.f;
     uint32_t hi, lo;
@@ -871,7 +876,7 @@ __global__ void pack_mcf_mma_1x1_kernel(const float* __restrict__ v, const float
   }
 }
 size_t mcf_mma_conv_words(int C) { return (size_t)((4 * C + 15) / 16) * (6 * ((C + 15) / 16)) * 128 * 2; }
-size_t mcf_mma_1x1_words(int C) { return (size_t)((C + 7) / 8) * ((4 * C + 15) / 16) * 128 * 2; }
+size_t mcf_mma_1x1_words(int C) { return (size_t)((C + 3) / 4) * ((4 * C + 15) / 16) * 64 * 2; }
 void pack_mcf_mma(const float* shift_w, const float* v, const float* os, uint32_t* conv_dst, uint32_t* x1_dst, int hid, int C,
                   int kh, int kw, int order, int row, cudaStream_t st) {
   pack_mcf_mma_conv_kernel<<<std::max(1, std::min(64, (int)(mcf_mma_conv_words(C) / 2 + 255) / 256)), 256, 0, st>>>(shift_w, conv_dst, hid, C, kh, kw, order);
