@@ -32,6 +32,9 @@ UNIT = "videos/s"
 # algorithmic work: per 16-frame 128^2 video, C0 = 32
 GFLOP_PER_VIDEO_MIN = 260.8
 NICE_CONV2_FLOP_PER_PIXEL = 2.0 * 2048 * 2048          # one 1x1 2048->2048 conv output pixel (2 flop / MAC)
+# dram__bytes_read.sum + dram__bytes_write.sum of one NICE conv2 launch at B=64, fp32 mode, from the ncu --set full capture
+# summarised in profiles/r01_ncu_summary.md (50.5 MB read + 2.2..3.1 MB written; algorithmic reads are 50.4 MB)
+NCU_CONV2_TRAFFIC_BYTES = {("fp32", 64): 53.1e6}
 
 
 def parse():
@@ -303,7 +306,7 @@ def run_ours(a):
             flop = NICE_CONV2_FLOP_PER_PIXEL * B * 64            # algorithmic: 2*M*N*K with M = B*64 pixels
             ach = flop / (t / c * 1e-3) / 1e12
             roofline = {"kernel": "conv_tc_kernel (NICE coupling conv2: 1x1 2048->2048 implicit GEMM, M=B*64)", "bound": "tensor",
-                        "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                        "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": NCU_CONV2_TRAFFIC_BYTES.get((a.precision, B)),
                         "launches_per_step": c // nprof, "avg_launch_ms": t / c, "peak_source": peak_src,
                         "note": "algorithmic FLOPs (1x); fp32 mode issues 3 bf16 MMAs per product (bf16x3), so its ceiling is 1/3 of the bf16 peak"
                                 if a.precision == "fp32" else "algorithmic FLOPs"}
