@@ -24,7 +24,8 @@ constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
-constexpr size_t TC_SMEM_BUDGET = 200 * 1024;
+constexpr size_t TC_SMEM_BUDGET = 192 * 1024;      // pipeline stages
+constexpr size_t TC_EPI_STAGE_BYTES = 4096;          // per epilogue warp: 32 rows x 128 B transpose buffer (xor-swizzled)
 
 constexpr int TC_MAX_SUB = 4;
 struct TcSub {                    // one tap list + output phase (a parity class of a transposed conv; plain convs have one)
@@ -189,6 +190,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B needs 1024-byte alignment
+  uint8_t* epi_stage = smem + (size_t)a.stages * STAGE_BYTES;                      // 8 x 4 KB epilogue transpose buffers
   __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
@@ -308,6 +310,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const size_t opix = ((size_t)f * a.Ho + (size_t)oy) * a.Wo + (size_t)ox;
       const size_t zoff = a.nsub > 1 ? 0 : (size_t)z * a.split_stride;
 
+      // rows this lane stores in the transposed (coalesced) write-out: row_i = lane/8 + 4*i; their output pixels come from
+      // the lanes that own them (all-ones = row outside the image)
+      unsigned long long trow[8];
+      if constexpr (EPI_CHUNK == 32) {
+        const unsigned long long mine = valid ? (unsigned long long)opix : ~0ull;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) trow[i] = __shfl_sync(0xffffffffu, mine, (lane >> 3) + 4 * i);
+      }
+
       mbar_wait(&tmem_full_bar[as], aph);
       tc_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
@@ -324,10 +335,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
           for (int j = 0; j < EPI_CHUNK; ++j) v[j] = __uint_as_float(rr[j]);
         }
-        if (!valid) continue;
         const int oi = (a.split_col > 0 && n0 + c >= a.split_col) ? 1 : 0;     // warp-uniform: destination of this chunk
         const TcOut& od = a.o[oi];
-        const size_t ocol = opix * od.cstride + od.coff + (size_t)(n0 + c - (oi ? a.split_col : 0));
+        const size_t colbase = (size_t)od.coff + (size_t)(n0 + c - (oi ? a.split_col : 0));
         if (a.bias) {
           const float4* b4 = (const float4*)(a.bias + n0 + c);
 #pragma unroll
@@ -338,37 +348,66 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           }
         }
         act_tile<EPI_CHUNK>(v, od.act);
-        if (od.mode == OUT_F32_NHWC) {
-          float4* p = (float4*)((float*)od.out + zoff + ocol);
-#pragma unroll
-          for (int j = 0; j < EPI_CHUNK / 4; ++j)
-            if (4 * j < ncols) p[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        } else if (od.mode == OUT_F32_NCHW) {
+        if (od.mode == OUT_F32_NCHW) {
           // frames at the ABI edge: [f][N][Ho][Wo]; consecutive lanes are consecutive x -> coalesced per channel
+          if (valid) {
 #pragma unroll
-          for (int j = 0; j < EPI_CHUNK; ++j) {
-            const int n = n0 + c + j;
-            if (n < a.N) ((float*)od.out)[(((size_t)f * a.N + n) * a.Ho + oy) * a.Wo + ox] = v[j];
+            for (int j = 0; j < EPI_CHUNK; ++j) {
+              const int n = n0 + c + j;
+              if (n < a.N) ((float*)od.out)[(((size_t)f * a.N + n) * a.Ho + oy) * a.Wo + ox] = v[j];
+            }
           }
+        } else if (EPI_CHUNK == 32 && od.mode == OUT_F32_NHWC) {
+          // ---- fp32 rows: transpose through shared memory: lane = row on the way in, 8 lanes = one 128-byte row segment on the
+          //      way out, so every global store instruction writes full, contiguous sectors (4 rows x 128 B).  (Measured: a win
+          //      for fp32 outputs; for the bf16 operand planes the extra instructions cost more than the scattered 32-byte
+          //      stores, so those keep the direct path below.)
+          uint8_t* stg = epi_stage + (size_t)(warp - 2) * TC_EPI_STAGE_BYTES + lane * 128;
+          const int sw = lane & 7;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) *(float4*)(stg + ((j ^ sw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          __syncwarp();
+          const uint8_t* rd = epi_stage + (size_t)(warp - 2) * TC_EPI_STAGE_BYTES;
+          const int seg = lane & 7;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = (lane >> 3) + 4 * i;
+            if (trow[i] == ~0ull) continue;
+            const uint4 dv = *(const uint4*)(rd + row * 128 + ((seg ^ (row & 7)) << 4));
+            const size_t o = (size_t)trow[i] * od.cstride + colbase;
+            if (seg * 4 < ncols) *(uint4*)((float*)od.out + zoff + o + seg * 4) = dv;
+          }
+          __syncwarp();       // staging rows are rewritten by the next chunk
         } else {
-          uint32_t hi[EPI_CHUNK / 2], lo[EPI_CHUNK / 2];
+          // bf16 operand planes, and narrow tiles (BN = 32): direct row-per-lane stores
+          if (valid) {
+            const size_t ocol = opix * od.cstride + colbase;
+            if (od.mode == OUT_F32_NHWC) {
+              float4* p = (float4*)((float*)od.out + zoff + ocol);
 #pragma unroll
-          for (int j = 0; j < EPI_CHUNK / 2; ++j) {
-            const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-            const float2 hf = __bfloat1622float2(hh);
-            const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
-            hi[j] = *(const uint32_t*)&hh;
-            lo[j] = *(const uint32_t*)&ll;
-          }
-          uint4* ph4 = (uint4*)((__nv_bfloat16*)od.out + ocol);
+              for (int j = 0; j < EPI_CHUNK / 4; ++j)
+                if (4 * j < ncols) p[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
+              uint32_t hi[EPI_CHUNK / 2], lo[EPI_CHUNK / 2];
 #pragma unroll
-          for (int j = 0; j < EPI_CHUNK / 8; ++j)
-            if (8 * j < ncols) ph4[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-          if (od.mode == OUT_BF16_SPLIT) {
-            uint4* pl4 = (uint4*)((__nv_bfloat16*)od.out_lo + ocol);
+              for (int j = 0; j < EPI_CHUNK / 2; ++j) {
+                const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                const float2 hf = __bfloat1622float2(hh);
+                const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
+                hi[j] = *(const uint32_t*)&hh;
+                lo[j] = *(const uint32_t*)&ll;
+              }
+              uint4* ph4 = (uint4*)((__nv_bfloat16*)od.out + ocol);
 #pragma unroll
-            for (int j = 0; j < EPI_CHUNK / 8; ++j)
-              if (8 * j < ncols) pl4[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+              for (int j = 0; j < EPI_CHUNK / 8; ++j)
+                if (8 * j < ncols) ph4[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+              if (od.mode == OUT_BF16_SPLIT) {
+                uint4* pl4 = (uint4*)((__nv_bfloat16*)od.out_lo + ocol);
+#pragma unroll
+                for (int j = 0; j < EPI_CHUNK / 8; ++j)
+                  if (8 * j < ncols) pl4[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+              }
+            }
           }
         }
       }
@@ -451,10 +490,10 @@ static void launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CU
   constexpr int STAGE_BYTES = (NSPLIT == 3 ? 2 : 1) * (TC_BM * TC_BK * 2 + BN * TC_BK * 2);
   int stages = (int)std::min<size_t>(8, TC_SMEM_BUDGET / STAGE_BYTES);
   a.stages = stages;
-  size_t smem = (size_t)stages * STAGE_BYTES + 1024;
+  size_t smem = (size_t)stages * STAGE_BYTES + 1024 + TC_EPI_WARPS * TC_EPI_STAGE_BYTES;
   static bool attr_set = false;
   if (!attr_set) {
-    IPK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TC_SMEM_BUDGET + 1024)));
+    IPK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TC_SMEM_BUDGET + 1024 + TC_EPI_WARPS * TC_EPI_STAGE_BYTES)));
     attr_set = true;
   }
   const long long total = (long long)a.tiles_m * a.tiles_n * (a.nsub > 1 ? a.nsub : a.nsplit);
