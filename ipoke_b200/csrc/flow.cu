@@ -77,6 +77,10 @@ struct ipk_flow {
   int hterm_cols = 0, hstride = 0;
   void* E = nullptr; void* E_lo = nullptr;   // ELU(cond) operand [M][hch]
   float* Hterm = nullptr;
+  // two half-batches on two streams (see run_program)
+  bool dual_stream = false;
+  cudaStream_t st2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int K1pad_max = 0, Npad3_max = 0;
   int act_mode = OUT_F32_NHWC;
 };
@@ -372,28 +376,35 @@ static void upload_programs(ipk_flow* f, std::vector<Stage>& stages, cudaStream_
   IPK_CUDA(cudaStreamSynchronize(st));
 }
 
-static void run_nice_net(ipk_flow* f, const NiceLayer& n, int B, cudaStream_t st) {
-  const int M = B * 64, Hd = f->Hd;
+// element size of one operand plane row entry (fp32 rows, or bf16 planes)
+static inline size_t act_esz(const ipk_flow* f) { return f->act_mode == OUT_F32_NHWC ? 4 : 2; }
+static inline void* poff(void* p, size_t bytes) { return p ? (char*)p + bytes : nullptr; }
+
+// the coupling network of samples [b0, b0 + nb): every workspace buffer is indexed by pixel row, so a batch slice is a
+// pointer offset
+static void run_nice_net(ipk_flow* f, const NiceLayer& n, int b0, int nb, cudaStream_t st) {
+  const int M = nb * 64, Hd = f->Hd;
+  const size_t r0 = (size_t)b0 * 64, es = act_esz(f);
   const long long Mmax = (long long)f->cfg.max_batch * 64;
   // conv1 (im2col GEMM) + ELU
   {
-    ConvIn in; in.p = f->A1; in.p_lo = f->A1_lo; in.cstride = n.K1pad; in.F = M; in.H = 1; in.W = 1;
-    ConvOut out; out.p = f->H1; out.p_lo = f->H1_lo; out.mode = f->act_mode; out.cstride = Hd; out.Ho = 1; out.Wo = 1; out.act = ACT_ELU;
+    ConvIn in; in.p = poff(f->A1, r0 * n.K1pad * es); in.p_lo = poff(f->A1_lo, r0 * n.K1pad * es); in.cstride = n.K1pad; in.F = M; in.H = 1; in.W = 1;
+    ConvOut out; out.p = poff(f->H1, r0 * Hd * es); out.p_lo = poff(f->H1_lo, r0 * Hd * es); out.mode = f->act_mode; out.cstride = Hd; out.Ho = 1; out.Wo = 1; out.act = ACT_ELU;
     ProfScope ps("flow.nice.conv1", st);
     conv_run(n.c1, in, out, taps_1x1(), 1, st);
   }
   // conv2 (1x1) + ELU
   {
-    ConvIn in; in.p = f->H1; in.p_lo = f->H1_lo; in.cstride = Hd; in.F = M; in.H = 1; in.W = 1;
-    ConvOut out; out.p = f->H2; out.p_lo = f->H2_lo; out.mode = f->act_mode; out.cstride = Hd; out.Ho = 1; out.Wo = 1; out.act = ACT_ELU;
+    ConvIn in; in.p = poff(f->H1, r0 * Hd * es); in.p_lo = poff(f->H1_lo, r0 * Hd * es); in.cstride = Hd; in.F = M; in.H = 1; in.W = 1;
+    ConvOut out; out.p = poff(f->H2, r0 * Hd * es); out.p_lo = poff(f->H2_lo, r0 * Hd * es); out.mode = f->act_mode; out.cstride = Hd; out.Ho = 1; out.Wo = 1; out.act = ACT_ELU;
     ProfScope ps("flow.nice.conv2", st);
     conv_run(n.c2, in, out, taps_1x1(), 1, st);
   }
   // conv3: all nine tap responses in one GEMM, split-K into fp32 partial slices; bias, the 3x3 gather and the affine
   // transform happen in the next segment
   {
-    ConvIn in; in.p = f->H2; in.p_lo = f->H2_lo; in.cstride = Hd; in.F = M; in.H = 1; in.W = 1;
-    ConvOut out; out.p = f->partials; out.mode = OUT_F32_NHWC; out.cstride = n.c3.Npad; out.Ho = 1; out.Wo = 1;
+    ConvIn in; in.p = poff(f->H2, r0 * Hd * es); in.p_lo = poff(f->H2_lo, r0 * Hd * es); in.cstride = Hd; in.F = M; in.H = 1; in.W = 1;
+    ConvOut out; out.p = f->partials + r0 * n.c3.Npad; out.mode = OUT_F32_NHWC; out.cstride = n.c3.Npad; out.Ho = 1; out.Wo = 1;
     out.split_stride = Mmax * f->Npad3_max;
     ProfScope ps("flow.nice.conv3", st);
     const int ns = conv_run(n.c3, in, out, taps_1x1(), n.nsplit3, st);
@@ -403,29 +414,52 @@ static void run_nice_net(ipk_flow* f, const NiceLayer& n, int B, cudaStream_t st
 
 // Hterm[B*64][hstride] = bias + W1h_all * ELU(cond): the conditioning input of every MCF's 1x1 (MCFBlock.forward,
 // macow_utils.py:429-432: cat -> ELU -> 1x1 splits into a state part and this state-independent part)
-static void run_hterm(ipk_flow* f, int B, cudaStream_t st) {
+static void run_hterm(ipk_flow* f, int b0, int nb, cudaStream_t st) {
   if (f->hterm_cols == 0) return;
   ProfScope ps("flow.hterm_gemm", st);
-  const long long M = (long long)B * 64;
-  NormApply e; e.x = f->cond; e.F = 1; e.P = M; e.C = f->hch; e.act = ACT_ELU;
-  if (f->hterm_w.engine == IPK_PREC_FP32_SIMT) e.out_f32 = (float*)f->E;
-  else { e.out_hi = (__nv_bfloat16*)f->E; e.out_lo = (__nv_bfloat16*)f->E_lo; }
+  const long long M = (long long)nb * 64;
+  const size_t r0 = (size_t)b0 * 64;
+  const bool simt = f->hterm_w.engine == IPK_PREC_FP32_SIMT;
+  const size_t es = simt ? 4 : 2;
+  NormApply e; e.x = f->cond + r0 * f->hch; e.F = 1; e.P = M; e.C = f->hch; e.act = ACT_ELU;
+  if (simt) e.out_f32 = (float*)poff(f->E, r0 * f->hch * es);
+  else { e.out_hi = (__nv_bfloat16*)poff(f->E, r0 * f->hch * es); e.out_lo = (__nv_bfloat16*)poff(f->E_lo, r0 * f->hch * es); }
   norm_apply(e, st);
-  ConvIn in; in.p = f->E; in.p_lo = f->E_lo; in.cstride = f->hch; in.F = (int)M; in.H = 1; in.W = 1;
-  ConvOut out; out.p = f->Hterm; out.mode = OUT_F32_NHWC; out.cstride = f->hstride; out.Ho = 1; out.Wo = 1; out.bias = f->hterm_w.bias;
+  ConvIn in; in.p = poff(f->E, r0 * f->hch * es); in.p_lo = poff(f->E_lo, r0 * f->hch * es); in.cstride = f->hch; in.F = (int)M; in.H = 1; in.W = 1;
+  ConvOut out; out.p = f->Hterm + r0 * f->hstride; out.mode = OUT_F32_NHWC; out.cstride = f->hstride; out.Ho = 1; out.Wo = 1; out.bias = f->hterm_w.bias;
   conv_run(f->hterm_w, in, out, taps_1x1(), 1, st);
 }
 
-static void run_program(ipk_flow* f, std::vector<Stage>& stages, bool fwd, int B, cudaStream_t st) {
-  run_hterm(f, B, st);
+static void run_program_slice(ipk_flow* f, std::vector<Stage>& stages, bool fwd, int b0, int nb, cudaStream_t st) {
+  run_hterm(f, b0, nb, st);
   for (Stage& s : stages) {
     SegmentLaunch sl{s.d_ops, (int)s.host_ops.size(), s.C, s.has_mcf, f->cfg.precision != IPK_PREC_FP32_SIMT};
     {
       ProfScope ps(s.has_mcf ? "flow.segment.mcf" : "flow.segment.light", st);
-      flow_segment_run(sl, fwd, f->state, f->C0, f->logdet_ws, B, st);
+      flow_segment_run(sl, fwd, f->state, f->C0, f->logdet_ws, b0, nb, st);
     }
-    if (s.nice_id >= 0) run_nice_net(f, f->nices[s.nice_id], B, st);
+    if (s.nice_id >= 0) run_nice_net(f, f->nices[s.nice_id], b0, nb, st);
   }
+}
+
+// Samples are independent, and the flow alternates between kernels that fill the machine (coupling GEMMs) and kernels that
+// cannot (one CTA per sample on the 6 400-step MCF chain).  IPK_FLOW_DUAL_STREAM=1 runs large batches as two half-batches on
+// two streams so one half's GEMMs can take the SMs the other half's MCF lines leave idle.  It is OFF by default: the MCF
+// chain is latency- not throughput-bound, so every half still pays the full chain, and the persistent 225 KB-smem GEMM CTAs
+// do not co-reside with segment CTAs.
+static void run_program(ipk_flow* f, std::vector<Stage>& stages, bool fwd, int B, cudaStream_t st) {
+  const bool split = f->dual_stream && B >= 16 && !Prof::enabled();
+  if (!split) {
+    run_program_slice(f, stages, fwd, 0, B, st);
+    return;
+  }
+  const int nbA = (B + 1) / 2;
+  IPK_CUDA(cudaEventRecord(f->ev_fork, st));
+  IPK_CUDA(cudaStreamWaitEvent(f->st2, f->ev_fork, 0));
+  run_program_slice(f, stages, fwd, 0, nbA, st);
+  run_program_slice(f, stages, fwd, nbA, B - nbA, f->st2);
+  IPK_CUDA(cudaEventRecord(f->ev_join, f->st2));
+  IPK_CUDA(cudaStreamWaitEvent(st, f->ev_join, 0));
 }
 
 }  // namespace ipk
@@ -515,6 +549,13 @@ extern "C" int ipk_flow_finalize(ipk_flow* f, void* stream) {
   upload_programs(f, f->prog_fwd, st);
   upload_programs(f, f->prog_inv, st);
   IPK_CUDA(cudaStreamSynchronize(st));
+  {
+    const char* e = getenv("IPK_FLOW_DUAL_STREAM");
+    f->dual_stream = e && e[0] == '1';     // measured on B200 at B=64: 85.6 ms/step with, 82.2 without -> off by default
+    IPK_CUDA(cudaStreamCreateWithFlags(&f->st2, cudaStreamNonBlocking));
+    IPK_CUDA(cudaEventCreateWithFlags(&f->ev_fork, cudaEventDisableTiming));
+    IPK_CUDA(cudaEventCreateWithFlags(&f->ev_join, cudaEventDisableTiming));
+  }
   f->tensors.clear();
   f->finalized = true;
   IPK_CATCH
@@ -548,6 +589,9 @@ extern "C" int ipk_flow_destroy(ipk_flow* f) {
   if (!f) return IPK_OK;
   f->pool.release();
   f->ws.release();
+  if (f->st2) cudaStreamDestroy(f->st2);
+  if (f->ev_fork) cudaEventDestroy(f->ev_fork);
+  if (f->ev_join) cudaEventDestroy(f->ev_join);
   delete f;
   return IPK_OK;
 }

@@ -627,10 +627,10 @@ __device__ __forceinline__ int next_mcf(const MicroOp* __restrict__ ops, int fro
 template <bool FWD, bool MMA>
 __global__ void __launch_bounds__(SEG_THREADS, 1) flow_segment_kernel(const MicroOp* __restrict__ ops, int nops, int C, int has_mcf,
                                                                        float* __restrict__ state, int C0,
-                                                                       float* __restrict__ logdet) {
+                                                                       float* __restrict__ logdet, int b0) {
   extern __shared__ __align__(16) float smem[];
   const int tid = threadIdx.x;
-  const int b = blockIdx.x;
+  const int b = blockIdx.x + b0;
   const int Cs = (C + 3) / 4 * 4;
   const int C2s = (2 * C + 3) / 4 * 4;
   const bool fast = C <= FAST_MAXC;
@@ -799,7 +799,8 @@ void flow_segment_init() {
   IPK_CUDA(cudaFuncSetAttribute(flow_segment_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 }
 
-void flow_segment_run(const SegmentLaunch& s, bool forward, float* state, int C0, float* logdet, int B, cudaStream_t st) {
+void flow_segment_run(const SegmentLaunch& s, bool forward, float* state, int C0, float* logdet, int b0, int nb, cudaStream_t st) {
+  const int B = nb;
   if (s.nops == 0 || B == 0) return;
   const bool mma = s.mma && s.has_mcf && s.C <= FAST_MAXC;
   size_t smem = flow_segment_smem_bytes(s.C, s.has_mcf, mma);
@@ -807,7 +808,7 @@ void flow_segment_run(const SegmentLaunch& s, bool forward, float* state, int C0
   const int hm = s.has_mcf ? 1 : 0;
   const MicroOp* ops = s.ops;
   const int nops = s.nops, C = s.C;
-  auto go = [&](auto kernel) { launch_k(kernel, dim3(B), dim3(SEG_THREADS), smem, st, ops, nops, C, hm, state, C0, logdet); };
+  auto go = [&](auto kernel) { launch_k(kernel, dim3(B), dim3(SEG_THREADS), smem, st, ops, nops, C, hm, state, C0, logdet, b0); };
   if (forward) {
     if (mma) go(flow_segment_kernel<true, true>);
     else go(flow_segment_kernel<true, false>);

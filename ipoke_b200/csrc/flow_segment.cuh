@@ -46,8 +46,8 @@ struct SegmentLaunch {
 
 constexpr int MAX_NSPLIT = 9;   // upper bound on the split-K slices of a NICE conv3
 
-// state: [B][64][C0] fp32 NHWC (in place); logdet: [B] (forward only, accumulated)
-void flow_segment_run(const SegmentLaunch& s, bool forward, float* state, int C0, float* logdet, int B, cudaStream_t st);
+// state: [*][64][C0] fp32 NHWC (in place); logdet: [*] (forward only, accumulated); processes samples [b0, b0 + nb)
+void flow_segment_run(const SegmentLaunch& s, bool forward, float* state, int C0, float* logdet, int b0, int nb, cudaStream_t st);
 size_t flow_segment_smem_bytes(int C, bool has_mcf, bool mma);
 // mma.sync A-fragment packing of one MCF (see flow_segment.cu); sizes in 32-bit words (hi + lo planes)
 size_t mcf_mma_conv_words(int C);
