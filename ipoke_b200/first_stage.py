@@ -91,17 +91,21 @@ class SpadeCondMotionDecoder(nn.Module):
         self.chunk_videos = int(config.get("ipk_chunk_videos", 0))
         self._plan = None
         self._plan_key = None
+        self._plist = None
 
     def invalidate(self):
         self._plan = None
         self._plan_key = None
+        self._plist = None
 
     def _ensure_plan(self, device, batch, frames=1):
         if batch > self.max_batch or frames > self.max_frames:
             self.max_batch = max(self.max_batch, int(batch))
             self.max_frames = max(self.max_frames, int(frames))
             self.invalidate()
-        key = (device, self.precision, self.max_batch, self.max_frames, sum(int(q._version) for q in self.parameters()))
+        if self._plist is None:
+            self._plist = list(self.parameters())
+        key = (device, self.precision, self.max_batch, self.max_frames, sum(q._version for q in self._plist))
         if self._plan is not None and self._plan_key == key:
             return self._plan
         if device.type != "cuda":
