@@ -23,6 +23,13 @@ struct ConvOut {
   // cstride / coff / act; column index rebased to n - split_col); pixel mapping and bias array are shared
   const ConvOut* second = nullptr;
   int split_col = 0;                  // multiple of 32
+  // optional fused residual branch + output statistics (tensor-core engine, fp32 NHWC output, N >= 64):
+  //   out = act(conv + bias) + res_act((res - mean) * rstd)      with res[pix][res_cstride] fp32 in the output's pixel grid and
+  //   (mean, rstd) = res_mr[frame][N][2]; and stats[frame][N][2] += (sum, sum of squares) of `out` over the frame's pixels
+  const float* res = nullptr;
+  int res_cstride = 0, res_act = ACT_NONE;
+  const float* res_mr = nullptr;
+  double* stats = nullptr;            // accumulated with atomics; zero it first
 };
 
 // Activation operand of one launch.

@@ -52,6 +52,8 @@ struct TcArgs {
   int split_col;                  // columns >= split_col (when > 0) go to o[1]
   TcOut o[2];
   long long split_stride;
+  // fused residual branch + output statistics (see ConvOut)
+  const float* res; int res_cstride, res_act; const float* res_mr; double* stats;
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -348,6 +350,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           }
         }
         act_tile<EPI_CHUNK>(v, od.act);
+        if (EPI_CHUNK == 32 && a.res != nullptr) {
+          // residual branch of a ResBlock: + res_act((res - mean) * rstd), per-(frame, channel) statistics from res_mr
+          float rv[EPI_CHUNK];
+          if (valid) {
+            const float4* rp = (const float4*)(a.res + opix * a.res_cstride + n0 + c);
+#pragma unroll
+            for (int j = 0; j < EPI_CHUNK / 4; ++j) {
+              const float4 t4 = __ldg(rp + j);
+              rv[4 * j] = t4.x; rv[4 * j + 1] = t4.y; rv[4 * j + 2] = t4.z; rv[4 * j + 3] = t4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < EPI_CHUNK; ++j) rv[j] = 0.f;
+          }
+          if (a.res_mr) {
+            const float4* mp = (const float4*)(a.res_mr + ((size_t)min(f, a.F - 1) * a.N + n0 + c) * 2);     // (mean, rstd) pairs
+#pragma unroll
+            for (int j = 0; j < EPI_CHUNK / 2; ++j) {
+              const float4 m4 = __ldg(mp + j);
+              rv[2 * j] = (rv[2 * j] - m4.x) * m4.y;
+              rv[2 * j + 1] = (rv[2 * j + 1] - m4.z) * m4.w;
+            }
+          }
+          act_tile<EPI_CHUNK>(rv, a.res_act);
+#pragma unroll
+          for (int j = 0; j < EPI_CHUNK; ++j) v[j] = valid ? v[j] + rv[j] : 0.f;      // rows outside the image contribute 0 to the stats
+        }
         if (od.mode == OUT_F32_NCHW) {
           // frames at the ABI edge: [f][N][Ho][Wo]; consecutive lanes are consecutive x -> coalesced per channel
           if (valid) {
@@ -376,6 +405,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             const uint4 dv = *(const uint4*)(rd + row * 128 + ((seg ^ (row & 7)) << 4));
             const size_t o = (size_t)trow[i] * od.cstride + colbase;
             if (seg * 4 < ncols) *(uint4*)((float*)od.out + zoff + o + seg * 4) = dv;
+          }
+          if (a.stats != nullptr) {
+            // per-channel sum / sum of squares of this warp's 32 rows (one frame): lane = column, straight from the staging rows
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int row = 0; row < 32; ++row) {
+              const float t = *(const float*)(rd + row * 128 + (((lane >> 2) ^ (row & 7)) << 4) + (lane & 3) * 4);
+              s1 += t;
+              s2 = fmaf(t, t, s2);
+            }
+            const int fw = __shfl_sync(0xffffffffu, f, 0);          // frame of this warp's rows
+            if (lane < ncols && fw < a.F) {
+              double* sp = a.stats + ((size_t)fw * a.N + n0 + c + lane) * 2;
+              atomicAdd(sp, (double)s1);
+              atomicAdd(sp + 1, (double)s2);
+            }
           }
           __syncwarp();       // staging rows are rewritten by the next chunk
         } else {
@@ -559,6 +604,11 @@ static int conv_tc_impl(const ConvW& w, const ConvIn& in, const ConvOut& out, co
     a.o[i].out = o->p; a.o[i].out_lo = o->p_lo; a.o[i].act = o->act; a.o[i].mode = o->mode; a.o[i].cstride = o->cstride; a.o[i].coff = o->coff;
   }
   a.split_stride = out.split_stride;
+  a.res = out.res; a.res_cstride = out.res_cstride; a.res_act = out.res_act; a.res_mr = out.res_mr; a.stats = out.stats;
+  if (out.res || out.stats)
+    IPK_CHECK(out.mode == OUT_F32_NHWC && !out.second && nsplit == 1 && w.Npad == w.N && w.N % 32 == 0 && w.N >= 64 &&
+                  (long long)in.H * in.W >= 32 && out.ymul == 1 && out.xmul == 1,
+              IPK_ERR_UNSUPPORTED, "conv_tc_run: fused residual / statistics need a plain fp32 NHWC output with N %% 32 == 0, N >= 64");
   a.stages = 2;
 
   // activation maps: dims (C, W, H, F); the C extent is the true channel count so the K tail is zero-filled

@@ -220,18 +220,29 @@ static void decode_frames(ipk_fs* d, const float* h, int nv, int T, int v0, floa
       std::swap(subs[0], subs[3]);      // heaviest class (4 taps) first
       conv_tc_run_multi(ub.ctf, in, o1, subs, 4, st);
     }
-    // conv2: ZeroPad(1) + 3x3, no norm, no activation
+    // conv2: ZeroPad(1) + 3x3, no norm, no activation;  out = conv2 + ReLU(IN(res))      (ResBlock.forward, util.py:185-192)
     ConvIn in2; in2.p = d->bufY1; in2.p_lo = d->bufY1_lo; in2.cstride = ub.Cout; in2.F = F; in2.H = so; in2.W = so;
-    ConvOut o2; o2.p = d->bufY2; o2.cstride = ub.Cout; o2.Ho = so; o2.Wo = so; o2.bias = ub.c2.bias;
-    { ProfScope ps(("dec.up.conv2.b" + bi).c_str(), st); conv_run(ub.c2, in2, o2, taps_3x3(), 1, st); }
+    if (d->eng == IPK_PREC_FP32_SIMT) {
+      ConvOut o2; o2.p = d->bufY2; o2.cstride = ub.Cout; o2.Ho = so; o2.Wo = so; o2.bias = ub.c2.bias;
+      { ProfScope ps(("dec.up.conv2.b" + bi).c_str(), st); conv_run(ub.c2, in2, o2, taps_3x3(), 1, st); }
+      ProfScope pse(("dec.up.norm_spade.b" + bi).c_str(), st);
+      stats_norm(d, d->bufR, F, P, ub.Cout, 0, st);
+      // (the GroupNorm statistics of `out` needed by SPADE are accumulated by the same pass)
+      IPK_CUDA(cudaMemsetAsync(d->sums, 0, (size_t)F * ub.Cout * 2 * sizeof(double), st));
+      NormApply n; n.x = d->bufR; n.F = F; n.C = ub.Cout; n.P = P; n.mr = d->mr; n.act = ACT_RELU; n.add = d->bufY2; n.out_f32 = d->bufS;
+      n.stats_out = d->sums;
+      norm_apply(n, st);
+    } else {
+      // tensor-core engines: InstanceNorm statistics of res first, then conv2's epilogue adds ReLU(IN(res)), writes `out`
+      // and accumulates the GroupNorm statistics SPADE needs -- no separate residual / statistics passes over the tensor
+      { ProfScope pse(("dec.up.norm_spade.b" + bi).c_str(), st); stats_norm(d, d->bufR, F, P, ub.Cout, 0, st); }
+      IPK_CUDA(cudaMemsetAsync(d->sums, 0, (size_t)F * ub.Cout * 2 * sizeof(double), st));
+      ConvOut o2; o2.p = d->bufS; o2.cstride = ub.Cout; o2.Ho = so; o2.Wo = so; o2.bias = ub.c2.bias;
+      o2.res = d->bufR; o2.res_cstride = ub.Cout; o2.res_act = ACT_RELU; o2.res_mr = d->mr; o2.stats = d->sums;
+      ProfScope ps(("dec.up.conv2.b" + bi).c_str(), st);
+      conv_run(ub.c2, in2, o2, taps_3x3(), 1, st);
+    }
     ProfScope pse(("dec.up.norm_spade.b" + bi).c_str(), st);
-    // out = conv2 + ReLU(IN(res))      (ResBlock.forward, util.py:185-192)
-    stats_norm(d, d->bufR, F, P, ub.Cout, 0, st);
-    // (the GroupNorm statistics of `out` needed by SPADE are accumulated by the same pass)
-    IPK_CUDA(cudaMemsetAsync(d->sums, 0, (size_t)F * ub.Cout * 2 * sizeof(double), st));
-    NormApply n; n.x = d->bufR; n.F = F; n.C = ub.Cout; n.P = P; n.mr = d->mr; n.act = ACT_RELU; n.add = d->bufY2; n.out_f32 = d->bufS;
-    n.stats_out = d->sums;
-    norm_apply(n, st);
     // SPADE: GroupNorm(16, affine=False)(out) * (1 + gamma) + beta
     finalize_stats(d->sums, d->mr, F, P, ub.Cout, ub.groups, 1e-5f, st);
     NormApply sp; sp.x = d->bufS; sp.F = F; sp.C = ub.Cout; sp.P = P; sp.mr = d->mr; sp.spade = ub.SP + (size_t)v0 * P * 2 * ub.Cout; sp.T = T;
