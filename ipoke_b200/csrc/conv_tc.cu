@@ -54,6 +54,7 @@ struct TcArgs {
   long long split_stride;
   // fused residual branch + output statistics (see ConvOut)
   const float* res; int res_cstride, res_act; const float* res_mr; double* stats;
+  int stats_oi, stats_C;          // statistics cover the columns of destination o[stats_oi], stats_C channels per frame
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -377,6 +378,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
           for (int j = 0; j < EPI_CHUNK; ++j) v[j] = valid ? v[j] + rv[j] : 0.f;      // rows outside the image contribute 0 to the stats
         }
+        if (a.stats != nullptr && a.res == nullptr && !valid) {
+#pragma unroll
+          for (int j = 0; j < EPI_CHUNK; ++j) v[j] = 0.f;      // rows outside the image contribute 0 to the statistics
+        }
         if (od.mode == OUT_F32_NCHW) {
           // frames at the ABI edge: [f][N][Ho][Wo]; consecutive lanes are consecutive x -> coalesced per channel
           if (valid) {
@@ -406,7 +411,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             const size_t o = (size_t)trow[i] * od.cstride + colbase;
             if (seg * 4 < ncols) *(uint4*)((float*)od.out + zoff + o + seg * 4) = dv;
           }
-          if (a.stats != nullptr) {
+          if (a.stats != nullptr && oi == a.stats_oi) {
             // per-channel sum / sum of squares of this warp's 32 rows (one frame): lane = column, straight from the staging rows
             float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -417,7 +422,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             }
             const int fw = __shfl_sync(0xffffffffu, f, 0);          // frame of this warp's rows
             if (lane < ncols && fw < a.F) {
-              double* sp = a.stats + ((size_t)fw * a.N + n0 + c + lane) * 2;
+              double* sp = a.stats + ((size_t)fw * a.stats_C + (n0 + c - (oi ? a.split_col : 0)) + lane) * 2;
               atomicAdd(sp, (double)s1);
               atomicAdd(sp + 1, (double)s2);
             }
@@ -605,10 +610,19 @@ static int conv_tc_impl(const ConvW& w, const ConvIn& in, const ConvOut& out, co
   }
   a.split_stride = out.split_stride;
   a.res = out.res; a.res_cstride = out.res_cstride; a.res_act = out.res_act; a.res_mr = out.res_mr; a.stats = out.stats;
-  if (out.res || out.stats)
+  a.stats_oi = 0; a.stats_C = w.N;
+  if (out.res)
     IPK_CHECK(out.mode == OUT_F32_NHWC && !out.second && nsplit == 1 && w.Npad == w.N && w.N % 32 == 0 && w.N >= 64 &&
                   (long long)in.H * in.W >= 32 && out.ymul == 1 && out.xmul == 1,
-              IPK_ERR_UNSUPPORTED, "conv_tc_run: fused residual / statistics need a plain fp32 NHWC output with N %% 32 == 0, N >= 64");
+              IPK_ERR_UNSUPPORTED, "conv_tc_run: the fused residual needs a plain fp32 NHWC output with N %% 32 == 0, N >= 64");
+  if (!out.stats && out.second && out.second->stats) {     // statistics of the second destination's columns
+    a.stats = out.second->stats; a.stats_oi = 1; a.stats_C = w.N - out.split_col;
+    IPK_CHECK(out.second->mode == OUT_F32_NHWC, IPK_ERR_UNSUPPORTED, "conv_tc_run: fused statistics need an fp32 NHWC destination");
+  }
+  if (a.stats)
+    IPK_CHECK(nsplit == 1 && w.Npad == w.N && w.N % 32 == 0 && w.N >= 64 && (long long)in.H * in.W >= 32 &&
+                  (a.stats_oi == 1 || out.mode == OUT_F32_NHWC),
+              IPK_ERR_UNSUPPORTED, "conv_tc_run: fused statistics need fp32 NHWC output, N %% 32 == 0, N >= 64, >= 32 pixels per frame");
   a.stages = 2;
 
   // activation maps: dims (C, W, H, F); the C extent is the true channel count so the K tail is zero-filled

@@ -213,6 +213,8 @@ static void decode_frames(ipk_fs* d, const float* h, int nv, int T, int v0, floa
     } else {
       // both transposed convs and all four output parity classes in ONE launch: N = conv1 | res_conv, dual destination
       ProfScope ps(("dec.up.convT.b" + bi).c_str(), st);
+      IPK_CUDA(cudaMemsetAsync(d->sums, 0, (size_t)F * ub.Cout * 2 * sizeof(double), st));
+      orr.stats = d->sums;          // InstanceNorm statistics of res_conv's output, accumulated by the epilogue
       o1.bias = ub.ctf.bias; o1.second = &orr; o1.split_col = ub.Cout; o1.ymul = 2; o1.xmul = 2;
       ConvSub subs[4];
       for (int a = 0; a < 2; ++a)
@@ -235,7 +237,7 @@ static void decode_frames(ipk_fs* d, const float* h, int nv, int T, int v0, floa
     } else {
       // tensor-core engines: InstanceNorm statistics of res first, then conv2's epilogue adds ReLU(IN(res)), writes `out`
       // and accumulates the GroupNorm statistics SPADE needs -- no separate residual / statistics passes over the tensor
-      { ProfScope pse(("dec.up.norm_spade.b" + bi).c_str(), st); stats_norm(d, d->bufR, F, P, ub.Cout, 0, st); }
+      { ProfScope pse(("dec.up.norm_spade.b" + bi).c_str(), st); finalize_stats(d->sums, d->mr, F, P, ub.Cout, 0, 1e-5f, st); }
       IPK_CUDA(cudaMemsetAsync(d->sums, 0, (size_t)F * ub.Cout * 2 * sizeof(double), st));
       ConvOut o2; o2.p = d->bufS; o2.cstride = ub.Cout; o2.Ho = so; o2.Wo = so; o2.bias = ub.c2.bias;
       o2.res = d->bufR; o2.res_cstride = ub.Cout; o2.res_act = ACT_RELU; o2.res_mr = d->mr; o2.stats = d->sums;
