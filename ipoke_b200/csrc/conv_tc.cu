@@ -177,7 +177,7 @@ __device__ __forceinline__ void act_tile(float (&v)[NV], int act) {
 // Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue.
 // Two TMEM accumulator stages (2 x BN columns): the epilogue of tile i overlaps the main loop of tile i+1.
 // Tile order: linear id -> (split z, m tile, n tile) with n fastest, so CTAs running side by side share the A tile in L2.
-template <int BN, int NSPLIT>
+template <int BN, int NSPLIT, bool FUSED>       // FUSED: residual branch / output statistics in the epilogue (see ConvOut)
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, const TcArgs a) {
@@ -351,7 +351,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           }
         }
         act_tile<EPI_CHUNK>(v, od.act);
-        if (EPI_CHUNK == 32 && a.res != nullptr) {
+        if (FUSED && EPI_CHUNK == 32 && a.res != nullptr) {
           // residual branch of a ResBlock: + res_act((res - mean) * rstd), per-(frame, channel) statistics from res_mr
           float rv[EPI_CHUNK];
           if (valid) {
@@ -378,7 +378,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
           for (int j = 0; j < EPI_CHUNK; ++j) v[j] = valid ? v[j] + rv[j] : 0.f;      // rows outside the image contribute 0 to the stats
         }
-        if (a.stats != nullptr && a.res == nullptr && !valid) {
+        if (FUSED && a.stats != nullptr && a.res == nullptr && !valid) {
 #pragma unroll
           for (int j = 0; j < EPI_CHUNK; ++j) v[j] = 0.f;      // rows outside the image contribute 0 to the statistics
         }
@@ -411,7 +411,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             const size_t o = (size_t)trow[i] * od.cstride + colbase;
             if (seg * 4 < ncols) *(uint4*)((float*)od.out + zoff + o + seg * 4) = dv;
           }
-          if (a.stats != nullptr && oi == a.stats_oi) {
+          if (FUSED && a.stats != nullptr && oi == a.stats_oi) {
             // per-channel sum / sum of squares of this warp's 32 rows (one frame): lane = column, straight from the staging rows
             float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -534,7 +534,7 @@ static int sm_count() {
   return n;
 }
 
-template <int BN, int NSPLIT>
+template <int BN, int NSPLIT, bool FUSED>
 static void launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo, TcArgs& a,
                       cudaStream_t st) {
   constexpr int STAGE_BYTES = (NSPLIT == 3 ? 2 : 1) * (TC_BM * TC_BK * 2 + BN * TC_BK * 2);
@@ -543,12 +543,12 @@ static void launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CU
   size_t smem = (size_t)stages * STAGE_BYTES + 1024 + TC_EPI_WARPS * TC_EPI_STAGE_BYTES;
   static bool attr_set = false;
   if (!attr_set) {
-    IPK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TC_SMEM_BUDGET + 1024 + TC_EPI_WARPS * TC_EPI_STAGE_BYTES)));
+    IPK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, NSPLIT, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TC_SMEM_BUDGET + 1024 + TC_EPI_WARPS * TC_EPI_STAGE_BYTES)));
     attr_set = true;
   }
   const long long total = (long long)a.tiles_m * a.tiles_n * (a.nsub > 1 ? a.nsub : a.nsplit);
   const unsigned grid = (unsigned)std::min<long long>(total, sm_count());     // persistent: one CTA per SM
-  launch_k(conv_tc_kernel<BN, NSPLIT>, dim3(grid), dim3(TC_THREADS), smem, st, a_hi, a_lo, w_hi, w_lo, a);
+  launch_k(conv_tc_kernel<BN, NSPLIT, FUSED>, dim3(grid), dim3(TC_THREADS), smem, st, a_hi, a_lo, w_hi, w_lo, a);
 }
 
 static int conv_tc_impl(const ConvW& w, const ConvIn& in, const ConvOut& out, const ConvSub* subs, int nsub, int nsplit, cudaStream_t st) {
@@ -650,10 +650,16 @@ static int conv_tc_impl(const ConvW& w, const ConvIn& in, const ConvOut& out, co
   a.tiles_m = a.tiles_x * a.tiles_y * tiles_f;
   a.tiles_n = cdiv(w.Npad, BN);
   a.nsplit = nsplit;
-#define IPK_TC_CASE(bn)                                                       \
-  case bn:                                                                    \
-    if (split) launch_tc<bn, 3>(mA_hi, mA_lo, mW_hi, mW_lo, a, st);           \
-    else launch_tc<bn, 1>(mA_hi, mA_lo, mW_hi, mW_lo, a, st);                 \
+  const bool fused = a.res != nullptr || a.stats != nullptr;
+#define IPK_TC_CASE(bn)                                                                 \
+  case bn:                                                                              \
+    if (fused) {                                                                        \
+      if (split) launch_tc<bn, 3, true>(mA_hi, mA_lo, mW_hi, mW_lo, a, st);             \
+      else launch_tc<bn, 1, true>(mA_hi, mA_lo, mW_hi, mW_lo, a, st);                   \
+    } else {                                                                            \
+      if (split) launch_tc<bn, 3, false>(mA_hi, mA_lo, mW_hi, mW_lo, a, st);            \
+      else launch_tc<bn, 1, false>(mA_hi, mA_lo, mW_hi, mW_lo, a, st);                  \
+    }                                                                                   \
     break;
   switch (BN) {
     IPK_TC_CASE(32)
