@@ -55,6 +55,7 @@ struct TcArgs {
   // fused residual branch + output statistics (see ConvOut)
   const float* res; int res_cstride, res_act; const float* res_mr; double* stats;
   int stats_oi, stats_C;          // statistics cover the columns of destination o[stats_oi], stats_C channels per frame
+  int halo_variant;               // HALO kernels: 1 = row-shifted descriptors carry the swizzle base offset, 2 = they do not
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -113,6 +114,13 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
   return d;
+}
+// same with the matrix base offset field (bits 49..51) set.  Measured on B200: a start address that is a whole number of
+// 128-byte rows into a 1024-byte swizzle atom (row-shifted views of a halo tile) needs NO base offset -- the 128-byte swizzle
+// is a function of the shared-memory address bits, so the plain shifted start address reads the TMA-written rows correctly
+// (halo_variant 2, the default); setting the field to (start >> 7) & 7 (variant 1) gives wrong results.
+__device__ __forceinline__ uint64_t umma_desc_sw128_off(uint32_t smem_addr, uint32_t base_off) {
+  return umma_desc_sw128(smem_addr) | ((uint64_t)(base_off & 7) << 49);
 }
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
@@ -177,14 +185,19 @@ __device__ __forceinline__ void act_tile(float (&v)[NV], int act) {
 // Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue.
 // Two TMEM accumulator stages (2 x BN columns): the epilogue of tile i overlaps the main loop of tile i+1.
 // Tile order: linear id -> (split z, m tile, n tile) with n fastest, so CTAs running side by side share the A tile in L2.
-template <int BN, int NSPLIT, bool FUSED>       // FUSED: residual branch / output statistics in the epilogue (see ConvOut)
+// FUSED: residual branch / output statistics in the epilogue (see ConvOut).
+// HALO (3x3 convs on 128-wide images, one image row per tile): the producer loads each input row ONCE as a 130-pixel box
+// (x = -1 .. 128, zero-filled outside) and the three dx taps are row-shifted views of that box (UMMA descriptor start advanced by
+// dx * 128 bytes) instead of three separate TMA loads: A traffic / 3.
+constexpr int TC_HALO_A_BYTES = 17 * 1024;      // 130 rows x 128 B = 16 640 B, padded to keep the regions 1024-byte aligned
+template <int BN, int NSPLIT, bool FUSED, bool HALO>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, const TcArgs a) {
   constexpr int A_BYTES = TC_BM * TC_BK * 2;         // 16 KB
   constexpr int W_BYTES = BN * TC_BK * 2;
   constexpr int NPLANES = NSPLIT == 3 ? 2 : 1;
-  constexpr int STAGE_BYTES = NPLANES * (A_BYTES + W_BYTES);
+  constexpr int STAGE_BYTES = HALO ? NPLANES * (TC_HALO_A_BYTES + 3 * W_BYTES) : NPLANES * (A_BYTES + W_BYTES);
   constexpr uint32_t IDESC = umma_idesc_bf16(TC_BM, BN);
   constexpr int MAX_STAGES = 8;
   constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
@@ -234,6 +247,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int ty = r2 / a.tiles_x, tx = r2 - ty * a.tiles_x;
         const int f0 = tf * a.bf, y0 = ty * a.bh, x0 = tx * a.bw, n0 = nt * BN;
         const TcSub& sb = a.sub[a.nsub > 1 ? z : 0];
+        if constexpr (HALO) {
+          // one stage per (input row dy, k-block): the 130-pixel row box of both planes + the weights of its three dx taps
+          for (int dyi = 0; dyi < 3; ++dyi)
+            for (int kb = 0; kb < a.nkb; ++kb) {
+              mbar_wait(&empty_bar[s], ph ^ 1);
+              uint8_t* st = smem + (size_t)s * STAGE_BYTES;
+              mbar_expect_tx(&full_bar[s], NPLANES * (130 * 128 + 3 * W_BYTES));
+              tma_load_4d(st, &tmA_hi, &full_bar[s], kb * TC_BK, -1, y0 + dyi - 1, f0);
+              if (NSPLIT == 3) tma_load_4d(st + TC_HALO_A_BYTES, &tmA_lo, &full_bar[s], kb * TC_BK, -1, y0 + dyi - 1, f0);
+              uint8_t* wst = st + NPLANES * TC_HALO_A_BYTES;
+              for (int dxi = 0; dxi < 3; ++dxi) {
+                const int wrow = (dyi * 3 + dxi) * a.Npad + n0;
+                tma_load_2d(wst + dxi * W_BYTES, &tmW_hi, &full_bar[s], kb * TC_BK, wrow);
+                if (NSPLIT == 3) tma_load_2d(wst + (3 + dxi) * W_BYTES, &tmW_lo, &full_bar[s], kb * TC_BK, wrow);
+              }
+              if (++s == stages) { s = 0; ph ^= 1; }
+            }
+          continue;
+        }
         const int it_begin = a.nsub > 1 ? 0 : z * a.iters_per_split;
         const int it_end = min(sb.ntaps * a.nkb, it_begin + a.iters_per_split);
         int t = it_begin / a.nkb, kb = it_begin - t * a.nkb;
@@ -265,10 +297,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int z = tile / tiles_mn;
         const int it_begin = a.nsub > 1 ? 0 : z * a.iters_per_split;
-        const int iters = min(a.sub[a.nsub > 1 ? z : 0].ntaps * a.nkb, it_begin + a.iters_per_split) - it_begin;
+        const int iters = HALO ? 3 * a.nkb : min(a.sub[a.nsub > 1 ? z : 0].ntaps * a.nkb, it_begin + a.iters_per_split) - it_begin;
         mbar_wait(&tmem_empty_bar[as], aph ^ 1);      // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(as * BN);
+        if constexpr (HALO) {
+          for (int it = 0; it < iters; ++it) {
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+            const uint32_t sw = sa + NPLANES * TC_HALO_A_BYTES;
+#pragma unroll
+            for (int dxi = 0; dxi < 3; ++dxi) {
+              // rows dxi .. dxi+127 of the 130-row box: output pixel x reads input x + dx = box row x + dxi
+              const uint32_t boff = a.halo_variant == 1 ? (uint32_t)dxi : 0u;
+              const uint64_t da_hi = umma_desc_sw128_off(sa + dxi * 128, boff);
+              const uint64_t dw_hi = umma_desc_sw128(sw + dxi * W_BYTES);
+#pragma unroll
+              for (int k = 0; k < TC_BK / 16; ++k) {
+                const uint64_t koff = (uint64_t)((k * 32) >> 4);
+                umma_bf16(tacc, da_hi + koff, dw_hi + koff, IDESC, (it > 0 || dxi > 0 || k > 0) ? 1u : 0u);
+                if (NSPLIT == 3) {
+                  const uint64_t da_lo = umma_desc_sw128_off(sa + TC_HALO_A_BYTES + dxi * 128, boff);
+                  const uint64_t dw_lo = umma_desc_sw128(sw + (3 + dxi) * W_BYTES);
+                  umma_bf16(tacc, da_lo + koff, dw_hi + koff, IDESC, 1u);
+                  umma_bf16(tacc, da_hi + koff, dw_lo + koff, IDESC, 1u);
+                }
+              }
+            }
+            umma_commit(&empty_bar[s]);
+            if (it == iters - 1) umma_commit(&tmem_full_bar[as]);
+            if (++s == stages) { s = 0; ph ^= 1; }
+          }
+          if (++as == 2) { as = 0; aph ^= 1; }
+          continue;
+        }
         for (int it = 0; it < iters; ++it) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
@@ -534,21 +597,23 @@ static int sm_count() {
   return n;
 }
 
-template <int BN, int NSPLIT, bool FUSED>
+template <int BN, int NSPLIT, bool FUSED, bool HALO>
 static void launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo, TcArgs& a,
                       cudaStream_t st) {
-  constexpr int STAGE_BYTES = (NSPLIT == 3 ? 2 : 1) * (TC_BM * TC_BK * 2 + BN * TC_BK * 2);
+  constexpr int STAGE_BYTES = HALO ? (NSPLIT == 3 ? 2 : 1) * (TC_HALO_A_BYTES + 3 * BN * TC_BK * 2)
+                                   : (NSPLIT == 3 ? 2 : 1) * (TC_BM * TC_BK * 2 + BN * TC_BK * 2);
   int stages = (int)std::min<size_t>(8, TC_SMEM_BUDGET / STAGE_BYTES);
+  IPK_CHECK(stages >= 2, IPK_ERR_UNSUPPORTED, "conv_tc: pipeline needs at least two stages (stage %d bytes)", STAGE_BYTES);
   a.stages = stages;
   size_t smem = (size_t)stages * STAGE_BYTES + 1024 + TC_EPI_WARPS * TC_EPI_STAGE_BYTES;
   static bool attr_set = false;
   if (!attr_set) {
-    IPK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, NSPLIT, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TC_SMEM_BUDGET + 1024 + TC_EPI_WARPS * TC_EPI_STAGE_BYTES)));
+    IPK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, NSPLIT, FUSED, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TC_SMEM_BUDGET + 1024 + TC_EPI_WARPS * TC_EPI_STAGE_BYTES)));
     attr_set = true;
   }
   const long long total = (long long)a.tiles_m * a.tiles_n * (a.nsub > 1 ? a.nsub : a.nsplit);
   const unsigned grid = (unsigned)std::min<long long>(total, sm_count());     // persistent: one CTA per SM
-  launch_k(conv_tc_kernel<BN, NSPLIT, FUSED>, dim3(grid), dim3(TC_THREADS), smem, st, a_hi, a_lo, w_hi, w_lo, a);
+  launch_k(conv_tc_kernel<BN, NSPLIT, FUSED, HALO>, dim3(grid), dim3(TC_THREADS), smem, st, a_hi, a_lo, w_hi, w_lo, a);
 }
 
 static int conv_tc_impl(const ConvW& w, const ConvIn& in, const ConvOut& out, const ConvSub* subs, int nsub, int nsplit, cudaStream_t st) {
@@ -651,14 +716,34 @@ static int conv_tc_impl(const ConvW& w, const ConvIn& in, const ConvOut& out, co
   a.tiles_n = cdiv(w.Npad, BN);
   a.nsplit = nsplit;
   const bool fused = a.res != nullptr || a.stats != nullptr;
+  // halo mode: full 3x3 tap set on a 128-wide image, one image row per tile, 64-column N tiles (the decoder's last conv2)
+  static const int halo_env = []() { const char* e = getenv("IPK_TC_HALO"); return e ? atoi(e) : 2; }();     // 0 = off
+  bool halo = halo_env > 0 && nsub == 1 && nsplit == 1 && in.W == TC_BM && a.bw == TC_BM && subs[0].taps.n == 9 && BN == 64;
+  if (halo)
+    for (int i = 0; i < 9; ++i)
+      halo = halo && subs[0].taps.dy[i] == i / 3 - 1 && subs[0].taps.dx[i] == i % 3 - 1 && subs[0].taps.widx[i] == i;
+  a.halo_variant = halo_env;
+  if (halo) {
+    int hb[4] = {TC_BK, 130, 1, 1};
+    const CUtensorMap hA_hi = make_map(ahi, 4, ad, as, hb);
+    const CUtensorMap hA_lo = split ? make_map((const __nv_bfloat16*)in.p_lo + in.coff, 4, ad, as, hb) : hA_hi;
+    if (fused) {
+      if (split) launch_tc<64, 3, true, true>(hA_hi, hA_lo, mW_hi, mW_lo, a, st);
+      else launch_tc<64, 1, true, true>(hA_hi, hA_lo, mW_hi, mW_lo, a, st);
+    } else {
+      if (split) launch_tc<64, 3, false, true>(hA_hi, hA_lo, mW_hi, mW_lo, a, st);
+      else launch_tc<64, 1, false, true>(hA_hi, hA_lo, mW_hi, mW_lo, a, st);
+    }
+    return nsplit;
+  }
 #define IPK_TC_CASE(bn)                                                                 \
   case bn:                                                                              \
     if (fused) {                                                                        \
-      if (split) launch_tc<bn, 3, true>(mA_hi, mA_lo, mW_hi, mW_lo, a, st);             \
-      else launch_tc<bn, 1, true>(mA_hi, mA_lo, mW_hi, mW_lo, a, st);                   \
+      if (split) launch_tc<bn, 3, true, false>(mA_hi, mA_lo, mW_hi, mW_lo, a, st);      \
+      else launch_tc<bn, 1, true, false>(mA_hi, mA_lo, mW_hi, mW_lo, a, st);            \
     } else {                                                                            \
-      if (split) launch_tc<bn, 3, false>(mA_hi, mA_lo, mW_hi, mW_lo, a, st);            \
-      else launch_tc<bn, 1, false>(mA_hi, mA_lo, mW_hi, mW_lo, a, st);                  \
+      if (split) launch_tc<bn, 3, false, false>(mA_hi, mA_lo, mW_hi, mW_lo, a, st);     \
+      else launch_tc<bn, 1, false, false>(mA_hi, mA_lo, mW_hi, mW_lo, a, st);           \
     }                                                                                   \
     break;
   switch (BN) {
