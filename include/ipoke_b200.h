@@ -16,6 +16,8 @@
  *                   (ConvGRU.forward                               models/modules/motion_models/rnn.py:104-133,
  *                    SpadeCondConvDecoder.forward                  models/modules/autoencoders/fully_conv_models.py:166-177)
  *   ipk_sample_* <- PokeMotionModel.forward_sample loop body       models/second_stage_video.py:333-341
+ *   ipk_enc_*    <- PokeMotionModel.encode_first_stage             models/second_stage_video.py:352-359
+ *                   (ResNetMotionEncoder.forward                   models/modules/motion_models/motion_encoder.py:224-241)
  *   ipk_*_set_tensor takes the reference's state-dict key names unchanged.
  */
 #ifndef IPOKE_B200_H_
@@ -77,8 +79,21 @@ typedef struct ipk_fs_config {
   int32_t chunk_videos;               /* videos decoded per pass (0 = auto)   */
 } ipk_fs_config;
 
+/* Mirrors the keys ResNetMotionEncoder.__init__ reads (motion_encoder.py:152-160). */
+typedef struct ipk_enc_config {
+  int32_t z_dim;
+  int32_t img_size;                   /* H = W of the input frames (64 or 128)           */
+  int32_t max_frames;                 /* data.max_frames; the encoder sees max_frames + 1 */
+  int32_t full_seq;
+  int32_t n_channels;                 /* len(ENC_M_channels)                              */
+  int32_t channels[IPK_MAX_DEC];
+  int32_t min_spatial_size;
+  int32_t max_batch;
+} ipk_enc_config;
+
 typedef struct ipk_flow ipk_flow;
 typedef struct ipk_fs ipk_fs;
+typedef struct ipk_enc ipk_enc;
 
 int ipk_version(void);
 const char* ipk_last_error(void);
@@ -114,6 +129,15 @@ int ipk_fs_gru_step(ipk_fs* d, const float* x, const float* hidden, float* new_h
 /* one decoder pass (SpadeCondConvDecoder.forward): h[B,z,8,8], x0[B,3,S,S] -> frame[B,3,S,S] */
 int ipk_fs_gen(ipk_fs* d, const float* h, const float* x0, float* frame, int32_t B, void* stream);
 int ipk_fs_destroy(ipk_fs* d);
+
+/* ---- first-stage 3-D conv video encoder (second-stage training path; no gradients) ---- */
+int ipk_enc_create(const ipk_enc_config* cfg, ipk_enc** out);
+int ipk_enc_set_tensor(ipk_enc* e, const char* name, const void* dev_ptr, int64_t numel, int dtype);
+int ipk_enc_finalize(ipk_enc* e, void* stream);
+/* X[B,3,T,S,S] (NCDHW), eps[B,z,8,8] (reparameterisation noise, drawn by the host so RNG stays in Python)
+ * -> z = eps * exp(logvar / 2) + mu, mu, logvar, each [B,z,8,8] */
+int ipk_enc_forward(ipk_enc* e, const float* X, const float* eps, float* z, float* mu, float* logvar, int32_t B, int32_t T, void* stream);
+int ipk_enc_destroy(ipk_enc* e);
 
 /* ---- whole sampling step with DEVICE buffers: flow inverse -> GRU + decoder ---- */
 int ipk_sample(ipk_flow* f, ipk_fs* d, const float* z, const float* cond, const float* x0, float* frames,

@@ -28,10 +28,17 @@ class FsConfig(ctypes.Structure):
                 ("max_batch", ctypes.c_int32), ("max_frames", ctypes.c_int32), ("chunk_videos", ctypes.c_int32)]
 
 
+class EncConfig(ctypes.Structure):
+    _fields_ = [("z_dim", ctypes.c_int32), ("img_size", ctypes.c_int32), ("max_frames", ctypes.c_int32), ("full_seq", ctypes.c_int32),
+                ("n_channels", ctypes.c_int32), ("channels", ctypes.c_int32 * IPK_MAX_DEC), ("min_spatial_size", ctypes.c_int32),
+                ("max_batch", ctypes.c_int32)]
+
+
 EXPORTS = [
     "ipk_version", "ipk_last_error", "ipk_launch_count", "ipk_launch_count_reset", "ipk_prof_enable", "ipk_prof_report",
     "ipk_flow_create", "ipk_flow_set_tensor", "ipk_flow_finalize", "ipk_flow_reverse", "ipk_flow_forward", "ipk_flow_destroy",
     "ipk_fs_create", "ipk_fs_set_tensor", "ipk_fs_finalize", "ipk_fs_decode", "ipk_fs_gru_step", "ipk_fs_gen", "ipk_fs_destroy",
+    "ipk_enc_create", "ipk_enc_set_tensor", "ipk_enc_finalize", "ipk_enc_forward", "ipk_enc_destroy",
     "ipk_sample", "ipk_sample_host", "ipk_test_gemm", "ipk_test_conv3x3", "ipk_test_convT3x3",
 ]
 
@@ -68,6 +75,11 @@ def lib():
     L.ipk_fs_gru_step.argtypes = [vp, vp, vp, vp, i32, vp]
     L.ipk_fs_gen.argtypes = [vp, vp, vp, vp, i32, vp]
     L.ipk_fs_destroy.argtypes = [vp]
+    L.ipk_enc_create.argtypes = [ctypes.POINTER(EncConfig), ctypes.POINTER(vp)]
+    L.ipk_enc_set_tensor.argtypes = [vp, cp, vp, i64, ctypes.c_int]
+    L.ipk_enc_finalize.argtypes = [vp, vp]
+    L.ipk_enc_forward.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp]
+    L.ipk_enc_destroy.argtypes = [vp]
     L.ipk_sample.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp]
     L.ipk_sample_host.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp]
     L.ipk_test_gemm.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
@@ -75,7 +87,7 @@ def lib():
     L.ipk_test_convT3x3.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
-        if name.startswith(("ipk_flow_", "ipk_fs_", "ipk_sample", "ipk_test_")):
+        if name.startswith(("ipk_flow_", "ipk_fs_", "ipk_enc_", "ipk_sample", "ipk_test_")):
             fn.restype = ctypes.c_int
     _lib = L
     return L

@@ -131,6 +131,7 @@ struct NormApplyK {
   float* out_f32; __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
   double* stats_out;       // optional: per-(frame, channel) sum / sum of squares of the OUTPUT values, accumulated
   int ppb;                 // pixels per block
+  int act_last;            // activation after the residual add
 };
 // grid (pixel chunks, F): a block works on `ppb` pixels of ONE frame; thread = (channel quad c4 = tid % C4, pixel lane =
 // tid / C4).  Per-channel constants (mean, rstd, affine) sit in registers; no integer division per element.
@@ -177,8 +178,8 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(const NormApplyK a) {
         float t = v[i];
         if (a.mr) t = (t - mean[i]) * rstd[i];
         if (a.w) t = t * gw[i] + gb[i];
-        t = act_apply(t, a.act);
-        t += ad[i];
+        if (a.act_last) t = act_apply(t + ad[i], a.act);
+        else t = act_apply(t, a.act) + ad[i];
         if (a.spade) t = t * sg[i] + sb[i];
         v[i] = t;
         s[i] += t;
@@ -232,7 +233,7 @@ void norm_apply(const NormApply& n0, cudaStream_t st) {
   const long long want_blocks = 148LL * 8;
   while (ppb > lanes && (long long)n.F * ((n.P + ppb - 1) / ppb) < want_blocks) ppb /= 2;
   ppb = std::max<long long>(ppb, lanes);
-  NormApplyK a{n.x, n.F, n.C, n.P, n.mr, n.w, n.b, n.act, n.add, n.spade, n.T, n.out_f32, n.out_hi, n.out_lo, n.stats_out, (int)ppb};
+  NormApplyK a{n.x, n.F, n.C, n.P, n.mr, n.w, n.b, n.act, n.add, n.spade, n.T, n.out_f32, n.out_hi, n.out_lo, n.stats_out, (int)ppb, n.act_last ? 1 : 0};
   dim3 g((unsigned)((n.P + ppb - 1) / ppb), (unsigned)n.F);
   IPK_CHECK(n.F <= 65535, IPK_ERR_UNSUPPORTED, "norm_apply: too many frames per launch (%d)", n.F);
   launch_k(norm_apply_kernel, g, dim3(256), 0, st, a);

@@ -26,7 +26,8 @@ struct NormApply {
   const float* w = nullptr;      // per-channel affine weight or null
   const float* b = nullptr;
   int act = ACT_NONE;
-  const float* add = nullptr;    // residual [F][P][C] added after the activation
+  const float* add = nullptr;    // residual [F][P][C] added after the activation (before it when act_last is set)
+  bool act_last = false;         // out = act(norm(x) + add)  (BasicBlock of the 3-D encoder)
   const float* spade = nullptr;  // [B][P][2C]: (1 + gamma | beta), video index = f / T
   int T = 1;
   float* out_f32 = nullptr;      // any of the three outputs may be null

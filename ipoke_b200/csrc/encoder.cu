@@ -1,0 +1,400 @@
+// First-stage 3-D conv video encoder (training path of the second stage):
+//   PokeMotionModel.encode_first_stage      models/second_stage_video.py:352-359
+//   ResNetMotionEncoder.forward / __init__  models/modules/motion_models/motion_encoder.py:150-241
+//   BasicBlock                              models/modules/motion_models/motion_encoder.py:45-74
+//
+// Data layout: NDHWC fp32 [B][T][H][W][C] (the 3 input channels padded to 4).  Every Conv3d is an implicit GEMM over
+// (tap, channel) with the taps outermost, so one k-chunk of a tile row is a contiguous run of channels of one input voxel.
+// GroupNorm(16) statistics run over the whole (T, H, W) volume of a sample: the shared norm pass with F = B, P = T*H*W.
+// This is the fp32 FFMA first cut of the row (parity first); the tcgen05 engine takes it over once it grows 5-D maps.
+#include <map>
+#include <string>
+#include <cmath>
+#include "conv.cuh"
+#include "elementwise.cuh"
+
+namespace ipk {
+
+struct TensorRefE { const void* p; int64_t numel; };
+
+struct Conv3dDesc {
+  int Cin, Cout;          // Cin as stored (multiple of 4)
+  int kt, ky, kx, st, sy, sx, pt, py, px;
+  float* w = nullptr;     // [kt][ky][kx][Cin][Cout]
+};
+
+struct Conv3dArgs {
+  const float* in; float* out; const float* w;
+  int B, Ti, Hi, Wi, Cin, To, Ho, Wo, Cout;
+  int kt, ky, kx, st, sy, sx, pt, py, px;
+};
+
+constexpr int C3_BM = 64, C3_BN = 64, C3_BK = 16;
+
+// 256 threads: 64 output voxels x 64 output channels per CTA, 4 x 4 outputs per thread
+__global__ void __launch_bounds__(256) conv3d_simt_kernel(const Conv3dArgs a) {
+  __shared__ __align__(16) float As[C3_BK][C3_BM + 4];
+  __shared__ __align__(16) float Ws[C3_BK][C3_BN];
+  __shared__ int vb[C3_BM], vt[C3_BM], vy[C3_BM], vx[C3_BM];
+  pdl_wait();
+  pdl_trigger();
+  const int tid = threadIdx.x;
+  const long long M = (long long)a.B * a.To * a.Ho * a.Wo;
+  const long long m0 = (long long)blockIdx.x * C3_BM;
+  const int n0 = blockIdx.y * C3_BN;
+  if (tid < C3_BM) {
+    long long m = m0 + tid;
+    if (m < M) {
+      int x = (int)(m % a.Wo); m /= a.Wo;
+      int y = (int)(m % a.Ho); m /= a.Ho;
+      int t = (int)(m % a.To);
+      vb[tid] = (int)(m / a.To); vt[tid] = t * a.st - a.pt; vy[tid] = y * a.sy - a.py; vx[tid] = x * a.sx - a.px;
+    } else {
+      vb[tid] = -1; vt[tid] = 0; vy[tid] = 0; vx[tid] = 0;
+    }
+  }
+  __syncthreads();
+  const int kc = a.Cin < C3_BK ? a.Cin : C3_BK;          // channels per k-chunk (Cin is 4 or a multiple of 16)
+  const int arow = tid >> 2, aq = tid & 3;               // A staging: row, float4 index inside the chunk
+  const int tx = tid & 15, ty = tid >> 4;                // compute: 16 x 16 threads, 4 x 4 outputs each
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int ntaps = a.kt * a.ky * a.kx;
+  for (int tap = 0; tap < ntaps; ++tap) {
+    const int dt = tap / (a.ky * a.kx), dy = (tap / a.kx) % a.ky, dx = tap % a.kx;
+    const int ti = vt[arow] + dt, yi = vy[arow] + dy, xi = vx[arow] + dx;
+    const bool ok = vb[arow] >= 0 && ti >= 0 && ti < a.Ti && yi >= 0 && yi < a.Hi && xi >= 0 && xi < a.Wi;
+    const float* ip = a.in + ((((size_t)max(vb[arow], 0) * a.Ti + max(ti, 0)) * a.Hi + max(yi, 0)) * a.Wi + max(xi, 0)) * a.Cin;
+    const float* wt = a.w + (size_t)tap * a.Cin * a.Cout;
+    for (int c0 = 0; c0 < a.Cin; c0 += kc) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok && aq * 4 < kc) v = __ldg((const float4*)(ip + c0) + aq);
+      As[aq * 4 + 0][arow] = v.x; As[aq * 4 + 1][arow] = v.y; As[aq * 4 + 2][arow] = v.z; As[aq * 4 + 3][arow] = v.w;
+      for (int e = tid; e < C3_BK * C3_BN; e += 256) {
+        const int k = e / C3_BN, n = e % C3_BN;
+        Ws[k][n] = (k < kc && n0 + n < a.Cout) ? __ldg(wt + (size_t)(c0 + k) * a.Cout + n0 + n) : 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < C3_BK; ++kk) {
+        float av[4], wv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) av[i] = As[kk][ty * 4 + i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) wv[j] = Ws[kk][tx * 4 + j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < a.Cout) a.out[(size_t)m * a.Cout + n] = acc[i][j];
+    }
+  }
+}
+
+// w: OIDHW [Cout][CinSrc][kt][ky][kx] -> [tap][Cin (zero padded)][Cout]
+__global__ void pack_conv3d_kernel(const float* __restrict__ w, float* __restrict__ dst, int Cout, int CinSrc, int Cin, int ntaps) {
+  const long long total = (long long)ntaps * Cin * Cout;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(e % Cout), c = (int)((e / Cout) % Cin), tap = (int)(e / ((long long)Cout * Cin));
+    dst[e] = c < CinSrc ? w[((size_t)n * CinSrc + c) * ntaps + tap] : 0.f;
+  }
+}
+
+// X [B][3][T][H][W] (NCDHW) -> [B][T][H][W][4] (4th channel zero)
+__global__ void ncdhw_to_ndhwc4_kernel(const float* __restrict__ in, float* __restrict__ out, int B, long long V) {
+  const long long total = (long long)B * V;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long b = e / V, v = e % V;
+    const float* ip = in + (size_t)b * 3 * V + v;
+    ((float4*)out)[e] = make_float4(ip[0], ip[V], ip[2 * V], 0.f);
+  }
+}
+
+// heads [B*64][2z] (mu | logvar) + eps [B][z][64] -> z, mu, logvar NCHW [B][z][64]     (reparameterize, motion_encoder.py:218-222)
+__global__ void reparam_kernel(const float* __restrict__ heads, const float* __restrict__ eps, float* __restrict__ zo, float* __restrict__ mu,
+                               float* __restrict__ lv, int B, int z) {
+  const int total = B * z * 64;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int p = e % 64, c = (e / 64) % z, b = e / (64 * z);
+    const float m = heads[((size_t)b * 64 + p) * 2 * z + c], l = heads[((size_t)b * 64 + p) * 2 * z + z + c];
+    mu[e] = m;
+    lv[e] = l;
+    zo[e] = eps[e] * expf(0.5f * l) + m;
+  }
+}
+
+struct EncBlock {
+  Conv3dDesc c1, c2, ds;
+  bool has_ds = false;
+  float *g1w, *g1b, *g2w, *g2b, *gdw, *gdb;
+};
+
+}  // namespace ipk
+
+using namespace ipk;
+
+struct ipk_enc {
+  ipk_enc_config cfg;
+  std::map<std::string, TensorRefE> tensors;
+  bool finalized = false;
+  DevPool pool;
+  Arena ws;
+  Conv3dDesc stem;
+  float *stem_gw = nullptr, *stem_gb = nullptr;
+  std::vector<EncBlock> blocks;
+  ConvW heads;               // conv_mu | conv_var fused along N (2-D 3x3, fp32 FFMA engine)
+  int last_C = 0;
+  // workspace
+  float *X4 = nullptr, *bufA = nullptr, *bufB = nullptr, *bufC = nullptr, *bufD = nullptr, *hbuf = nullptr;
+  double* sums = nullptr; float* mr = nullptr;
+  size_t act_elems = 0;
+};
+
+namespace ipk {
+
+static const TensorRefE& eneed(ipk_enc* e, const std::string& name, int64_t numel) {
+  auto it = e->tensors.find(name);
+  IPK_CHECK(it != e->tensors.end(), IPK_ERR_MISSING, "encoder: missing tensor '%s'", name.c_str());
+  IPK_CHECK(it->second.numel == numel, IPK_ERR_SHAPE, "encoder: tensor '%s' has %lld elements, expected %lld", name.c_str(),
+            (long long)it->second.numel, (long long)numel);
+  return it->second;
+}
+static float* ecopy(ipk_enc* e, const std::string& name, int n, cudaStream_t st) {
+  float* p = e->pool.alloc<float>(n);
+  IPK_CUDA(cudaMemcpyAsync(p, eneed(e, name, n).p, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return p;
+}
+static Conv3dDesc build_conv3d(ipk_enc* e, const std::string& name, int Cout, int CinSrc, int kt, int ky, int kx, int st_, int sy, int sx,
+                               int pt, int py, int px, cudaStream_t st) {
+  Conv3dDesc d;
+  d.Cin = round_up(CinSrc, 4); d.Cout = Cout;
+  d.kt = kt; d.ky = ky; d.kx = kx; d.st = st_; d.sy = sy; d.sx = sx; d.pt = pt; d.py = py; d.px = px;
+  const int ntaps = kt * ky * kx;
+  const TensorRefE& w = eneed(e, name, (int64_t)Cout * CinSrc * ntaps);
+  d.w = e->pool.alloc<float>((size_t)ntaps * d.Cin * Cout);
+  const long long total = (long long)ntaps * d.Cin * Cout;
+  pack_conv3d_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, st>>>((const float*)w.p, d.w, Cout, CinSrc, d.Cin, ntaps);
+  IPK_LAUNCH_CHECK();
+  return d;
+}
+static inline int out_extent(int n, int k, int s, int p) { return (n + 2 * p - k) / s + 1; }
+
+struct Vol { int T, H, W, C; size_t voxels() const { return (size_t)T * H * W; } };
+
+static Vol conv3d_out(const Conv3dDesc& d, const Vol& v) {
+  return Vol{out_extent(v.T, d.kt, d.st, d.pt), out_extent(v.H, d.ky, d.sy, d.py), out_extent(v.W, d.kx, d.sx, d.px), d.Cout};
+}
+
+static Vol run_conv3d(const Conv3dDesc& d, const float* in, const Vol& v, float* out, int B, cudaStream_t st) {
+  IPK_CHECK(v.C == d.Cin, IPK_ERR_STATE, "encoder: conv input has %d channels, layer expects %d", v.C, d.Cin);
+  const Vol o = conv3d_out(d, v);
+  Conv3dArgs a{in, out, d.w, B, v.T, v.H, v.W, d.Cin, o.T, o.H, o.W, d.Cout, d.kt, d.ky, d.kx, d.st, d.sy, d.sx, d.pt, d.py, d.px};
+  const long long M = (long long)B * o.voxels();
+  dim3 g((unsigned)((M + C3_BM - 1) / C3_BM), (unsigned)cdiv(d.Cout, C3_BN));
+  launch_k(conv3d_simt_kernel, g, dim3(256), 0, st, a);
+  return o;
+}
+
+// GroupNorm(16) over the (T, H, W) volume of each sample (+ affine, optional residual, ReLU)
+static void group_norm(ipk_enc* e, const float* x, const Vol& v, int B, const float* gw, const float* gb, const float* add, bool relu,
+                       float* out, cudaStream_t st) {
+  const long long P = (long long)v.voxels();
+  IPK_CUDA(cudaMemsetAsync(e->sums, 0, (size_t)B * v.C * 2 * sizeof(double), st));
+  NormApply s; s.x = x; s.F = B; s.C = v.C; s.P = P; s.stats_out = e->sums;
+  norm_apply(s, st);
+  finalize_stats(e->sums, e->mr, B, P, v.C, 16, 1e-5f, st);
+  NormApply n; n.x = x; n.F = B; n.C = v.C; n.P = P; n.mr = e->mr; n.w = gw; n.b = gb; n.add = add; n.act = relu ? ACT_RELU : ACT_NONE;
+  n.act_last = add != nullptr; n.out_f32 = out;
+  norm_apply(n, st);
+}
+
+// ResNetMotionEncoder.__init__ layer plan (motion_encoder.py:161-190)
+struct StagePlan { int inplanes, planes, st, sy, sx; };
+static std::vector<StagePlan> stage_plan(const ipk_enc_config& c) {
+  std::vector<int> ch(c.channels, c.channels + c.n_channels);
+  const bool first_down = ((int)ch.size() - 1 < (int)std::ceil(std::log2((double)c.max_frames))) || c.full_seq;
+  std::vector<StagePlan> v;
+  v.push_back({ch[0], ch[1], first_down ? 2 : 1, 1, 1});
+  v.push_back({ch[1], ch[2], 2, 2, 2});
+  v.push_back({ch[2], ch[3], 2, 2, 2});
+  bool has4 = c.full_seq && c.max_frames >= 16;
+  int s4t = 2, s4s = 1;
+  if (c.img_size / 8 > c.min_spatial_size) { has4 = true; s4s = 2; }
+  if (has4) {
+    if (ch.size() < 5) ch.push_back(ch.back());
+    v.push_back({ch[3], ch[4], s4t, s4s, s4s});
+  }
+  if (c.img_size / 16 > c.min_spatial_size) {
+    IPK_CHECK(ch.size() >= 6, IPK_ERR_INVALID, "encoder: layer5 needs ENC_M_channels[5]");
+    v.push_back({ch[4], ch[5], 2, 2, 2});
+  }
+  return v;
+}
+
+}  // namespace ipk
+
+extern "C" int ipk_enc_create(const ipk_enc_config* cfg, ipk_enc** out) {
+  IPK_TRY
+  IPK_CHECK(cfg && out, IPK_ERR_INVALID, "ipk_enc_create: null argument");
+  IPK_CHECK(cfg->n_channels >= 4 && cfg->n_channels <= IPK_MAX_DEC, IPK_ERR_INVALID, "encoder: ENC_M_channels needs 4..8 entries");
+  IPK_CHECK(cfg->z_dim > 0 && cfg->z_dim % 2 == 0 && cfg->max_batch > 0 && cfg->max_frames > 1 && cfg->img_size >= 32, IPK_ERR_INVALID, "encoder: bad sizes");
+  for (int i = 0; i < cfg->n_channels; ++i)
+    IPK_CHECK(cfg->channels[i] % 16 == 0, IPK_ERR_UNSUPPORTED, "encoder: channel counts must be multiples of 16 (GroupNorm(16))");
+  stage_plan(*cfg);
+  ipk_enc* e = new ipk_enc();
+  e->cfg = *cfg;
+  *out = e;
+  IPK_CATCH
+}
+
+extern "C" int ipk_enc_set_tensor(ipk_enc* e, const char* name, const void* dev_ptr, int64_t numel, int dtype) {
+  IPK_TRY
+  IPK_CHECK(e && name && dev_ptr, IPK_ERR_INVALID, "ipk_enc_set_tensor: null argument");
+  IPK_CHECK(!e->finalized, IPK_ERR_STATE, "ipk_enc_set_tensor after finalize");
+  IPK_CHECK(dtype == IPK_F32, IPK_ERR_SHAPE, "encoder: tensor '%s' must be fp32", name);
+  e->tensors[name] = TensorRefE{dev_ptr, numel};
+  IPK_CATCH
+}
+
+extern "C" int ipk_enc_finalize(ipk_enc* e, void* stream) {
+  IPK_TRY
+  IPK_CHECK(e && !e->finalized, IPK_ERR_STATE, "encoder: null or already finalized");
+  cudaStream_t st = (cudaStream_t)stream;
+  const ipk_enc_config& c = e->cfg;
+  e->stem = build_conv3d(e, "conv1.weight", c.channels[0], 3, 3, 7, 7, 2, 2, 2, 1, 3, 3, st);
+  e->stem_gw = ecopy(e, "bn1.weight", c.channels[0], st);
+  e->stem_gb = ecopy(e, "bn1.bias", c.channels[0], st);
+  auto plan = stage_plan(c);
+  // walk the shapes for the workspace while building
+  Vol v{c.max_frames + 1, c.img_size, c.img_size, 4};          // the second stage feeds max_frames + 1 frames (full_seq)
+  size_t maxe = v.voxels() * 4;
+  v = conv3d_out(e->stem, v);
+  maxe = std::max(maxe, v.voxels() * v.C);
+  for (size_t li = 0; li < plan.size(); ++li) {
+    const StagePlan& sp = plan[li];
+    int inp = sp.inplanes;
+    for (int b = 0; b < 2; ++b) {
+      const std::string p = "layer" + std::to_string(li + 1) + "." + std::to_string(b) + ".";
+      EncBlock blk;
+      const int s_t = b == 0 ? sp.st : 1, s_y = b == 0 ? sp.sy : 1, s_x = b == 0 ? sp.sx : 1;
+      blk.c1 = build_conv3d(e, p + "conv1.weight", sp.planes, inp, 3, 3, 3, s_t, s_y, s_x, 1, 1, 1, st);
+      blk.g1w = ecopy(e, p + "bn1.weight", sp.planes, st); blk.g1b = ecopy(e, p + "bn1.bias", sp.planes, st);
+      blk.c2 = build_conv3d(e, p + "conv2.weight", sp.planes, sp.planes, 3, 3, 3, 1, 1, 1, 1, 1, 1, st);
+      blk.g2w = ecopy(e, p + "bn2.weight", sp.planes, st); blk.g2b = ecopy(e, p + "bn2.bias", sp.planes, st);
+      blk.has_ds = b == 0 && (s_t != 1 || s_y != 1 || s_x != 1 || inp != sp.planes);
+      if (blk.has_ds) {
+        blk.ds = build_conv3d(e, p + "downsample.0.weight", sp.planes, inp, 1, 1, 1, s_t, s_y, s_x, 0, 0, 0, st);
+        blk.gdw = ecopy(e, p + "downsample.1.weight", sp.planes, st); blk.gdb = ecopy(e, p + "downsample.1.bias", sp.planes, st);
+      }
+      v = conv3d_out(blk.c1, v);
+      maxe = std::max(maxe, v.voxels() * v.C);
+      e->blocks.push_back(blk);
+      inp = sp.planes;
+    }
+  }
+  IPK_CHECK(v.H == 8 && v.W == 8, IPK_ERR_INVALID, "encoder: final grid is %dx%d, expected 8x8", v.H, v.W);
+  e->last_C = v.C;
+  // heads: conv_mu | conv_var, 2-D 3x3, pad 1
+  const int z = c.z_dim;
+  e->heads = conv_alloc(e->pool, IPK_PREC_FP32_SIMT, 9, v.C, 2 * z, true);
+  {
+    PackSrc s; s.N = z; s.Ksrc = v.C; s.kh = 3; s.kw = 3;
+    const std::vector<int> all9 = {0, 1, 2, 3, 4, 5, 6, 7, 8};
+    s.w = (const float*)eneed(e, "conv_mu.weight", (int64_t)z * v.C * 9).p;
+    conv_pack_into(e->heads, 0, s, all9, st);
+    conv_pack_bias(e->heads, 0, (const float*)eneed(e, "conv_mu.bias", z).p, z, 0.f, st);
+    s.w = (const float*)eneed(e, "conv_var.weight", (int64_t)z * v.C * 9).p;
+    conv_pack_into(e->heads, z, s, all9, st);
+    conv_pack_bias(e->heads, z, (const float*)eneed(e, "conv_var.bias", z).p, z, 0.f, st);
+  }
+  e->act_elems = maxe;
+  const size_t B = c.max_batch;
+  auto rb = [](size_t b) { return (b + 255) / 256 * 256; };
+  e->ws.init(5 * rb(B * maxe * 4) + rb(B * 64 * 2 * z * 4) + rb(B * 1024 * 2 * 8) + rb(B * 1024 * 2 * 4) + 65536);
+  e->X4 = e->ws.alloc<float>(B * maxe);
+  e->bufA = e->ws.alloc<float>(B * maxe);
+  e->bufB = e->ws.alloc<float>(B * maxe);
+  e->bufC = e->ws.alloc<float>(B * maxe);
+  e->bufD = e->ws.alloc<float>(B * maxe);
+  e->hbuf = e->ws.alloc<float>(B * 64 * 2 * z);
+  e->sums = e->ws.alloc<double>(B * 1024 * 2);
+  e->mr = e->ws.alloc<float>(B * 1024 * 2);
+  IPK_CUDA(cudaStreamSynchronize(st));
+  e->tensors.clear();
+  e->finalized = true;
+  IPK_CATCH
+}
+
+extern "C" int ipk_enc_forward(ipk_enc* e, const float* X, const float* eps, float* z_out, float* mu, float* logvar, int32_t B, int32_t T, void* stream) {
+  IPK_TRY
+  IPK_CHECK(e && e->finalized, IPK_ERR_STATE, "encoder not finalized");
+  IPK_CHECK(X && eps && z_out && mu && logvar, IPK_ERR_INVALID, "ipk_enc_forward: null buffer");
+  IPK_CHECK(B > 0 && B <= e->cfg.max_batch, IPK_ERR_INVALID, "encoder: batch %d outside (0, %d]", B, e->cfg.max_batch);
+  IPK_CHECK(T > 0 && T <= e->cfg.max_frames + 1, IPK_ERR_INVALID, "encoder: %d frames outside (0, %d]", T, e->cfg.max_frames + 1);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int S = e->cfg.img_size;
+  Vol v{T, S, S, 4};
+  {
+    const long long V = (long long)v.voxels();
+    ncdhw_to_ndhwc4_kernel<<<(int)std::min<long long>(((long long)B * V + 255) / 256, 148 * 32), 256, 0, st>>>(X, e->X4, B, V);
+    IPK_LAUNCH_CHECK();
+  }
+  // stem: Conv3d(3 -> C0, (3,7,7), stride 2, pad (1,3,3)) + GroupNorm(16) + ReLU
+  float* x = e->bufA;
+  {
+    Vol o = run_conv3d(e->stem, e->X4, v, e->bufB, B, st);
+    group_norm(e, e->bufB, o, B, e->stem_gw, e->stem_gb, nullptr, true, x, st);
+    v = o;
+  }
+  // BasicBlocks (motion_encoder.py:56-74): out = relu(gn2(conv2(relu(gn1(conv1(x))))) + residual)
+  for (const EncBlock& blk : e->blocks) {
+    float* y = e->bufB; float* t = e->bufC; float* r = e->bufD;
+    Vol o = run_conv3d(blk.c1, x, v, t, B, st);
+    group_norm(e, t, o, B, blk.g1w, blk.g1b, nullptr, true, y, st);
+    run_conv3d(blk.c2, y, o, t, B, st);
+    const float* res = x;
+    if (blk.has_ds) {
+      run_conv3d(blk.ds, x, v, y, B, st);
+      group_norm(e, y, o, B, blk.gdw, blk.gdb, nullptr, false, r, st);
+      res = r;
+    }
+    float* nx = (x == e->bufA) ? e->X4 : e->bufA;          // ping-pong the block output
+    group_norm(e, t, o, B, blk.g2w, blk.g2b, res, true, nx, st);
+    x = nx;
+    v = o;
+  }
+  IPK_CHECK(v.T == 1 && v.H == 8 && v.W == 8, IPK_ERR_INVALID, "encoder: %d frames leave a %dx%dx%d volume; the temporal extent must collapse to 1 "
+            "(motion_encoder.py:241 squeezes it)", T, v.T, v.H, v.W);
+  // conv_mu | conv_var (2-D 3x3) and the reparameterisation with host-supplied eps
+  {
+    ConvIn in; in.p = x; in.cstride = v.C; in.F = B; in.H = 8; in.W = 8;
+    ConvOut o; o.p = e->hbuf; o.cstride = 2 * e->cfg.z_dim; o.Ho = 8; o.Wo = 8; o.bias = e->heads.bias;
+    conv_run(e->heads, in, o, taps_3x3(), 1, st);
+    reparam_kernel<<<cdiv(B * e->cfg.z_dim * 64, 256), 256, 0, st>>>(e->hbuf, eps, z_out, mu, logvar, B, e->cfg.z_dim);
+    IPK_LAUNCH_CHECK();
+  }
+  IPK_CATCH
+}
+
+extern "C" int ipk_enc_destroy(ipk_enc* e) {
+  if (!e) return IPK_OK;
+  e->pool.release();
+  e->ws.release();
+  delete e;
+  return IPK_OK;
+}

@@ -141,6 +141,54 @@ def first_stage_param_spec(cfg):
     yield from conv("gen.out_conv.conv.", 3, dec[-1])
 
 
+def encoder_stages(cfg):
+    """Layer plan of ResNetMotionEncoder.__init__ (motion_encoder.py:161-190): [(name, inplanes, planes, stride)]."""
+    ch = list(cfg["ENC_M_channels"])
+    first_down = (len(ch) - 1 < int(math.ceil(math.log2(cfg["max_frames"])))) or cfg["full_seq"]
+    st = [("layer1", ch[0], ch[1], (2, 1, 1) if first_down else (1, 1, 1)), ("layer2", ch[1], ch[2], (2, 2, 2)),
+          ("layer3", ch[2], ch[3], (2, 2, 2))]
+    stride4 = (2, 1, 1) if (cfg["full_seq"] and cfg["max_frames"] >= 16) else None
+    if cfg["img_size"] // 8 > cfg.get("min_spatial_size", 8):
+        stride4 = (2, 2, 2)
+    if stride4 is not None:
+        if len(ch) < 5:
+            ch.append(ch[-1])
+        st.append(("layer4", ch[3], ch[4], stride4))
+    if cfg["img_size"] // 16 > cfg.get("min_spatial_size", 8):
+        st.append(("layer5", ch[4], ch[5], (2, 2, 2)))
+    return st
+
+
+def encoder_param_spec(cfg):
+    """(name, shape, dtype, is_buffer, init) for every tensor of ResNetMotionEncoder's state-dict."""
+    f32 = torch.float32
+    ch0 = cfg["ENC_M_channels"][0]
+
+    def gn(p, c):
+        yield p + "weight", (c,), f32, False, ("ones",)
+        yield p + "bias", (c,), f32, False, ("zeros",)
+
+    yield "conv1.weight", (ch0, 3, 3, 7, 7), f32, False, ("normal", math.sqrt(2.0 / (ch0 * 147)))      # kaiming_normal_, fan_out
+    yield from gn("bn1.", ch0)
+    stages = encoder_stages(cfg)
+    for name, inplanes, planes, stride in stages:
+        inp = inplanes
+        for b in range(2):
+            p = f"{name}.{b}."
+            yield p + "conv1.weight", (planes, inp, 3, 3, 3), f32, False, ("normal", math.sqrt(2.0 / (planes * 27)))
+            yield from gn(p + "bn1.", planes)
+            yield p + "conv2.weight", (planes, planes, 3, 3, 3), f32, False, ("normal", math.sqrt(2.0 / (planes * 27)))
+            yield from gn(p + "bn2.", planes)
+            if b == 0 and (stride != (1, 1, 1) or inp != planes):
+                yield p + "downsample.0.weight", (planes, inp, 1, 1, 1), f32, False, ("normal", math.sqrt(2.0 / planes))
+                yield from gn(p + "downsample.1.", planes)
+            inp = planes
+    last = stages[-1][2]
+    for head in ("conv_mu", "conv_var"):
+        yield head + ".weight", (cfg["z_dim"], last, 3, 3), f32, False, ("conv", last * 9)
+        yield head + ".bias", (cfg["z_dim"],), f32, False, ("conv_bias", last * 9)
+
+
 def init_tensor(shape, dtype, init, prev=None):
     kind = init[0]
     if kind == "zeros":

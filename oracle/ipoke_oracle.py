@@ -578,6 +578,107 @@ def sample_videos(flow_sd, flow_cfg, fs_sd, fs_cfg, z: Tensor, cond: Tensor, x0:
 
 
 # ----------------------------------------------------------------------------------------------
+# first-stage 3-D conv video encoder (training path: PokeMotionModel.encode_first_stage,
+# second_stage_video.py:352-359 -> ResNetMotionEncoder, models/modules/motion_models/motion_encoder.py:150-241)
+# ----------------------------------------------------------------------------------------------
+def encoder_config(z_dim=32, img_size=128, max_frames=10, full_seq=True, channels=None, min_spatial_size=8) -> dict:
+    """The keys ResNetMotionEncoder.__init__ reads from dic (motion_encoder.py:152-160); ENC_M_channels as in
+    config/first_stage.yaml:60."""
+    if channels is None:
+        channels = [64, 128, 256, 256, 256] if img_size == 128 else [64, 128, 256, 256]
+    return dict(z_dim=z_dim, img_size=img_size, max_frames=max_frames, full_seq=full_seq, ENC_M_channels=list(channels),
+                min_spatial_size=min_spatial_size, deterministic=False)
+
+
+def encoder_layers(cfg: dict) -> List[dict]:
+    """Layer plan of ResNetMotionEncoder.__init__ (motion_encoder.py:161-190): list of residual stages
+    dict(name, inplanes, planes, stride=(st,sy,sx), blocks=2)."""
+    ch = list(cfg["ENC_M_channels"])
+    max_frames = cfg["max_frames"]
+    first_block_down = (len(ch) - 1 < int(math.ceil(math.log2(max_frames)))) or cfg["full_seq"]      # :164-166
+    s1 = (2, 1, 1) if first_block_down else (1, 1, 1)
+    stages = [dict(name="layer1", inplanes=ch[0], planes=ch[1], stride=s1),
+              dict(name="layer2", inplanes=ch[1], planes=ch[2], stride=(2, 2, 2)),
+              dict(name="layer3", inplanes=ch[2], planes=ch[3], stride=(2, 2, 2))]
+    stride4 = (2, 1, 1) if (cfg["full_seq"] and max_frames >= 16) else None                             # :172
+    if cfg["img_size"] // 2 ** 3 > cfg["min_spatial_size"]:                                             # :174-175
+        stride4 = (2, 2, 2)
+    if stride4 is not None:
+        if len(ch) < 5:
+            ch.append(ch[-1])                                                                           # :179-181
+        stages.append(dict(name="layer4", inplanes=ch[3], planes=ch[4], stride=stride4))
+    if cfg["img_size"] // 2 ** 4 > cfg["min_spatial_size"]:                                             # :184-186
+        stages.append(dict(name="layer5", inplanes=ch[-2] if len(ch) > 5 else ch[4], planes=ch[5], stride=(2, 2, 2)))
+    return stages
+
+
+def synth_encoder_state_dict(cfg: dict, seed: int = 0) -> Dict[str, Tensor]:
+    """Seeded synthetic encoder checkpoint with the reference's keys/shapes: Conv3d kaiming-normal fan_out
+    (motion_encoder.py:192-194), GroupNorm weight ~ 1 + 0.1 N(0,1), bias ~ 0.05 N(0,1), 2-D heads nn.Conv2d default."""
+    gen = torch.Generator().manual_seed(seed)
+    sd: Dict[str, Tensor] = {}
+
+    def conv3(name, cout, cin, k):
+        fan_out = cout * k[0] * k[1] * k[2]
+        sd[name] = _nrm(gen, (cout, cin) + tuple(k), math.sqrt(2.0 / fan_out))
+
+    def gn(p, c):
+        sd[p + "weight"] = 1.0 + _nrm(gen, (c,), 0.1)
+        sd[p + "bias"] = _nrm(gen, (c,), 0.05)
+
+    ch0 = cfg["ENC_M_channels"][0]
+    conv3("conv1.weight", ch0, 3, (3, 7, 7))
+    gn("bn1.", ch0)
+    stages = encoder_layers(cfg)
+    for st in stages:
+        inp = st["inplanes"]
+        for b in range(2):
+            p = f"{st['name']}.{b}."
+            conv3(p + "conv1.weight", st["planes"], inp, (3, 3, 3))
+            gn(p + "bn1.", st["planes"])
+            conv3(p + "conv2.weight", st["planes"], st["planes"], (3, 3, 3))
+            gn(p + "bn2.", st["planes"])
+            if b == 0 and (st["stride"] != (1, 1, 1) or inp != st["planes"]):
+                conv3(p + "downsample.0.weight", st["planes"], inp, (1, 1, 1))
+                gn(p + "downsample.1.", st["planes"])
+            inp = st["planes"]
+    last = stages[-1]["planes"]
+    for head in ("conv_mu", "conv_var"):
+        b = 1.0 / math.sqrt(last * 9)
+        sd[head + ".weight"] = _uni(gen, (cfg["z_dim"], last, 3, 3), b)
+        sd[head + ".bias"] = _uni(gen, (cfg["z_dim"],), b)
+    return sd
+
+
+def encoder_forward(sd, cfg: dict, X: Tensor, eps: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    """ResNetMotionEncoder.forward (motion_encoder.py:224-241) with the reparameterisation noise `eps` supplied by the
+    caller (the reference draws it on the CPU generator, :220).  X: [B,3,T,H,W] -> (z, mu, logvar) each [B,z,8,8]."""
+    dt = X.dtype
+    w = lambda k: sd[k].to(dt)
+
+    def gnorm(x, p):
+        return F.group_norm(x, 16, w(p + "weight"), w(p + "bias"), 1e-5)
+
+    x = F.relu(gnorm(F.conv3d(X, w("conv1.weight"), None, stride=(2, 2, 2), padding=(1, 3, 3)), "bn1."))
+    for st in encoder_layers(cfg):
+        for b in range(2):
+            p = f"{st['name']}.{b}."
+            stride = st["stride"] if b == 0 else (1, 1, 1)
+            out = F.relu(gnorm(F.conv3d(x, w(p + "conv1.weight"), None, stride=stride, padding=1), p + "bn1."))      # BasicBlock :56-74
+            out = gnorm(F.conv3d(out, w(p + "conv2.weight"), None, stride=1, padding=1), p + "bn2.")
+            res = x
+            if (p + "downsample.0.weight") in sd:
+                res = gnorm(F.conv3d(x, w(p + "downsample.0.weight"), None, stride=stride), p + "downsample.1.")
+            x = F.relu(out + res)
+    assert x.shape[2] == 1, f"temporal extent {x.shape[2]} != 1 before squeeze (motion_encoder.py:241)"
+    emb = x.squeeze(2)
+    mu = F.conv2d(emb, w("conv_mu.weight"), w("conv_mu.bias"), padding=1)
+    logvar = F.conv2d(emb, w("conv_var.weight"), w("conv_var.bias"), padding=1)
+    z = eps.to(dt) * torch.exp(0.5 * logvar) + mu                                                                    # :218-222
+    return z, mu, logvar
+
+
+# ----------------------------------------------------------------------------------------------
 # synthetic inputs (SURVEY.md section 8d config 1)
 # ----------------------------------------------------------------------------------------------
 def synth_inputs(B: int, C0: int, h_channels: int, spatial: int, seed: int = 42):

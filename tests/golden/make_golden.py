@@ -43,6 +43,38 @@ FS_CASES = {
 }
 
 
+ENC_CASES = {
+    # name: (cfg kwargs, B, T, weight seed, input seed)
+    "enc_64": (dict(z_dim=32, img_size=64, max_frames=10), 2, 11, 41, 51),
+    "enc_128": (dict(z_dim=32, img_size=128, max_frames=10), 1, 11, 42, 52),
+}
+
+
+def run_enc_case(name, spec, out_dir):
+    kw, B, T, wseed, iseed = spec
+    cfg = O.encoder_config(**kw)
+    sd = O.synth_encoder_state_dict(cfg, seed=wseed)
+    m = ref_import.encoder_fn()(dic=dict(cfg, ENC_M_channels=list(cfg["ENC_M_channels"])))
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    g = torch.Generator().manual_seed(iseed)
+    X = torch.rand((B, 3, T, cfg["img_size"], cfg["img_size"]), generator=g) * 2 - 1
+    with torch.no_grad():
+        torch.manual_seed(iseed + 1)            # the reference draws eps on the default CPU generator (motion_encoder.py:220)
+        z_ref, mu_ref, lv_ref = m(X)
+        torch.manual_seed(iseed + 1)
+        eps = torch.FloatTensor(mu_ref.size()).normal_()
+        z_or, mu_or, lv_or = O.encoder_forward(sd, cfg, X, eps)
+        z64, mu64, lv64 = O.encoder_forward(sd, cfg, X.double(), eps.double())
+    fix = dict(kind="encoder", cfg_kwargs=kw, B=B, T=T, wseed=wseed, iseed=iseed, z=z_ref.clone(), mu=mu_ref.clone(), logvar=lv_ref.clone(),
+               eps=eps.clone(),
+               oracle_vs_ref=max((z_or - z_ref).abs().max().item(), (mu_or - mu_ref).abs().max().item(), (lv_or - lv_ref).abs().max().item()),
+               ref_fp32_vs_oracle_fp64=(mu64.float() - mu_ref).abs().max().item(), torch_version=torch.__version__)
+    torch.save(fix, os.path.join(out_dir, name + ".pt"))
+    print(f"{name}: z {tuple(z_ref.shape)} oracle-vs-ref {fix['oracle_vs_ref']:.2e} fp64 {fix['ref_fp32_vs_oracle_fp64']:.2e} "
+          f"mu std {mu_ref.std().item():.3f} logvar std {lv_ref.std().item():.3f}")
+
+
 def ref_flow(cfg, sd):
     Flow = ref_import.flow_cls()
     m = Flow(dict(cfg))
@@ -121,6 +153,9 @@ if __name__ == "__main__":
     for n, s in FS_CASES.items():
         if a.only in (None, n):
             run_fs_case(n, s, HERE)
+    for n, s in ENC_CASES.items():
+        if a.only in (None, n):
+            run_enc_case(n, s, HERE)
     if a.full:
         for n, s in FULL_FLOW_CASES.items():
             if a.only in (None, n):

@@ -39,3 +39,9 @@ def first_stage_parts():
     from models.modules.motion_models.rnn import ConvGRU
     from models.modules.autoencoders.fully_conv_models import SpadeCondConvDecoder
     return ConvGRU, SpadeCondConvDecoder
+
+
+def encoder_fn():
+    install()
+    from models.modules.motion_models.motion_encoder import resnet18_alternative
+    return resnet18_alternative

@@ -71,6 +71,7 @@ def test_struct_layout_matches_header():
     L = _lib()
     assert ctypes.sizeof(L.FlowConfig) == 4 * (4 + 32 + 5)
     assert ctypes.sizeof(L.FsConfig) == 4 * (4 + 8 + 4)
+    assert ctypes.sizeof(L.EncConfig) == 4 * (5 + 8 + 2)
     src = open(HEADER).read()
     assert "#define IPK_MAX_LEVELS 32" in src and "#define IPK_MAX_DEC 8" in src
 
@@ -111,3 +112,11 @@ def test_state_dict_layout_matches_oracle_checkpoint():
     assert sorted(own.keys()) == sorted(dsd.keys())
     for k in dsd:
         assert own[k].shape == dsd[k].shape, k
+    for size in (64, 128):
+        ecfg = O.encoder_config(z_dim=32, img_size=size, max_frames=10)
+        esd = O.synth_encoder_state_dict(ecfg, seed=0)
+        e = ipk.ResNetMotionEncoder(dict(ecfg))
+        own = e.state_dict()
+        assert sorted(own.keys()) == sorted(esd.keys())
+        for k in esd:
+            assert own[k].shape == esd[k].shape, k

@@ -41,6 +41,21 @@ def test_first_stage_oracle_matches_reference(name):
     assert (frames - fx["frames"]).abs().max().item() < 5e-5
 
 
+@pytest.mark.parametrize("name", ["enc_64", "enc_128"])
+def test_encoder_oracle_matches_reference(name):
+    """3-D conv video encoder (training path): oracle restatement vs the reference's resnet18_alternative output."""
+    fx = golden(name)
+    cfg = O.encoder_config(**fx["cfg_kwargs"])
+    sd = O.synth_encoder_state_dict(cfg, seed=fx["wseed"])
+    g = torch.Generator().manual_seed(fx["iseed"])
+    X = torch.rand((fx["B"], 3, fx["T"], cfg["img_size"], cfg["img_size"]), generator=g) * 2 - 1
+    with torch.no_grad():
+        z, mu, lv = O.encoder_forward(sd, cfg, X, fx["eps"])
+    assert z.shape == fx["z"].shape == (fx["B"], cfg["z_dim"], 8, 8)
+    for a, b in ((z, fx["z"]), (mu, fx["mu"]), (lv, fx["logvar"])):
+        assert (a - b).abs().max().item() < 5e-5
+
+
 def test_shuffle_roundtrip_exact():
     cfg = O.flow_config(flow_in_channels=16, flow_mid_channels=16, h_channels=4, num_steps=[1], factor=2)
     sd = O.synth_flow_state_dict(cfg, seed=9)
