@@ -16,6 +16,8 @@
  *                   (ConvGRU.forward                               models/modules/motion_models/rnn.py:104-133,
  *                    SpadeCondConvDecoder.forward                  models/modules/autoencoders/fully_conv_models.py:166-177)
  *   ipk_sample_* <- PokeMotionModel.forward_sample loop body       models/second_stage_video.py:333-341
+ *   ipk_cenc_*   <- ConvEncoder.forward (poke embedder / conditioner)  models/modules/autoencoders/fully_conv_models.py:74-88
+ *                   as called by make_flow_input                    models/second_stage_video.py:268-287
  *   ipk_enc_*    <- PokeMotionModel.encode_first_stage             models/second_stage_video.py:352-359
  *                   (ResNetMotionEncoder.forward                   models/modules/motion_models/motion_encoder.py:224-241)
  *   ipk_*_set_tensor takes the reference's state-dict key names unchanged.
@@ -91,9 +93,20 @@ typedef struct ipk_enc_config {
   int32_t max_batch;
 } ipk_enc_config;
 
+/* ConvEncoder(nf_in, nf_max, n_stages, variational=False) as wired by FirstStageWrapper (fully_conv_models.py:9-22). */
+typedef struct ipk_cenc_config {
+  int32_t nf_in;                      /* 2 (poke map) or 3 (image); 5 with poke_and_image is not supported yet */
+  int32_t nf_max;
+  int32_t spatial;                    /* input H = W                                       */
+  int32_t min_spatial_size;
+  int32_t n_stages;                   /* log2(spatial / min_spatial_size)                  */
+  int32_t max_batch;
+} ipk_cenc_config;
+
 typedef struct ipk_flow ipk_flow;
 typedef struct ipk_fs ipk_fs;
 typedef struct ipk_enc ipk_enc;
+typedef struct ipk_cenc ipk_cenc;
 
 int ipk_version(void);
 const char* ipk_last_error(void);
@@ -138,6 +151,14 @@ int ipk_enc_finalize(ipk_enc* e, void* stream);
  * -> z = eps * exp(logvar / 2) + mu, mu, logvar, each [B,z,8,8] */
 int ipk_enc_forward(ipk_enc* e, const float* X, const float* eps, float* z, float* mu, float* logvar, int32_t B, int32_t T, void* stream);
 int ipk_enc_destroy(ipk_enc* e);
+
+/* ---- conditioning encoders (frozen ConvEncoder of the poke embedder / image conditioner) ---- */
+int ipk_cenc_create(const ipk_cenc_config* cfg, ipk_cenc** out);
+int ipk_cenc_set_tensor(ipk_cenc* e, const char* name, const void* dev_ptr, int64_t numel, int dtype);
+int ipk_cenc_finalize(ipk_cenc* e, void* stream);
+/* x[B,nf_in,S,S] -> out[B,nf_max,8,8] (after the bottleneck) and, if non-null, mean[B,nf_max,8,8] (before it) */
+int ipk_cenc_forward(ipk_cenc* e, const float* x, float* out, float* mean, int32_t B, void* stream);
+int ipk_cenc_destroy(ipk_cenc* e);
 
 /* ---- whole sampling step with DEVICE buffers: flow inverse -> GRU + decoder ---- */
 int ipk_sample(ipk_flow* f, ipk_fs* d, const float* z, const float* cond, const float* x0, float* frames,

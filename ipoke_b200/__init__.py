@@ -2,6 +2,7 @@
 latent ConvGRU + SPADE decoder) behind the reference's module interfaces.  All compute is hand-written sm_100a CUDA in
 libipoke_b200.so; there is no CPU / PyTorch fallback."""
 from . import _lib  # noqa: F401
+from .cond_encoder import ConvEncoder, make_cond  # noqa: F401
 from .encoder import ResNetMotionEncoder, encode_first_stage  # noqa: F401
 from .first_stage import SpadeCondMotionDecoder, decode_first_stage  # noqa: F401
 from .flow import SupervisedMacowTransformer, flow_nll  # noqa: F401

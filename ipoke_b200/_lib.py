@@ -34,10 +34,16 @@ class EncConfig(ctypes.Structure):
                 ("max_batch", ctypes.c_int32)]
 
 
+class CencConfig(ctypes.Structure):
+    _fields_ = [("nf_in", ctypes.c_int32), ("nf_max", ctypes.c_int32), ("spatial", ctypes.c_int32), ("min_spatial_size", ctypes.c_int32),
+                ("n_stages", ctypes.c_int32), ("max_batch", ctypes.c_int32)]
+
+
 EXPORTS = [
     "ipk_version", "ipk_last_error", "ipk_launch_count", "ipk_launch_count_reset", "ipk_prof_enable", "ipk_prof_report",
     "ipk_flow_create", "ipk_flow_set_tensor", "ipk_flow_finalize", "ipk_flow_reverse", "ipk_flow_forward", "ipk_flow_destroy",
     "ipk_fs_create", "ipk_fs_set_tensor", "ipk_fs_finalize", "ipk_fs_decode", "ipk_fs_gru_step", "ipk_fs_gen", "ipk_fs_destroy",
+    "ipk_cenc_create", "ipk_cenc_set_tensor", "ipk_cenc_finalize", "ipk_cenc_forward", "ipk_cenc_destroy",
     "ipk_enc_create", "ipk_enc_set_tensor", "ipk_enc_finalize", "ipk_enc_forward", "ipk_enc_destroy",
     "ipk_sample", "ipk_sample_host", "ipk_test_gemm", "ipk_test_conv3x3", "ipk_test_convT3x3",
 ]
@@ -75,6 +81,11 @@ def lib():
     L.ipk_fs_gru_step.argtypes = [vp, vp, vp, vp, i32, vp]
     L.ipk_fs_gen.argtypes = [vp, vp, vp, vp, i32, vp]
     L.ipk_fs_destroy.argtypes = [vp]
+    L.ipk_cenc_create.argtypes = [ctypes.POINTER(CencConfig), ctypes.POINTER(vp)]
+    L.ipk_cenc_set_tensor.argtypes = [vp, cp, vp, i64, ctypes.c_int]
+    L.ipk_cenc_finalize.argtypes = [vp, vp]
+    L.ipk_cenc_forward.argtypes = [vp, vp, vp, vp, i32, vp]
+    L.ipk_cenc_destroy.argtypes = [vp]
     L.ipk_enc_create.argtypes = [ctypes.POINTER(EncConfig), ctypes.POINTER(vp)]
     L.ipk_enc_set_tensor.argtypes = [vp, cp, vp, i64, ctypes.c_int]
     L.ipk_enc_finalize.argtypes = [vp, vp]
@@ -87,7 +98,7 @@ def lib():
     L.ipk_test_convT3x3.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
-        if name.startswith(("ipk_flow_", "ipk_fs_", "ipk_enc_", "ipk_sample", "ipk_test_")):
+        if name.startswith(("ipk_flow_", "ipk_fs_", "ipk_enc_", "ipk_cenc_", "ipk_sample", "ipk_test_")):
             fn.restype = ctypes.c_int
     _lib = L
     return L

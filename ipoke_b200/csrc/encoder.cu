@@ -21,10 +21,11 @@ struct Conv3dDesc {
   int Cin, Cout;          // Cin as stored (multiple of 4)
   int kt, ky, kx, st, sy, sx, pt, py, px;
   float* w = nullptr;     // [kt][ky][kx][Cin][Cout]
+  float* bias = nullptr;  // [Cout] or null
 };
 
 struct Conv3dArgs {
-  const float* in; float* out; const float* w;
+  const float* in; float* out; const float* w; const float* bias;
   int B, Ti, Hi, Wi, Cin, To, Ho, Wo, Cout;
   int kt, ky, kx, st, sy, sx, pt, py, px;
 };
@@ -101,17 +102,20 @@ __global__ void __launch_bounds__(256) conv3d_simt_kernel(const Conv3dArgs a) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx * 4 + j;
-      if (n < a.Cout) a.out[(size_t)m * a.Cout + n] = acc[i][j];
+      if (n < a.Cout) a.out[(size_t)m * a.Cout + n] = acc[i][j] + (a.bias ? __ldg(a.bias + n) : 0.f);
     }
   }
 }
 
 // w: OIDHW [Cout][CinSrc][kt][ky][kx] -> [tap][Cin (zero padded)][Cout]
-__global__ void pack_conv3d_kernel(const float* __restrict__ w, float* __restrict__ dst, int Cout, int CinSrc, int Cin, int ntaps) {
+__global__ void pack_conv3d_kernel(const float* __restrict__ w, float* __restrict__ dst, int Cout, int CinSrc, int Cin, int ntaps,
+                                   const float* __restrict__ sigma) {
   const long long total = (long long)ntaps * Cin * Cout;
+  const float inv = sigma ? 1.0f / sigma[0] : 1.0f;     // eval-mode spectral norm: W / sigma
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int n = (int)(e % Cout), c = (int)((e / Cout) % Cin), tap = (int)(e / ((long long)Cout * Cin));
-    dst[e] = c < CinSrc ? w[((size_t)n * CinSrc + c) * ntaps + tap] : 0.f;
+    dst[e] = c < CinSrc ? (sigma ? w[((size_t)n * CinSrc + c) * ntaps + tap] / sigma[0] : w[((size_t)n * CinSrc + c) * ntaps + tap]) : 0.f;
+    (void)inv;
   }
 }
 
@@ -122,6 +126,16 @@ __global__ void ncdhw_to_ndhwc4_kernel(const float* __restrict__ in, float* __re
     const long long b = e / V, v = e % V;
     const float* ip = in + (size_t)b * 3 * V + v;
     ((float4*)out)[e] = make_float4(ip[0], ip[V], ip[2 * V], 0.f);
+  }
+}
+
+// x [B][C][P] (NCHW, C <= 4) -> [B][P][4] (missing channels zero)
+__global__ void nchw_to_nhwc4_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int C, long long P) {
+  const long long total = (long long)B * P;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long b = e / P, p = e % P;
+    const float* ip = in + (size_t)b * C * P + p;
+    ((float4*)out)[e] = make_float4(ip[0], C > 1 ? ip[P] : 0.f, C > 2 ? ip[2 * P] : 0.f, C > 3 ? ip[3 * P] : 0.f);
   }
 }
 
@@ -188,7 +202,7 @@ static Conv3dDesc build_conv3d(ipk_enc* e, const std::string& name, int Cout, in
   const TensorRefE& w = eneed(e, name, (int64_t)Cout * CinSrc * ntaps);
   d.w = e->pool.alloc<float>((size_t)ntaps * d.Cin * Cout);
   const long long total = (long long)ntaps * d.Cin * Cout;
-  pack_conv3d_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, st>>>((const float*)w.p, d.w, Cout, CinSrc, d.Cin, ntaps);
+  pack_conv3d_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, st>>>((const float*)w.p, d.w, Cout, CinSrc, d.Cin, ntaps, nullptr);
   IPK_LAUNCH_CHECK();
   return d;
 }
@@ -203,7 +217,7 @@ static Vol conv3d_out(const Conv3dDesc& d, const Vol& v) {
 static Vol run_conv3d(const Conv3dDesc& d, const float* in, const Vol& v, float* out, int B, cudaStream_t st) {
   IPK_CHECK(v.C == d.Cin, IPK_ERR_STATE, "encoder: conv input has %d channels, layer expects %d", v.C, d.Cin);
   const Vol o = conv3d_out(d, v);
-  Conv3dArgs a{in, out, d.w, B, v.T, v.H, v.W, d.Cin, o.T, o.H, o.W, d.Cout, d.kt, d.ky, d.kx, d.st, d.sy, d.sx, d.pt, d.py, d.px};
+  Conv3dArgs a{in, out, d.w, d.bias, B, v.T, v.H, v.W, d.Cin, o.T, o.H, o.W, d.Cout, d.kt, d.ky, d.kx, d.st, d.sy, d.sx, d.pt, d.py, d.px};
   const long long M = (long long)B * o.voxels();
   dim3 g((unsigned)((M + C3_BM - 1) / C3_BM), (unsigned)cdiv(d.Cout, C3_BN));
   launch_k(conv3d_simt_kernel, g, dim3(256), 0, st, a);
@@ -392,6 +406,199 @@ extern "C" int ipk_enc_forward(ipk_enc* e, const float* X, const float* eps, flo
 }
 
 extern "C" int ipk_enc_destroy(ipk_enc* e) {
+  if (!e) return IPK_OK;
+  e->pool.release();
+  e->ws.release();
+  delete e;
+  return IPK_OK;
+}
+
+
+// ================================================================================================ conditioning encoders
+// ConvEncoder (models/modules/autoencoders/fully_conv_models.py:28-94), deterministic: the frozen poke embedder and image
+// conditioner of make_flow_input (models/second_stage_video.py:268-287).  Stride-2 3x3 convs run on the same implicit-GEMM
+// kernel as the video encoder (T = 1); Group/InstanceNorm + ELU + residual through the shared norm pass.
+namespace ipk {
+struct CBlock {                 // Conv2dBlock: conv (+bias) -> norm -> act
+  Conv3dDesc conv;
+  float *gw = nullptr, *gb = nullptr;   // GroupNorm affine (null: InstanceNorm, no affine)
+};
+}  // namespace ipk
+
+struct ipk_cenc {
+  ipk_cenc_config cfg;
+  std::map<std::string, TensorRefE> tensors;
+  bool finalized = false;
+  DevPool pool;
+  Arena ws;
+  CBlock stem;
+  struct Res { CBlock c1, c2, rc; bool has_rc; int stride; };
+  std::vector<Res> blocks;     // stride-2 ResBlocks, then the bottleneck ResBlock (stride 1)
+  float *X4 = nullptr, *bufA = nullptr, *bufB = nullptr, *bufC = nullptr, *bufD = nullptr;
+  double* sums = nullptr; float* mr = nullptr;
+};
+
+namespace ipk {
+
+static const TensorRefE& cneed(ipk_cenc* e, const std::string& name, int64_t numel) {
+  auto it = e->tensors.find(name);
+  IPK_CHECK(it != e->tensors.end(), IPK_ERR_MISSING, "cond encoder: missing tensor '%s'", name.c_str());
+  IPK_CHECK(it->second.numel == numel, IPK_ERR_SHAPE, "cond encoder: tensor '%s' has %lld elements, expected %lld", name.c_str(),
+            (long long)it->second.numel, (long long)numel);
+  return it->second;
+}
+static bool chas(ipk_cenc* e, const std::string& name) { return e->tensors.find(name) != e->tensors.end(); }
+
+static CBlock build_cblock(ipk_cenc* e, const std::string& p, int Cout, int CinSrc, int stride, bool group_norm_affine, cudaStream_t st) {
+  CBlock b;
+  Conv3dDesc& d = b.conv;
+  d.Cin = round_up(CinSrc, 4); d.Cout = Cout;
+  d.kt = 1; d.ky = 3; d.kx = 3; d.st = 1; d.sy = stride; d.sx = stride; d.pt = 0; d.py = 1; d.px = 1;
+  const int64_t numel = (int64_t)Cout * CinSrc * 9;
+  const float* w; const float* sigma = nullptr;
+  if (chas(e, p + "conv.weight_orig")) {
+    w = (const float*)cneed(e, p + "conv.weight_orig", numel).p;
+    float* sg = e->pool.alloc<float>(1);
+    spectral_sigma(w, (const float*)cneed(e, p + "conv.weight_u", Cout).p, (const float*)cneed(e, p + "conv.weight_v", (int64_t)CinSrc * 9).p, sg,
+                   Cout, CinSrc, 9, false, st);
+    sigma = sg;
+  } else {
+    w = (const float*)cneed(e, p + "conv.weight", numel).p;
+  }
+  d.w = e->pool.alloc<float>((size_t)9 * d.Cin * Cout);
+  const long long total = 9LL * d.Cin * Cout;
+  pack_conv3d_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, st>>>(w, d.w, Cout, CinSrc, d.Cin, 9, sigma);
+  IPK_LAUNCH_CHECK();
+  d.bias = e->pool.alloc<float>(Cout);
+  IPK_CUDA(cudaMemcpyAsync(d.bias, cneed(e, p + "conv.bias", Cout).p, Cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (group_norm_affine) {
+    b.gw = e->pool.alloc<float>(Cout); b.gb = e->pool.alloc<float>(Cout);
+    IPK_CUDA(cudaMemcpyAsync(b.gw, cneed(e, p + "norm.weight", Cout).p, Cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    IPK_CUDA(cudaMemcpyAsync(b.gb, cneed(e, p + "norm.bias", Cout).p, Cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  return b;
+}
+
+// Conv2dBlock.forward (util.py:256-273): conv -> GroupNorm(16) | InstanceNorm -> activation [-> + residual]
+static Vol run_cblock(ipk_cenc* e, const CBlock& b, const float* in, const Vol& v, float* tmp, float* out, int B, int act, const float* add,
+                      cudaStream_t st) {
+  const Vol o = run_conv3d(b.conv, in, v, tmp, B, st);
+  const long long P = (long long)o.voxels();
+  IPK_CUDA(cudaMemsetAsync(e->sums, 0, (size_t)B * o.C * 2 * sizeof(double), st));
+  NormApply s; s.x = tmp; s.F = B; s.C = o.C; s.P = P; s.stats_out = e->sums;
+  norm_apply(s, st);
+  finalize_stats(e->sums, e->mr, B, P, o.C, b.gw ? 16 : 0, 1e-5f, st);
+  NormApply n; n.x = tmp; n.F = B; n.C = o.C; n.P = P; n.mr = e->mr; n.w = b.gw; n.b = b.gb; n.act = act; n.add = add; n.out_f32 = out;
+  norm_apply(n, st);
+  return o;
+}
+
+static std::vector<int> cenc_widths(const ipk_cenc_config& c) {
+  std::vector<int> w{32};
+  for (int i = 1; i < c.n_stages; ++i) w.push_back(std::min(w.back() * 2, c.nf_max));
+  return w;
+}
+
+}  // namespace ipk
+
+extern "C" int ipk_cenc_create(const ipk_cenc_config* cfg, ipk_cenc** out) {
+  IPK_TRY
+  IPK_CHECK(cfg && out, IPK_ERR_INVALID, "ipk_cenc_create: null argument");
+  IPK_CHECK(cfg->nf_in >= 1 && cfg->nf_in <= 4, IPK_ERR_UNSUPPORTED, "cond encoder: nf_in must be 1..4 (got %d)", cfg->nf_in);
+  IPK_CHECK(cfg->nf_max % 16 == 0 && cfg->nf_max >= 32, IPK_ERR_UNSUPPORTED, "cond encoder: nf_max must be a multiple of 16 >= 32");
+  IPK_CHECK(cfg->n_stages >= 1 && cfg->n_stages <= 8 && cfg->spatial == (cfg->min_spatial_size << cfg->n_stages), IPK_ERR_INVALID,
+            "cond encoder: spatial %d != min_spatial_size %d << n_stages %d", cfg->spatial, cfg->min_spatial_size, cfg->n_stages);
+  IPK_CHECK(cfg->max_batch > 0, IPK_ERR_INVALID, "cond encoder: max_batch must be positive");
+  ipk_cenc* e = new ipk_cenc();
+  e->cfg = *cfg;
+  *out = e;
+  IPK_CATCH
+}
+
+extern "C" int ipk_cenc_set_tensor(ipk_cenc* e, const char* name, const void* dev_ptr, int64_t numel, int dtype) {
+  IPK_TRY
+  IPK_CHECK(e && name && dev_ptr, IPK_ERR_INVALID, "ipk_cenc_set_tensor: null argument");
+  IPK_CHECK(!e->finalized, IPK_ERR_STATE, "ipk_cenc_set_tensor after finalize");
+  IPK_CHECK(dtype == IPK_F32, IPK_ERR_SHAPE, "cond encoder: tensor '%s' must be fp32", name);
+  e->tensors[name] = TensorRefE{dev_ptr, numel};
+  IPK_CATCH
+}
+
+extern "C" int ipk_cenc_finalize(ipk_cenc* e, void* stream) {
+  IPK_TRY
+  IPK_CHECK(e && !e->finalized, IPK_ERR_STATE, "cond encoder: null or already finalized");
+  cudaStream_t st = (cudaStream_t)stream;
+  const ipk_cenc_config& c = e->cfg;
+  const std::vector<int> w = cenc_widths(c);
+  e->stem = build_cblock(e, "model.0.", w[0], c.nf_in, 2, true, st);
+  for (size_t i = 1; i < w.size(); ++i) {
+    const std::string p = "model." + std::to_string(i) + ".";
+    ipk_cenc::Res r;
+    r.c1 = build_cblock(e, p + "conv1.", w[i], w[i - 1], 2, true, st);
+    r.c2 = build_cblock(e, p + "conv2.", w[i], w[i], 1, true, st);
+    r.rc = build_cblock(e, p + "res_conv.", w[i], w[i - 1], 2, false, st);
+    r.has_rc = true; r.stride = 2;
+    e->blocks.push_back(r);
+  }
+  {
+    const std::string p = "bottleneck.0.";
+    ipk_cenc::Res r;
+    r.c1 = build_cblock(e, p + "conv1.", c.nf_max, w.back(), 1, true, st);
+    r.c2 = build_cblock(e, p + "conv2.", c.nf_max, c.nf_max, 1, true, st);
+    r.has_rc = w.back() != c.nf_max; r.stride = 1;
+    if (r.has_rc) r.rc = build_cblock(e, p + "res_conv.", c.nf_max, w.back(), 1, false, st);
+    e->blocks.push_back(r);
+  }
+  const size_t B = c.max_batch;
+  const size_t maxe = std::max<size_t>((size_t)c.spatial * c.spatial * 4, (size_t)(c.spatial / 2) * (c.spatial / 2) * std::max(w[0], c.nf_max));
+  auto rb = [](size_t b) { return (b + 255) / 256 * 256; };
+  e->ws.init(5 * rb(B * maxe * 4) + rb(B * 1024 * 2 * 8) + rb(B * 1024 * 2 * 4) + 65536);
+  e->X4 = e->ws.alloc<float>(B * maxe);
+  e->bufA = e->ws.alloc<float>(B * maxe);
+  e->bufB = e->ws.alloc<float>(B * maxe);
+  e->bufC = e->ws.alloc<float>(B * maxe);
+  e->bufD = e->ws.alloc<float>(B * maxe);
+  e->sums = e->ws.alloc<double>(B * 1024 * 2);
+  e->mr = e->ws.alloc<float>(B * 1024 * 2);
+  IPK_CUDA(cudaStreamSynchronize(st));
+  e->tensors.clear();
+  e->finalized = true;
+  IPK_CATCH
+}
+
+extern "C" int ipk_cenc_forward(ipk_cenc* e, const float* x, float* out, float* mean, int32_t B, void* stream) {
+  IPK_TRY
+  IPK_CHECK(e && e->finalized, IPK_ERR_STATE, "cond encoder not finalized");
+  IPK_CHECK(x && out, IPK_ERR_INVALID, "ipk_cenc_forward: null buffer");
+  IPK_CHECK(B > 0 && B <= e->cfg.max_batch, IPK_ERR_INVALID, "cond encoder: batch %d outside (0, %d]", B, e->cfg.max_batch);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int S = e->cfg.spatial;
+  {
+    const long long P = (long long)S * S;
+    nchw_to_nhwc4_kernel<<<(int)std::min<long long>(((long long)B * P + 255) / 256, 148 * 32), 256, 0, st>>>(x, e->X4, B, e->cfg.nf_in, P);
+    IPK_LAUNCH_CHECK();
+  }
+  Vol v{1, S, S, 4};
+  float* cur = e->bufA;
+  v = run_cblock(e, e->stem, e->X4, v, e->bufB, cur, B, ACT_ELU, nullptr, st);
+  for (size_t i = 0; i < e->blocks.size(); ++i) {
+    const ipk_cenc::Res& r = e->blocks[i];
+    if (i + 1 == e->blocks.size() && mean) nhwc_to_nchw(cur, mean, B, v.C, v.H * v.W, v.C, st);     // `mean` = input of the bottleneck
+    // ResBlock.forward (util.py:185-192): out = conv2(conv1(x)) + res_conv(x)
+    const float* res = cur;
+    if (r.has_rc) { run_cblock(e, r.rc, cur, v, e->bufB, e->bufD, B, ACT_ELU, nullptr, st); res = e->bufD; }
+    Vol o = run_cblock(e, r.c1, cur, v, e->bufB, e->bufC, B, ACT_ELU, nullptr, st);
+    float* nxt = (cur == e->bufA) ? e->X4 : e->bufA;
+    run_cblock(e, r.c2, e->bufC, o, e->bufB, nxt, B, ACT_NONE, res, st);
+    cur = nxt;
+    v = o;
+  }
+  IPK_CHECK(v.H == e->cfg.min_spatial_size && v.C == e->cfg.nf_max, IPK_ERR_STATE, "cond encoder: unexpected output volume %dx%dx%d", v.H, v.W, v.C);
+  nhwc_to_nchw(cur, out, B, v.C, v.H * v.W, v.C, st);
+  IPK_CATCH
+}
+
+extern "C" int ipk_cenc_destroy(ipk_cenc* e) {
   if (!e) return IPK_OK;
   e->pool.release();
   e->ws.release();

@@ -15,10 +15,21 @@ from .flow import SupervisedMacowTransformer
 
 
 class PokeMotionSampler:
-    def __init__(self, flow: SupervisedMacowTransformer, first_stage_model: SpadeCondMotionDecoder):
+    def __init__(self, flow: SupervisedMacowTransformer, first_stage_model: SpadeCondMotionDecoder, conditioner=None, poke_embedder=None):
+        """conditioner / poke_embedder: optional ipoke_b200.ConvEncoder drop-ins for `self.conditioner.encoder` and
+        `self.poke_embedder.encoder` (second_stage_video.py:274,281); without them the caller passes `cond` itself."""
         self.flow = flow
         self.first_stage_model = first_stage_model
+        self.conditioner = conditioner
+        self.poke_embedder = poke_embedder
         self._pinned = {}
+
+    def make_cond(self, x0, poke):
+        """Conditioning half of make_flow_input (second_stage_video.py:268-287,311): cat[conditioner(x0), poke_embedder(poke)]."""
+        from .cond_encoder import make_cond
+        if self.conditioner is None or self.poke_embedder is None:
+            raise RuntimeError("PokeMotionSampler.make_cond needs the conditioner and poke embedder encoders")
+        return make_cond(self.conditioner, self.poke_embedder, x0, poke)
 
     # -- second_stage_video.py:289-300: z ~ N(0, I) drawn on the CPU default generator, then moved to the device
     def draw_noise(self, batch_size, device=None, generator=None):
@@ -71,11 +82,15 @@ class PokeMotionSampler:
                                                   B, int(length), _lib.current_stream_ptr()), "ipk_sample_host")
         return out
 
-    def forward_sample(self, X, cond, n_samples=1, n_logged_vids=1, length=None, add_first_frame=False):
-        """PokeMotionModel.forward_sample (second_stage_video.py:326-343): returns a list of n_samples CPU tensors."""
+    def forward_sample(self, X, cond=None, n_samples=1, n_logged_vids=1, length=None, add_first_frame=False, poke=None):
+        """PokeMotionModel.forward_sample (second_stage_video.py:326-343): returns a list of n_samples CPU tensors.
+        Pass `cond`, or `poke` to have it computed by the conditioning encoders -- ONCE for all samples (the reference
+        re-encodes the same batch for every sample, second_stage_video.py:332-333; the result is sample-invariant)."""
         videos = []
         if length is None:
             length = X.size(1) - 1
+        if cond is None:
+            cond = self.make_cond(X[:, 0], poke)
         with torch.no_grad():
             for _ in range(n_samples):
                 z = self.draw_noise(X.size(0)).type_as(X)

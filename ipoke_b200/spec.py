@@ -189,6 +189,46 @@ def encoder_param_spec(cfg):
         yield head + ".bias", (cfg["z_dim"],), f32, False, ("conv_bias", last * 9)
 
 
+def cond_encoder_param_spec(nf_in, nf_max, n_stages):
+    """(name, shape, dtype, is_buffer, init) for ConvEncoder(nf_in, nf_max, n_stages, variational=False)
+    (models/modules/autoencoders/fully_conv_models.py:28-72): spectral-normed stride-2 blocks + a plain bottleneck ResBlock."""
+    f32 = torch.float32
+    widths = [32]
+    for _ in range(n_stages - 1):
+        widths.append(min(widths[-1] * 2, nf_max))
+
+    def gn(p, c):
+        yield p + "weight", (c,), f32, False, ("ones",)
+        yield p + "bias", (c,), f32, False, ("zeros",)
+
+    def conv(p, cout, cin, sn):
+        if sn:
+            yield p + "bias", (cout,), f32, False, ("conv_bias", cin * 9)
+            yield p + "weight_orig", (cout, cin, 3, 3), f32, False, ("conv", cin * 9)
+            yield p + "weight_u", (cout,), f32, True, ("unit",)
+            yield p + "weight_v", (cin * 9,), f32, True, ("unit",)
+        else:
+            yield p + "weight", (cout, cin, 3, 3), f32, False, ("conv", cin * 9)
+            yield p + "bias", (cout,), f32, False, ("conv_bias", cin * 9)
+
+    yield from gn("model.0.norm.", widths[0])
+    yield from conv("model.0.conv.", widths[0], nf_in, True)
+    for i in range(1, len(widths)):
+        p = f"model.{i}."
+        yield from gn(p + "conv1.norm.", widths[i])
+        yield from conv(p + "conv1.conv.", widths[i], widths[i - 1], True)
+        yield from gn(p + "conv2.norm.", widths[i])
+        yield from conv(p + "conv2.conv.", widths[i], widths[i], True)
+        yield from conv(p + "res_conv.conv.", widths[i], widths[i - 1], True)
+    p = "bottleneck.0."
+    yield from gn(p + "conv1.norm.", nf_max)
+    yield from conv(p + "conv1.conv.", nf_max, widths[-1], False)
+    yield from gn(p + "conv2.norm.", nf_max)
+    yield from conv(p + "conv2.conv.", nf_max, nf_max, False)
+    if widths[-1] != nf_max:
+        yield from conv(p + "res_conv.conv.", nf_max, widths[-1], False)
+
+
 def init_tensor(shape, dtype, init, prev=None):
     kind = init[0]
     if kind == "zeros":

@@ -499,10 +499,10 @@ def gru_step(sd, cfg, x, hidden: List[Tensor]) -> List[Tensor]:
     return new
 
 
-def _conv_block(sd, p, x, norm, act, dt):
+def _conv_block(sd, p, x, norm, act, dt, stride=1):
     """Conv2dBlock.forward (util.py:256-273): ZeroPad(1) + 3x3 conv [+ norm] [+ activation]."""
     w = spectral_weight(sd, p + "conv.").to(dt)
-    x = F.conv2d(x, w, sd[p + "conv.bias"].to(dt), padding=1)
+    x = F.conv2d(x, w, sd[p + "conv.bias"].to(dt), stride=stride, padding=1)
     if norm == "group":
         x = F.group_norm(x, 16, sd[p + "norm.weight"].to(dt), sd[p + "norm.bias"].to(dt), eps=1e-5)
     elif norm == "in":
@@ -676,6 +676,81 @@ def encoder_forward(sd, cfg: dict, X: Tensor, eps: Tensor) -> Tuple[Tensor, Tens
     logvar = F.conv2d(emb, w("conv_var.weight"), w("conv_var.bias"), padding=1)
     z = eps.to(dt) * torch.exp(0.5 * logvar) + mu                                                                    # :218-222
     return z, mu, logvar
+
+
+# ----------------------------------------------------------------------------------------------
+# conditioning encoders (poke embedder / image conditioner): ConvEncoder, fully_conv_models.py:28-94
+# (next-row component of SURVEY.md section 8f rank 1; used by make_flow_input, second_stage_video.py:268-287,311)
+# ----------------------------------------------------------------------------------------------
+def cond_encoder_config(nf_in=3, nf_max=64, spatial=128, min_spatial_size=8) -> dict:
+    """FirstStageWrapper wiring (fully_conv_models.py:9-22): n_stages = log2(spatial / min_spatial_size); deterministic."""
+    return dict(nf_in=nf_in, nf_max=nf_max, spatial=spatial, min_spatial_size=min_spatial_size,
+                n_stages=int(math.log2(spatial // min_spatial_size)))
+
+
+def cond_encoder_widths(cfg: dict) -> List[int]:
+    """Channel widths after each stage of ConvEncoder.__init__ (fully_conv_models.py:38-61): 32, then min(2*nf, nf_max)."""
+    w = [32]
+    for _ in range(cfg["n_stages"] - 1):
+        w.append(min(w[-1] * 2, cfg["nf_max"]))
+    return w
+
+
+def synth_cond_encoder_state_dict(cfg: dict, seed: int = 0) -> Dict[str, Tensor]:
+    """Seeded checkpoint of ConvEncoder(nf_in, nf_max, n_stages, variational=False) with the reference's keys: stride-2
+    blocks carry legacy spectral norm (weight_orig / weight_u / weight_v), the bottleneck ResBlock does not."""
+    gen = torch.Generator().manual_seed(seed)
+    sd: Dict[str, Tensor] = {}
+
+    def conv(p, cout, cin, sn):
+        b = 1.0 / math.sqrt(cin * 9)
+        sd[p + "bias"] = _uni(gen, (cout,), b)
+        if sn:
+            sd[p + "weight_orig"] = _uni(gen, (cout, cin, 3, 3), b)
+            sd[p + "weight_u"] = F.normalize(torch.randn(cout, generator=gen), dim=0, eps=1e-12)
+            sd[p + "weight_v"] = F.normalize(torch.randn(cin * 9, generator=gen), dim=0, eps=1e-12)
+        else:
+            sd[p + "weight"] = _uni(gen, (cout, cin, 3, 3), b)
+
+    def gn(p, c):
+        sd[p + "weight"] = 1.0 + _nrm(gen, (c,), 0.1)
+        sd[p + "bias"] = _nrm(gen, (c,), 0.05)
+
+    widths = cond_encoder_widths(cfg)
+    gn("model.0.norm.", widths[0])
+    conv("model.0.conv.", widths[0], cfg["nf_in"], True)
+    for i in range(1, len(widths)):
+        p = f"model.{i}."
+        gn(p + "conv1.norm.", widths[i]); conv(p + "conv1.conv.", widths[i], widths[i - 1], True)
+        gn(p + "conv2.norm.", widths[i]); conv(p + "conv2.conv.", widths[i], widths[i], True)
+        conv(p + "res_conv.conv.", widths[i], widths[i - 1], True)
+    nf, nmax = widths[-1], cfg["nf_max"]
+    p = "bottleneck.0."
+    gn(p + "conv1.norm.", nmax); conv(p + "conv1.conv.", nmax, nf, False)
+    gn(p + "conv2.norm.", nmax); conv(p + "conv2.conv.", nmax, nmax, False)
+    if nf != nmax:
+        conv(p + "res_conv.conv.", nmax, nf, False)
+    return sd
+
+
+def cond_encoder_forward(sd, cfg: dict, x: Tensor) -> Tuple[Tensor, Tensor]:
+    """ConvEncoder.forward, variational=False (fully_conv_models.py:74-88): returns (out, mean) with mean = the activations
+    before the bottleneck; callers take [0] (second_stage_video.py:274,281)."""
+    dt = x.dtype
+    x = _conv_block(sd, "model.0.", x, "group", "elu", dt, stride=2)
+    widths = cond_encoder_widths(cfg)
+    for i in range(1, len(widths)):
+        p = f"model.{i}."
+        res = _conv_block(sd, p + "res_conv.", x, "in", "elu", dt, stride=2)          # ResBlock :170-176, 185-192
+        out = _conv_block(sd, p + "conv1.", x, "group", "elu", dt, stride=2)
+        out = _conv_block(sd, p + "conv2.", out, "group", "none", dt)
+        x = out + res
+    mean = x
+    p = "bottleneck.0."
+    res = _conv_block(sd, p + "res_conv.", x, "in", "elu", dt) if (p + "res_conv.conv.bias") in sd else x
+    out = _conv_block(sd, p + "conv1.", x, "group", "elu", dt)
+    out = _conv_block(sd, p + "conv2.", out, "group", "none", dt)
+    return out + res, mean
 
 
 # ----------------------------------------------------------------------------------------------

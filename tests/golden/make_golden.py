@@ -75,6 +75,34 @@ def run_enc_case(name, spec, out_dir):
           f"mu std {mu_ref.std().item():.3f} logvar std {lv_ref.std().item():.3f}")
 
 
+CENC_CASES = {
+    # name: (cfg kwargs, B, weight seed, input seed)
+    "cenc_poke_128": (dict(nf_in=2, spatial=128), 2, 61, 71),
+    "cenc_img_64": (dict(nf_in=3, spatial=64), 2, 62, 72),
+}
+
+
+def run_cenc_case(name, spec, out_dir):
+    kw, B, wseed, iseed = spec
+    cfg = O.cond_encoder_config(**kw)
+    sd = O.synth_cond_encoder_state_dict(cfg, seed=wseed)
+    m = ref_import.cond_encoder_cls()(nf_in=cfg["nf_in"], nf_max=cfg["nf_max"], n_stages=cfg["n_stages"], variational=False)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    g = torch.Generator().manual_seed(iseed)
+    x = torch.rand((B, cfg["nf_in"], cfg["spatial"], cfg["spatial"]), generator=g) * 2 - 1
+    with torch.no_grad():
+        out_ref, mean_ref, logstd = m(x)
+        out_or, mean_or = O.cond_encoder_forward(sd, cfg, x)
+        out64, _ = O.cond_encoder_forward(sd, cfg, x.double())
+    assert logstd is None
+    fix = dict(kind="cond_encoder", cfg_kwargs=kw, B=B, wseed=wseed, iseed=iseed, out=out_ref.clone(), mean=mean_ref.clone(),
+               oracle_vs_ref=max((out_or - out_ref).abs().max().item(), (mean_or - mean_ref).abs().max().item()),
+               ref_fp32_vs_oracle_fp64=(out64.float() - out_ref).abs().max().item(), torch_version=torch.__version__)
+    torch.save(fix, os.path.join(out_dir, name + ".pt"))
+    print(f"{name}: out {tuple(out_ref.shape)} oracle-vs-ref {fix['oracle_vs_ref']:.2e} fp64 {fix['ref_fp32_vs_oracle_fp64']:.2e} out std {out_ref.std().item():.3f}")
+
+
 def ref_flow(cfg, sd):
     Flow = ref_import.flow_cls()
     m = Flow(dict(cfg))
@@ -153,6 +181,9 @@ if __name__ == "__main__":
     for n, s in FS_CASES.items():
         if a.only in (None, n):
             run_fs_case(n, s, HERE)
+    for n, s in CENC_CASES.items():
+        if a.only in (None, n):
+            run_cenc_case(n, s, HERE)
     for n, s in ENC_CASES.items():
         if a.only in (None, n):
             run_enc_case(n, s, HERE)

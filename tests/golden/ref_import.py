@@ -45,3 +45,9 @@ def encoder_fn():
     install()
     from models.modules.motion_models.motion_encoder import resnet18_alternative
     return resnet18_alternative
+
+
+def cond_encoder_cls():
+    install()
+    from models.modules.autoencoders.fully_conv_models import ConvEncoder
+    return ConvEncoder

@@ -72,6 +72,7 @@ def test_struct_layout_matches_header():
     assert ctypes.sizeof(L.FlowConfig) == 4 * (4 + 32 + 5)
     assert ctypes.sizeof(L.FsConfig) == 4 * (4 + 8 + 4)
     assert ctypes.sizeof(L.EncConfig) == 4 * (5 + 8 + 2)
+    assert ctypes.sizeof(L.CencConfig) == 4 * 6
     src = open(HEADER).read()
     assert "#define IPK_MAX_LEVELS 32" in src and "#define IPK_MAX_DEC 8" in src
 
@@ -112,6 +113,14 @@ def test_state_dict_layout_matches_oracle_checkpoint():
     assert sorted(own.keys()) == sorted(dsd.keys())
     for k in dsd:
         assert own[k].shape == dsd[k].shape, k
+    for nf_in, size in ((2, 128), (3, 64)):
+        ccfg = O.cond_encoder_config(nf_in=nf_in, spatial=size)
+        csd = O.synth_cond_encoder_state_dict(ccfg, seed=0)
+        ce = ipk.ConvEncoder(nf_in, ccfg["nf_max"], ccfg["n_stages"])
+        own = ce.state_dict()
+        assert sorted(own.keys()) == sorted(csd.keys())
+        for k in csd:
+            assert own[k].shape == csd[k].shape, k
     for size in (64, 128):
         ecfg = O.encoder_config(z_dim=32, img_size=size, max_frames=10)
         esd = O.synth_encoder_state_dict(ecfg, seed=0)

@@ -48,3 +48,37 @@ def test_encoder_default_eps_matches_reference_rng_and_is_batch_invariant():
     assert maxabs(mu1, mu[1:2]) < 1e-6
     with pytest.raises(ValueError):
         m(torch.zeros(1, 3, 11, 32, 32, device="cuda"))
+
+
+@pytest.mark.parametrize("name", ["cenc_poke_128", "cenc_img_64"])
+def test_cond_encoder_matches_reference_golden(name):
+    """Frozen ConvEncoder of the poke embedder / image conditioner (make_flow_input) vs the reference's output."""
+    import ipoke_b200 as ipk
+    fx = golden(name)
+    cfg = O.cond_encoder_config(**fx["cfg_kwargs"])
+    sd = O.synth_cond_encoder_state_dict(cfg, seed=fx["wseed"])
+    g = torch.Generator().manual_seed(fx["iseed"])
+    x = torch.rand((fx["B"], cfg["nf_in"], cfg["spatial"], cfg["spatial"]), generator=g) * 2 - 1
+    m = ipk.ConvEncoder(cfg["nf_in"], cfg["nf_max"], cfg["n_stages"], ipk_max_batch=fx["B"])
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    out, mean, logstd = m(x.cuda())
+    e = (maxabs(out, fx["out"]), maxabs(mean, fx["mean"]))
+    print(f"{name}: out/mean max-abs {e[0]:.2e} {e[1]:.2e}")
+    assert logstd is None and max(e) < 1e-4
+
+
+def test_make_cond_feeds_the_flow():
+    """make_flow_input's conditioning: cat[conditioner(x0), poke_embedder(poke)] has the flow's h_channels = 128."""
+    import ipoke_b200 as ipk
+    ic, pc = O.cond_encoder_config(nf_in=3, spatial=64), O.cond_encoder_config(nf_in=2, spatial=64)
+    img = ipk.ConvEncoder(3, 64, ic["n_stages"]); img.load_state_dict(O.synth_cond_encoder_state_dict(ic, seed=1))
+    pk = ipk.ConvEncoder(2, 64, pc["n_stages"]); pk.load_state_dict(O.synth_cond_encoder_state_dict(pc, seed=2))
+    g = torch.Generator().manual_seed(0)
+    x0 = torch.rand((2, 3, 64, 64), generator=g) * 2 - 1
+    poke = torch.zeros(2, 2, 64, 64); poke[:, :, 30:35, 20:25] = 0.7
+    cond = ipk.make_cond(img.cuda().eval(), pk.cuda().eval(), x0.cuda(), poke.cuda())
+    with torch.no_grad():
+        ref = torch.cat([O.cond_encoder_forward(O.synth_cond_encoder_state_dict(ic, seed=1), ic, x0)[0],
+                         O.cond_encoder_forward(O.synth_cond_encoder_state_dict(pc, seed=2), pc, poke)[0]], dim=1)
+    assert cond.shape == (2, 128, 8, 8) and maxabs(cond, ref) < 1e-4

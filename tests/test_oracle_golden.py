@@ -56,6 +56,18 @@ def test_encoder_oracle_matches_reference(name):
         assert (a - b).abs().max().item() < 5e-5
 
 
+@pytest.mark.parametrize("name", ["cenc_poke_128", "cenc_img_64"])
+def test_cond_encoder_oracle_matches_reference(name):
+    fx = golden(name)
+    cfg = O.cond_encoder_config(**fx["cfg_kwargs"])
+    sd = O.synth_cond_encoder_state_dict(cfg, seed=fx["wseed"])
+    g = torch.Generator().manual_seed(fx["iseed"])
+    x = torch.rand((fx["B"], cfg["nf_in"], cfg["spatial"], cfg["spatial"]), generator=g) * 2 - 1
+    with torch.no_grad():
+        out, mean = O.cond_encoder_forward(sd, cfg, x)
+    assert (out - fx["out"]).abs().max().item() < 5e-5 and (mean - fx["mean"]).abs().max().item() < 5e-5
+
+
 def test_shuffle_roundtrip_exact():
     cfg = O.flow_config(flow_in_channels=16, flow_mid_channels=16, h_channels=4, num_steps=[1], factor=2)
     sd = O.synth_flow_state_dict(cfg, seed=9)
