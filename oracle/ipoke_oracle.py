@@ -232,7 +232,7 @@ def actnorm_fwd(sd, p, x):
     B, C, H, W = x.shape
     out = x * ls.exp() + b
     logdet = ls.view(1, C).sum(dim=1) * (H * W)
-    return out, logdet * torch.ones(B, dtype=x.dtype)
+    return out, logdet * torch.ones(B, dtype=x.dtype, device=x.device)
 
 
 def actnorm_bwd(sd, p, y):

@@ -103,6 +103,46 @@ def run_cenc_case(name, spec, out_dir):
     print(f"{name}: out {tuple(out_ref.shape)} oracle-vs-ref {fix['oracle_vs_ref']:.2e} fp64 {fix['ref_fp32_vs_oracle_fp64']:.2e} out std {out_ref.std().item():.3f}")
 
 
+I3D_CASES = {
+    # name: (B, T, S, weight seed, input seed)
+    "i3d_t10": (2, 10, 64, 61, 71),
+    "i3d_t16": (1, 16, 128, 62, 72),
+}
+
+
+def run_i3d_case(name, spec, out_dir):
+    """FVD chain: synthetic I3D weights -> reference I3D (strict load) on preprocess()ed clips; Frechet distance of
+    seeded Gaussians through the reference's calculate_frechet_distance."""
+    import numpy as np
+    from oracle import fvd_oracle as FO
+    M = ref_import.metrics_module()
+    B, T, S, wseed, iseed = spec
+    sd = FO.synth_i3d_state_dict(wseed)
+    m = M.I3D(400, "rgb")
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    g = torch.Generator().manual_seed(iseed)
+    vid_a = torch.rand((B, T, 3, S, S), generator=g) * 2 - 1
+    vid_b = torch.rand((B, T, 3, S, S), generator=g)                     # already in [0,1]: preprocess must not denorm it
+    pa, pb = M.preprocess(vid_a, vid_b)
+    act_ref = M.get_activations(pa, m, batch_size=B)
+    with torch.no_grad():
+        soft, logits = m(pb.permute(0, 2, 1, 3, 4))
+    rng = np.random.RandomState(iseed)
+    f1 = rng.randn(64, 12) * 1.5 + 0.3
+    f2 = rng.randn(80, 12) @ (np.eye(12) + 0.2 * rng.randn(12, 12))
+    fd_ref = M.calculate_frechet_distance(f1.mean(0), np.cov(f1, rowvar=False), f2.mean(0), np.cov(f2, rowvar=False))
+    # oracle in the same run
+    opa, opb = FO.preprocess(vid_a), FO.preprocess(vid_b)
+    act_or = FO.activations(sd, opa, batch_size=B)
+    fix = dict(B=B, T=T, S=S, wseed=wseed, iseed=iseed, act_a=torch.from_numpy(act_ref), logits_b=logits,
+               pre_a_sum=pa.double().sum().item(), pre_b_sum=pb.double().sum().item(), f1=f1, f2=f2, fd=float(fd_ref),
+               oracle_vs_ref=float(np.abs(act_or - act_ref).max()), logit_std=float(act_ref.std()))
+    torch.save(fix, os.path.join(out_dir, name + ".pt"))
+    print(f"{name}: logits std {fix['logit_std']:.3f} oracle-vs-ref {fix['oracle_vs_ref']:.2e} "
+          f"pre {(opa - pa).abs().max().item():.1e} fd {fd_ref:.4f} vs oracle {FO.fvd_from_activations(f1, f2):.4f}")
+
+
 def ref_flow(cfg, sd):
     Flow = ref_import.flow_cls()
     m = Flow(dict(cfg))
@@ -187,6 +227,9 @@ if __name__ == "__main__":
     for n, s in ENC_CASES.items():
         if a.only in (None, n):
             run_enc_case(n, s, HERE)
+    for n, s in I3D_CASES.items():
+        if a.only in (None, n):
+            run_i3d_case(n, s, HERE)
     if a.full:
         for n, s in FULL_FLOW_CASES.items():
             if a.only in (None, n):

@@ -6,6 +6,9 @@ Only used by tests/golden/make_golden.py (fixture generation, run in the build c
 Shims:
   * `opt_einsum` is imported by models/modules/INN/modules.py:9 but only used by attention blocks
     (attention: false in every shipped config) -> empty stub module.
+  * `utils/metrics.py` imports pytorch_lightning.metrics(.functional), lpips and utils.logging (:3,4,14,17), none of
+    which the FVD chain uses -> stub modules; `scipy.linalg.sqrtm(disp=False)` (:660) was removed from SciPy ->
+    a wrapper restoring the (result, errest) return.
   * `Spade.forward` hard-codes `.cuda()` (models/modules/autoencoders/util.py:496) and so does
     `ResNetMotionEncoder.reparameterize` (motion_encoder.py:220) -> Tensor.cuda becomes identity.
 """
@@ -51,3 +54,31 @@ def cond_encoder_cls():
     install()
     from models.modules.autoencoders.fully_conv_models import ConvEncoder
     return ConvEncoder
+
+
+def metrics_module():
+    """utils.metrics of the reference (I3D, preprocess, get_activations, calculate_frechet_distance)."""
+    install()
+    import scipy.linalg
+    for name in ("pytorch_lightning", "pytorch_lightning.metrics", "pytorch_lightning.metrics.functional", "lpips"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["pytorch_lightning.metrics"].Metric = object
+    sys.modules["pytorch_lightning.metrics.functional"].ssim = None
+    sys.modules["pytorch_lightning.metrics.functional"].psnr = None
+    sys.modules["lpips"].LPIPS = object
+    import utils as ref_utils                       # the reference's package (REF is first on sys.path)
+    if "utils.logging" not in sys.modules:
+        m = types.ModuleType("utils.logging")
+        m.make_nn_var_plot = None
+        sys.modules["utils.logging"] = m
+        ref_utils.logging = m
+    if not getattr(scipy.linalg, "_ipk_sqrtm_shim", False):
+        _sqrtm = scipy.linalg.sqrtm
+        def sqrtm(a, disp=True, **k):
+            r = _sqrtm(a, **k)
+            return r if disp else (r, 0.0)
+        scipy.linalg.sqrtm = sqrtm
+        scipy.linalg._ipk_sqrtm_shim = True
+    import utils.metrics as M
+    return M

@@ -101,3 +101,47 @@ def test_full_size_flow_oracle_matches_reference():
     with torch.no_grad():
         x = O.flow_reverse(sd, cfg, z, cond)
     assert (x - fx["x_rev"]).abs().max().item() < 5e-4
+
+
+@pytest.mark.parametrize("name", ["i3d_t10", "i3d_t16"])
+def test_fvd_chain_oracle_matches_reference(name):
+    """FVD chain (I3D logits, preprocess, Frechet distance) restated in oracle/fvd_oracle.py vs the reference's
+    utils/metrics.py run on the same seeded weights and clips (tests/golden/make_golden.py: run_i3d_case)."""
+    import numpy as np
+    from oracle import fvd_oracle as FO
+    fx = golden(name)
+    sd = FO.synth_i3d_state_dict(fx["wseed"])
+    g = torch.Generator().manual_seed(fx["iseed"])
+    vid_a = torch.rand((fx["B"], fx["T"], 3, fx["S"], fx["S"]), generator=g) * 2 - 1
+    vid_b = torch.rand((fx["B"], fx["T"], 3, fx["S"], fx["S"]), generator=g)
+    pa, pb = FO.preprocess(vid_a), FO.preprocess(vid_b)
+    assert abs(pa.double().sum().item() - fx["pre_a_sum"]) < 1e-6 * abs(fx["pre_a_sum"])
+    assert abs(pb.double().sum().item() - fx["pre_b_sum"]) < 1e-6 * abs(fx["pre_b_sum"])       # [0,1] input is not denormed
+    assert pa.min() >= 0 and pa.max() <= 1
+    act = FO.activations(sd, pa, batch_size=fx["B"])
+    assert np.abs(act - fx["act_a"].numpy()).max() < 1e-3 * fx["logit_std"]
+    with torch.no_grad():
+        lb = FO.i3d_logits(sd, pb.permute(0, 2, 1, 3, 4))
+    assert (lb - fx["logits_b"]).abs().max().item() < 1e-3 * fx["logit_std"]
+    assert abs(FO.fvd_from_activations(fx["f1"], fx["f2"]) - fx["fd"]) < 1e-6 * fx["fd"]
+
+
+def test_frechet_distance_known_answers():
+    """identical Gaussians -> 0, unit mean shift in 3-D with equal covariance -> 3.0."""
+    import numpy as np
+    from oracle import fvd_oracle as FO
+    s = np.diag([1.0, 2.0, 0.5])
+    assert abs(FO.frechet_distance(np.zeros(3), s, np.zeros(3), s)) < 1e-9
+    assert abs(FO.frechet_distance(np.zeros(3), s, np.ones(3), s) - 3.0) < 1e-9
+
+
+def test_synth_pokes_layout():
+    from oracle import fvd_oracle as FO
+    poke, centres = FO.synth_pokes(4, 64, seed=5)
+    assert poke.shape == (4, 2, 64, 64) and centres.shape == (4, 1, 2)
+    for b in range(4):
+        nz = (poke[b].abs().sum(0) > 0)
+        assert nz.sum().item() == 25
+        ys, xs = torch.nonzero(nz, as_tuple=True)
+        assert ys.float().mean().item() == centres[b, 0, 0].item() and xs.float().mean().item() == centres[b, 0, 1].item()
+        assert 5 <= centres[b, 0, 0] < 59 and 5 <= centres[b, 0, 1] < 59
