@@ -282,6 +282,21 @@ def run_ours(a):
         d2h = frames_h.numel() * 4 * world
         e2e = {"value": B * world * a.steps / (float(ems.item()) / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "api": "PokeMotionSampler.sample_host -> ipk_sample_host (pinned host buffers; frames delivered to host per rank)"}
+        # same step with the post-processed sample (uint8 NTHWC, second_stage_video.py:673-675) leaving the device: 1/4 of the D2H bytes
+        for _ in range(2):
+            sampler.sample_host(z_h, cond_h, x0_h, T, device=dev, uint8=True)
+        sync()
+        u_e0, u_e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        u_e0.record()
+        for _ in range(a.steps):
+            frames_u8 = sampler.sample_host(z_h, cond_h, x0_h, T, device=dev, uint8=True)
+        u_e1.record()
+        sync()
+        ums = torch.tensor([u_e0.elapsed_time(u_e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ums, op=dist.ReduceOp.MAX)
+        e2e["uint8_frames"] = {"value": B * world * a.steps / (float(ums.item()) / 1e3), "unit": UNIT, "d2h_bytes_per_step": frames_u8.numel() * world,
+                               "api": "PokeMotionSampler.sample_host(uint8=True) -> ipk_sample_host_u8"}
     clk = clocks.stop() if rank == 0 else None
 
     # ---- per-phase device times (separate untimed pass, CUDA events on the launch stream around every phase)

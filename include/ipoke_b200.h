@@ -167,6 +167,15 @@ int ipk_sample(ipk_flow* f, ipk_fs* d, const float* z, const float* cond, const 
 int ipk_sample_host(ipk_flow* f, ipk_fs* d, const float* z_host, const float* cond_host, const float* x0_host,
                     float* frames_host, int32_t B, int32_t T, void* stream);
 
+/* ---- sample post-processing: what the callers of forward_sample do with every sample on the host,
+ * `((x + 1.) * 127.5).permute(0, 1, 3, 4, 2).numpy().astype(np.uint8)` (models/second_stage_video.py:673-675; the input of
+ * utils/logging.py:797 save_video), done on the device so that 1 byte per value crosses PCIe instead of 4.
+ * frames: device fp32 [n_frames][3][S][S] in [-1, 1] -> out: device uint8 [n_frames][S][S][3] (truncation, clamped). */
+int ipk_frames_to_u8(const float* frames, uint8_t* out, int64_t n_frames, int32_t spatial, void* stream);
+/* ipk_sample_host delivering uint8 NTHWC frames [B][T][S][S][3] to the host, chunk by chunk behind the decoder */
+int ipk_sample_host_u8(ipk_flow* f, ipk_fs* d, const float* z_host, const float* cond_host, const float* x0_host,
+                       uint8_t* frames_u8_host, int32_t B, int32_t T, void* stream);
+
 /* ---- kernel-level test hooks (used by tests/ to check single kernels against the oracle) ---- */
 /* out[M,N] = A[M,K] * W[N,K]^T through the engine selected by `precision` */
 int ipk_test_gemm(const float* A, const float* W, float* out, int32_t M, int32_t N, int32_t K, int32_t precision, void* stream);

@@ -89,7 +89,7 @@ extern "C" int ipk_prof_report(char* buf, int cap) {
 struct ipk_flow;
 struct ipk_fs;
 int ipk_fs_decode_nhwc(ipk_fs* d, const float* motion_nhwc, const float* x0, float* frames, int B, int T, cudaStream_t st,
-                       float* frames_host = nullptr, cudaStream_t copy_st = nullptr);
+                       float* frames_host = nullptr, cudaStream_t copy_st = nullptr, uint8_t* u8_dev = nullptr, uint8_t* u8_host = nullptr);
 int ipk_flow_reverse_nhwc(ipk_flow* f, const float* z, const float* cond, const float** state_nhwc, int B, cudaStream_t st);
 
 extern "C" int ipk_version(void) { return IPK_VERSION; }
@@ -111,8 +111,8 @@ extern "C" int ipk_sample(ipk_flow* f, ipk_fs* d, const float* z, const float* c
 
 namespace {
 struct HostStage {
-  float *z = nullptr, *cond = nullptr, *x0 = nullptr, *frames = nullptr;
-  size_t nz = 0, nc = 0, nx = 0, nf = 0;
+  float *z = nullptr, *cond = nullptr, *x0 = nullptr, *frames = nullptr, *u8 = nullptr;   // u8: byte buffer, capacity counted in floats
+  size_t nz = 0, nc = 0, nx = 0, nf = 0, nu = 0;
   cudaStream_t copy_st = nullptr;
   void ensure(float** p, size_t* cap, size_t n) {
     if (*cap >= n) return;
@@ -129,12 +129,9 @@ struct FlowDims { int C0, hch; };
 FlowDims ipk_flow_dims(ipk_flow* f);
 int ipk_fs_spatial(ipk_fs* d);
 
-extern "C" int ipk_sample_host(ipk_flow* f, ipk_fs* d, const float* z_host, const float* cond_host, const float* x0_host,
-                               float* frames_host, int32_t B, int32_t T, void* stream) {
-  IPK_TRY
-  IPK_CHECK(f && d && z_host && cond_host && x0_host && frames_host, IPK_ERR_INVALID, "ipk_sample_host: null argument");
+static void sample_host_impl(ipk_flow* f, ipk_fs* d, const float* z_host, const float* cond_host, const float* x0_host,
+                             float* frames_host, uint8_t* u8_host, int B, int T, cudaStream_t st) {
   std::lock_guard<std::mutex> lk(g_stage_mu);
-  cudaStream_t st = (cudaStream_t)stream;
   FlowDims fd = ipk_flow_dims(f);
   const int S = ipk_fs_spatial(d);
   const size_t nz = (size_t)B * fd.C0 * 64, nc = (size_t)B * fd.hch * 64, nx = (size_t)B * 3 * S * S, nf = (size_t)B * T * 3 * S * S;
@@ -142,17 +139,40 @@ extern "C" int ipk_sample_host(ipk_flow* f, ipk_fs* d, const float* z_host, cons
   g_stage.ensure(&g_stage.cond, &g_stage.nc, nc);
   g_stage.ensure(&g_stage.x0, &g_stage.nx, nx);
   g_stage.ensure(&g_stage.frames, &g_stage.nf, nf);
+  if (u8_host) g_stage.ensure(&g_stage.u8, &g_stage.nu, (nf + 3) / 4);
   IPK_CUDA(cudaMemcpyAsync(g_stage.z, z_host, nz * 4, cudaMemcpyHostToDevice, st));
   IPK_CUDA(cudaMemcpyAsync(g_stage.cond, cond_host, nc * 4, cudaMemcpyHostToDevice, st));
   IPK_CUDA(cudaMemcpyAsync(g_stage.x0, x0_host, nx * 4, cudaMemcpyHostToDevice, st));
   const float* motion = nullptr;
-  int rc = ipk_flow_reverse_nhwc(f, g_stage.z, g_stage.cond, &motion, B, st);
-  if (rc != 0) return rc;
+  ipk_flow_reverse_nhwc(f, g_stage.z, g_stage.cond, &motion, B, st);
   // frames leave chunk by chunk on a second stream while the next chunk is decoded
   if (!g_stage.copy_st) IPK_CUDA(cudaStreamCreateWithFlags(&g_stage.copy_st, cudaStreamNonBlocking));
-  ipk_fs_decode_nhwc(d, motion, g_stage.x0, g_stage.frames, B, T, st, frames_host, g_stage.copy_st);
+  ipk_fs_decode_nhwc(d, motion, g_stage.x0, g_stage.frames, B, T, st, frames_host, g_stage.copy_st,
+                     u8_host ? (uint8_t*)g_stage.u8 : nullptr, u8_host);
   IPK_CUDA(cudaStreamSynchronize(g_stage.copy_st));
   IPK_CUDA(cudaStreamSynchronize(st));
+}
+
+extern "C" int ipk_sample_host(ipk_flow* f, ipk_fs* d, const float* z_host, const float* cond_host, const float* x0_host,
+                               float* frames_host, int32_t B, int32_t T, void* stream) {
+  IPK_TRY
+  IPK_CHECK(f && d && z_host && cond_host && x0_host && frames_host, IPK_ERR_INVALID, "ipk_sample_host: null argument");
+  sample_host_impl(f, d, z_host, cond_host, x0_host, frames_host, nullptr, B, T, (cudaStream_t)stream);
+  IPK_CATCH
+}
+
+extern "C" int ipk_sample_host_u8(ipk_flow* f, ipk_fs* d, const float* z_host, const float* cond_host, const float* x0_host,
+                                  uint8_t* frames_u8_host, int32_t B, int32_t T, void* stream) {
+  IPK_TRY
+  IPK_CHECK(f && d && z_host && cond_host && x0_host && frames_u8_host, IPK_ERR_INVALID, "ipk_sample_host_u8: null argument");
+  sample_host_impl(f, d, z_host, cond_host, x0_host, nullptr, frames_u8_host, B, T, (cudaStream_t)stream);
+  IPK_CATCH
+}
+
+extern "C" int ipk_frames_to_u8(const float* frames, uint8_t* out, int64_t n_frames, int32_t spatial, void* stream) {
+  IPK_TRY
+  IPK_CHECK(frames && out && n_frames > 0 && spatial > 0, IPK_ERR_INVALID, "ipk_frames_to_u8: bad argument");
+  frames_to_u8(frames, out, n_frames, spatial * spatial, (cudaStream_t)stream);
   IPK_CATCH
 }
 

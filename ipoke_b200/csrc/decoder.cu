@@ -493,9 +493,10 @@ extern "C" int ipk_fs_finalize(ipk_fs* d, void* stream) {
 }
 
 // frames_host / copy_st (optional): every finished chunk of frames is copied to the host on a second stream while the next
-// chunk is being decoded; the caller synchronises copy_st.
+// chunk is being decoded; the caller synchronises copy_st.  u8_dev / u8_host (optional, same chunking): the chunk is also
+// converted to uint8 NTHWC (frames_to_u8) and THAT leaves for the host instead of the fp32 frames.
 static void fs_decode_impl(ipk_fs* d, const float* motion, bool motion_is_nhwc, const float* x0, float* frames, int B, int T, cudaStream_t st,
-                           float* frames_host = nullptr, cudaStream_t copy_st = nullptr) {
+                           float* frames_host = nullptr, cudaStream_t copy_st = nullptr, uint8_t* u8_dev = nullptr, uint8_t* u8_host = nullptr) {
   IPK_CHECK(d && d->finalized, IPK_ERR_STATE, "first stage not finalized");
   IPK_CHECK(B > 0 && B <= d->cfg.max_batch, IPK_ERR_INVALID, "first stage: batch %d outside (0, %d]", B, d->cfg.max_batch);
   IPK_CHECK(T > 0 && T <= d->cfg.max_frames, IPK_ERR_INVALID, "first stage: T %d outside (0, %d]", T, d->cfg.max_frames);
@@ -520,11 +521,13 @@ static void fs_decode_impl(ipk_fs* d, const float* motion, bool motion_is_nhwc, 
     int nv = std::min(d->chunk_videos, B - v0);
     const size_t off = (size_t)v0 * T * 3 * d->S * d->S, cnt = (size_t)nv * T * 3 * d->S * d->S;
     decode_frames(d, d->Hseq + (size_t)v0 * T * 64 * z, nv, T, v0, frames + off, st);
-    if (frames_host) {
+    if (u8_dev) frames_to_u8(frames + off, u8_dev + off, (long long)nv * T, d->S * d->S, st);
+    if (frames_host || u8_host) {
       if (!d->chunk_done) IPK_CUDA(cudaEventCreateWithFlags(&d->chunk_done, cudaEventDisableTiming));
       IPK_CUDA(cudaEventRecord(d->chunk_done, st));
       IPK_CUDA(cudaStreamWaitEvent(copy_st, d->chunk_done, 0));
-      IPK_CUDA(cudaMemcpyAsync(frames_host + off, frames + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, copy_st));
+      if (u8_host) IPK_CUDA(cudaMemcpyAsync(u8_host + off, u8_dev + off, cnt, cudaMemcpyDeviceToHost, copy_st));
+      else IPK_CUDA(cudaMemcpyAsync(frames_host + off, frames + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, copy_st));
     }
   }
 }
@@ -538,8 +541,8 @@ extern "C" int ipk_fs_decode(ipk_fs* d, const float* motion, const float* x0, fl
 
 // internal entry used by ipk_sample: motion already NHWC [B][64][z] on device
 int ipk_fs_decode_nhwc(ipk_fs* d, const float* motion_nhwc, const float* x0, float* frames, int B, int T, cudaStream_t st,
-                       float* frames_host, cudaStream_t copy_st) {
-  fs_decode_impl(d, motion_nhwc, true, x0, frames, B, T, st, frames_host, copy_st);
+                       float* frames_host, cudaStream_t copy_st, uint8_t* u8_dev, uint8_t* u8_host) {
+  fs_decode_impl(d, motion_nhwc, true, x0, frames, B, T, st, frames_host, copy_st, u8_dev, u8_host);
   return 0;
 }
 

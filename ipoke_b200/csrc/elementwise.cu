@@ -65,6 +65,39 @@ void copy_channels(const float* src, int scs, int scoff, float* dst, int dcs, in
   IPK_LAUNCH_CHECK();
 }
 
+// ------------------------------------------------------------------ sample post-processing (second_stage_video.py:673-675)
+// ((x + 1.) * 127.5).permute(0, 1, 3, 4, 2) ... .astype(np.uint8): fp32 frames [F][3][P] -> uint8 [F][P][3], the float -> uint8
+// conversion truncating like the C cast numpy performs (inputs are tanh outputs, so the product lies in [0, 255]; values
+// outside are clamped instead of wrapping).  One thread converts 4 consecutive pixels: three coalesced float4 loads, three
+// coalesced 32-bit stores.
+__device__ __forceinline__ uint32_t to_u8(float x) {
+  const float v = (x + 1.0f) * 127.5f;            // same two fp32 roundings as the reference expression
+  return (uint32_t)min(max(__float2int_rz(v), 0), 255);
+}
+__global__ void frames_to_u8_kernel(const float* __restrict__ in, uint8_t* __restrict__ out, long long F, int P) {
+  const int q = P / 4;                              // pixel quads per frame
+  const long long total = F * q;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long f = e / q;
+    const int p4 = (int)(e % q);
+    const float* src = in + (size_t)f * 3 * P + (size_t)p4 * 4;
+    const float4 r = *reinterpret_cast<const float4*>(src);
+    const float4 g = *reinterpret_cast<const float4*>(src + P);
+    const float4 b = *reinterpret_cast<const float4*>(src + 2 * (size_t)P);
+    const uint32_t c[12] = {to_u8(r.x), to_u8(g.x), to_u8(b.x), to_u8(r.y), to_u8(g.y), to_u8(b.y),
+                            to_u8(r.z), to_u8(g.z), to_u8(b.z), to_u8(r.w), to_u8(g.w), to_u8(b.w)};
+    uint32_t* dst = reinterpret_cast<uint32_t*>(out + ((size_t)f * P + (size_t)p4 * 4) * 3);
+    dst[0] = c[0] | (c[1] << 8) | (c[2] << 16) | (c[3] << 24);
+    dst[1] = c[4] | (c[5] << 8) | (c[6] << 16) | (c[7] << 24);
+    dst[2] = c[8] | (c[9] << 8) | (c[10] << 16) | (c[11] << 24);
+  }
+}
+void frames_to_u8(const float* frames_nchw, uint8_t* out_nhwc, long long F, int P, cudaStream_t st) {
+  IPK_CHECK(P % 4 == 0, IPK_ERR_UNSUPPORTED, "frames_to_u8: pixels per frame must be a multiple of 4 (got %d)", P);
+  frames_to_u8_kernel<<<grid_for(F * (P / 4)), 256, 0, st>>>(frames_nchw, out_nhwc, F, P);
+  IPK_LAUNCH_CHECK();
+}
+
 // ------------------------------------------------------------------ norm statistics
 // grid (chunks, F); each block reduces `ppb` pixels of one frame for all channels.
 __global__ void __launch_bounds__(256) channel_stats_kernel(const float* __restrict__ x, long long P, int C, int ppb, double* __restrict__ sums) {

@@ -12,6 +12,9 @@ void broadcast_chw_to_nhwc(const float* src, float* out, int B, int C, int P, in
 // copy channels: dst[m][dcoff + c] = src[m][scoff + c], m < M, c < C
 void copy_channels(const float* src, int scs, int scoff, float* dst, int dcs, int dcoff, long long M, int C, cudaStream_t st);
 
+// sample post-processing: fp32 frames [F][3][P] in [-1,1] -> uint8 [F][P][3] = trunc((x + 1) * 127.5) (second_stage_video.py:673-675)
+void frames_to_u8(const float* frames_nchw, uint8_t* out_nhwc, long long F, int P, cudaStream_t st);
+
 // per-(frame, channel) sum and sum of squares over the P pixels of a frame: sums[F][C][2] (double, accumulated; zero first)
 void channel_stats(const float* x, int F, long long P, int C, double* sums, cudaStream_t st);
 // mr[F][C][2] = (mean, rstd) per channel; groups == 0: InstanceNorm (per channel), else GroupNorm(groups) stats replicated
