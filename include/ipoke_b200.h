@@ -91,6 +91,7 @@ typedef struct ipk_enc_config {
   int32_t channels[IPK_MAX_DEC];
   int32_t min_spatial_size;
   int32_t max_batch;
+  int32_t precision;                  /* ipk_precision: tensor-core modes run every Conv3d with >= 64 input channels on tcgen05 */
 } ipk_enc_config;
 
 /* ConvEncoder(nf_in, nf_max, n_stages, variational=False) as wired by FirstStageWrapper (fully_conv_models.py:9-22). */

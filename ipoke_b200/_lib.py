@@ -31,7 +31,7 @@ class FsConfig(ctypes.Structure):
 class EncConfig(ctypes.Structure):
     _fields_ = [("z_dim", ctypes.c_int32), ("img_size", ctypes.c_int32), ("max_frames", ctypes.c_int32), ("full_seq", ctypes.c_int32),
                 ("n_channels", ctypes.c_int32), ("channels", ctypes.c_int32 * IPK_MAX_DEC), ("min_spatial_size", ctypes.c_int32),
-                ("max_batch", ctypes.c_int32)]
+                ("max_batch", ctypes.c_int32), ("precision", ctypes.c_int32)]
 
 
 class CencConfig(ctypes.Structure):

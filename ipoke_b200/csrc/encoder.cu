@@ -6,11 +6,15 @@
 // Data layout: NDHWC fp32 [B][T][H][W][C] (the 3 input channels padded to 4).  Every Conv3d is an implicit GEMM over
 // (tap, channel) with the taps outermost, so one k-chunk of a tile row is a contiguous run of channels of one input voxel.
 // GroupNorm(16) statistics run over the whole (T, H, W) volume of a sample: the shared norm pass with F = B, P = T*H*W.
-// This is the fp32 FFMA first cut of the row (parity first); the tcgen05 engine takes it over once it grows 5-D maps.
+// Tensor-core precisions (fp32 = bf16x3, bf16): every Conv3d with >= 64 input channels runs on the tcgen05 engine of conv3d_tc.cu
+// (5-D TMA boxes, strides as element strides, temporal-padding taps skipped, GroupNorm statistics fused into the epilogue); the
+// norm pass then writes the next conv's bf16 operand planes next to the fp32 activation.  The 3-channel stem and the fp32_simt
+// validation mode use the FFMA kernel below.
 #include <map>
 #include <string>
 #include <cmath>
 #include "conv.cuh"
+#include "conv3d_tc.cuh"
 #include "elementwise.cuh"
 
 namespace ipk {
@@ -22,7 +26,12 @@ struct Conv3dDesc {
   int kt, ky, kx, st, sy, sx, pt, py, px;
   float* w = nullptr;     // [kt][ky][kx][Cin][Cout]
   float* bias = nullptr;  // [Cout] or null
+  ConvW tcw;              // tensor-core packing [tap][Cout][Cin] (hi [, lo]) when `tc`
+  bool tc = false;
 };
+
+// an activation volume: fp32 NDHWC, plus (tensor-core precisions) the bf16 operand planes of the same values
+struct ActVol { float* f = nullptr; __nv_bfloat16* hi = nullptr; __nv_bfloat16* lo = nullptr; };
 
 struct Conv3dArgs {
   const float* in; float* out; const float* w; const float* bias;
@@ -174,7 +183,8 @@ struct ipk_enc {
   ConvW heads;               // conv_mu | conv_var fused along N (2-D 3x3, fp32 FFMA engine)
   int last_C = 0;
   // workspace
-  float *X4 = nullptr, *bufA = nullptr, *bufB = nullptr, *bufC = nullptr, *bufD = nullptr, *hbuf = nullptr;
+  float *X4 = nullptr, *bufC = nullptr, *bufD = nullptr, *hbuf = nullptr;
+  ActVol actA, actB, actX;      // block input / output ping-pong (actA, actX) and the mid-block activation (actB)
   double* sums = nullptr; float* mr = nullptr;
   size_t act_elems = 0;
 };
@@ -204,6 +214,11 @@ static Conv3dDesc build_conv3d(ipk_enc* e, const std::string& name, int Cout, in
   const long long total = (long long)ntaps * d.Cin * Cout;
   pack_conv3d_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, st>>>((const float*)w.p, d.w, Cout, CinSrc, d.Cin, ntaps, nullptr);
   IPK_LAUNCH_CHECK();
+  if (e->cfg.precision != IPK_PREC_FP32_SIMT && CinSrc % 64 == 0 && Cout % 64 == 0) {
+    d.tcw = conv_alloc(e->pool, e->cfg.precision, ntaps, CinSrc, Cout, false);
+    conv3d_tc_pack(d.tcw, (const float*)w.p, Cout, CinSrc, st);
+    d.tc = true;
+  }
   return d;
 }
 static inline int out_extent(int n, int k, int s, int p) { return (n + 2 * p - k) / s + 1; }
@@ -214,27 +229,47 @@ static Vol conv3d_out(const Conv3dDesc& d, const Vol& v) {
   return Vol{out_extent(v.T, d.kt, d.st, d.pt), out_extent(v.H, d.ky, d.sy, d.py), out_extent(v.W, d.kx, d.sx, d.px), d.Cout};
 }
 
-static Vol run_conv3d(const Conv3dDesc& d, const float* in, const Vol& v, float* out, int B, cudaStream_t st) {
+static Conv3dShape shape_of(const Conv3dDesc& d, const Vol& v) {
+  return Conv3dShape{d.Cin, d.Cout, v.T, v.H, v.W, d.kt, d.ky, d.kx, d.st, d.sy, d.sx, d.pt, d.py, d.px};
+}
+
+// Conv3d of `in` into the fp32 volume `out`.  Returns true when the GroupNorm statistics of the output were accumulated into
+// `sums` by the conv's own epilogue (tensor-core path); the caller zeroes `sums` first.
+static bool run_conv3d(const Conv3dDesc& d, const ActVol& in, const Vol& v, float* out, int B, double* sums, Vol* ov, cudaStream_t st) {
   IPK_CHECK(v.C == d.Cin, IPK_ERR_STATE, "encoder: conv input has %d channels, layer expects %d", v.C, d.Cin);
   const Vol o = conv3d_out(d, v);
-  Conv3dArgs a{in, out, d.w, d.bias, B, v.T, v.H, v.W, d.Cin, o.T, o.H, o.W, d.Cout, d.kt, d.ky, d.kx, d.st, d.sy, d.sx, d.pt, d.py, d.px};
+  *ov = o;
+  if (d.tc && in.hi != nullptr && conv3d_tc_supported(shape_of(d, v))) {
+    ProfScope ps("enc.conv3d.tc", st);
+    conv3d_tc_run(d.tcw, shape_of(d, v), in.hi, in.lo, B, out, sums, st);
+    return sums != nullptr;
+  }
+  ProfScope ps("enc.conv3d.simt", st);
+  Conv3dArgs a{in.f, out, d.w, d.bias, B, v.T, v.H, v.W, d.Cin, o.T, o.H, o.W, d.Cout, d.kt, d.ky, d.kx, d.st, d.sy, d.sx, d.pt, d.py, d.px};
   const long long M = (long long)B * o.voxels();
   dim3 g((unsigned)((M + C3_BM - 1) / C3_BM), (unsigned)cdiv(d.Cout, C3_BN));
   launch_k(conv3d_simt_kernel, g, dim3(256), 0, st, a);
-  return o;
+  return false;
 }
 
-// GroupNorm(16) over the (T, H, W) volume of each sample (+ affine, optional residual, ReLU)
-static void group_norm(ipk_enc* e, const float* x, const Vol& v, int B, const float* gw, const float* gb, const float* add, bool relu,
-                       float* out, cudaStream_t st) {
-  const long long P = (long long)v.voxels();
-  IPK_CUDA(cudaMemsetAsync(e->sums, 0, (size_t)B * v.C * 2 * sizeof(double), st));
-  NormApply s; s.x = x; s.F = B; s.C = v.C; s.P = P; s.stats_out = e->sums;
-  norm_apply(s, st);
-  finalize_stats(e->sums, e->mr, B, P, v.C, 16, 1e-5f, st);
-  NormApply n; n.x = x; n.F = B; n.C = v.C; n.P = P; n.mr = e->mr; n.w = gw; n.b = gb; n.add = add; n.act = relu ? ACT_RELU : ACT_NONE;
-  n.act_last = add != nullptr; n.out_f32 = out;
+// conv -> GroupNorm(16) over the (T, H, W) volume of each sample (+ affine, optional residual, ReLU) -> `out` (fp32 and, when
+// its plane pointers are set, the bf16 operand planes of the next conv).  `tmp` receives the raw conv output.
+static Vol conv_gn(ipk_enc* e, const Conv3dDesc& d, const ActVol& in, const Vol& v, float* tmp, int B, const float* gw, const float* gb,
+                   const float* add, bool relu, const ActVol& out, cudaStream_t st) {
+  Vol o;
+  IPK_CUDA(cudaMemsetAsync(e->sums, 0, (size_t)B * d.Cout * 2 * sizeof(double), st));
+  const bool have_stats = run_conv3d(d, in, v, tmp, B, e->sums, &o, st);
+  ProfScope ps("enc.group_norm", st);
+  const long long P = (long long)o.voxels();
+  if (!have_stats) {
+    NormApply s; s.x = tmp; s.F = B; s.C = o.C; s.P = P; s.stats_out = e->sums;
+    norm_apply(s, st);
+  }
+  finalize_stats(e->sums, e->mr, B, P, o.C, 16, 1e-5f, st);
+  NormApply n; n.x = tmp; n.F = B; n.C = o.C; n.P = P; n.mr = e->mr; n.w = gw; n.b = gb; n.add = add; n.act = relu ? ACT_RELU : ACT_NONE;
+  n.act_last = add != nullptr; n.out_f32 = out.f; n.out_hi = out.hi; n.out_lo = out.lo;
   norm_apply(n, st);
+  return o;
 }
 
 // ResNetMotionEncoder.__init__ layer plan (motion_encoder.py:161-190)
@@ -269,6 +304,7 @@ extern "C" int ipk_enc_create(const ipk_enc_config* cfg, ipk_enc** out) {
   IPK_CHECK(cfg->z_dim > 0 && cfg->z_dim % 2 == 0 && cfg->max_batch > 0 && cfg->max_frames > 1 && cfg->img_size >= 32, IPK_ERR_INVALID, "encoder: bad sizes");
   for (int i = 0; i < cfg->n_channels; ++i)
     IPK_CHECK(cfg->channels[i] % 16 == 0, IPK_ERR_UNSUPPORTED, "encoder: channel counts must be multiples of 16 (GroupNorm(16))");
+  IPK_CHECK(cfg->precision >= 0 && cfg->precision <= 2, IPK_ERR_INVALID, "encoder: bad precision");
   stage_plan(*cfg);
   ipk_enc* e = new ipk_enc();
   e->cfg = *cfg;
@@ -339,12 +375,19 @@ extern "C" int ipk_enc_finalize(ipk_enc* e, void* stream) {
   e->act_elems = maxe;
   const size_t B = c.max_batch;
   auto rb = [](size_t b) { return (b + 255) / 256 * 256; };
-  e->ws.init(5 * rb(B * maxe * 4) + rb(B * 64 * 2 * z * 4) + rb(B * 1024 * 2 * 8) + rb(B * 1024 * 2 * 4) + 65536);
+  const bool planes = c.precision != IPK_PREC_FP32_SIMT;
+  const bool lo = c.precision == IPK_PREC_FP32_SPLIT;
+  e->ws.init((6 + (planes ? 3 : 0)) * rb(B * maxe * 4) + rb(B * 64 * 2 * z * 4) + rb(B * 1024 * 2 * 8) + rb(B * 1024 * 2 * 4) + 65536);
   e->X4 = e->ws.alloc<float>(B * maxe);
-  e->bufA = e->ws.alloc<float>(B * maxe);
-  e->bufB = e->ws.alloc<float>(B * maxe);
   e->bufC = e->ws.alloc<float>(B * maxe);
   e->bufD = e->ws.alloc<float>(B * maxe);
+  for (ActVol* a : {&e->actA, &e->actB, &e->actX}) {
+    a->f = e->ws.alloc<float>(B * maxe);
+    if (planes) {
+      a->hi = e->ws.alloc<__nv_bfloat16>(B * maxe);
+      if (lo) a->lo = e->ws.alloc<__nv_bfloat16>(B * maxe);
+    }
+  }
   e->hbuf = e->ws.alloc<float>(B * 64 * 2 * z);
   e->sums = e->ws.alloc<double>(B * 1024 * 2);
   e->mr = e->ws.alloc<float>(B * 1024 * 2);
@@ -369,26 +412,23 @@ extern "C" int ipk_enc_forward(ipk_enc* e, const float* X, const float* eps, flo
     IPK_LAUNCH_CHECK();
   }
   // stem: Conv3d(3 -> C0, (3,7,7), stride 2, pad (1,3,3)) + GroupNorm(16) + ReLU
-  float* x = e->bufA;
+  ActVol x = e->actA;
   {
-    Vol o = run_conv3d(e->stem, e->X4, v, e->bufB, B, st);
-    group_norm(e, e->bufB, o, B, e->stem_gw, e->stem_gb, nullptr, true, x, st);
-    v = o;
+    ActVol in; in.f = e->X4;
+    v = conv_gn(e, e->stem, in, v, e->bufC, B, e->stem_gw, e->stem_gb, nullptr, true, x, st);
   }
   // BasicBlocks (motion_encoder.py:56-74): out = relu(gn2(conv2(relu(gn1(conv1(x))))) + residual)
   for (const EncBlock& blk : e->blocks) {
-    float* y = e->bufB; float* t = e->bufC; float* r = e->bufD;
-    Vol o = run_conv3d(blk.c1, x, v, t, B, st);
-    group_norm(e, t, o, B, blk.g1w, blk.g1b, nullptr, true, y, st);
-    run_conv3d(blk.c2, y, o, t, B, st);
-    const float* res = x;
+    const ActVol y = e->actB;
+    const Vol o = conv_gn(e, blk.c1, x, v, e->bufC, B, blk.g1w, blk.g1b, nullptr, true, y, st);
+    const float* res = x.f;
     if (blk.has_ds) {
-      run_conv3d(blk.ds, x, v, y, B, st);
-      group_norm(e, y, o, B, blk.gdw, blk.gdb, nullptr, false, r, st);
-      res = r;
+      ActVol r; r.f = e->bufD;
+      conv_gn(e, blk.ds, x, v, e->bufC, B, blk.gdw, blk.gdb, nullptr, false, r, st);
+      res = r.f;
     }
-    float* nx = (x == e->bufA) ? e->X4 : e->bufA;          // ping-pong the block output
-    group_norm(e, t, o, B, blk.g2w, blk.g2b, res, true, nx, st);
+    const ActVol nx = (x.f == e->actA.f) ? e->actX : e->actA;          // ping-pong the block output
+    conv_gn(e, blk.c2, y, o, e->bufC, B, blk.g2w, blk.g2b, res, true, nx, st);
     x = nx;
     v = o;
   }
@@ -396,7 +436,7 @@ extern "C" int ipk_enc_forward(ipk_enc* e, const float* X, const float* eps, flo
             "(motion_encoder.py:241 squeezes it)", T, v.T, v.H, v.W);
   // conv_mu | conv_var (2-D 3x3) and the reparameterisation with host-supplied eps
   {
-    ConvIn in; in.p = x; in.cstride = v.C; in.F = B; in.H = 8; in.W = 8;
+    ConvIn in; in.p = x.f; in.cstride = v.C; in.F = B; in.H = 8; in.W = 8;
     ConvOut o; o.p = e->hbuf; o.cstride = 2 * e->cfg.z_dim; o.Ho = 8; o.Wo = 8; o.bias = e->heads.bias;
     conv_run(e->heads, in, o, taps_3x3(), 1, st);
     reparam_kernel<<<cdiv(B * e->cfg.z_dim * 64, 256), 256, 0, st>>>(e->hbuf, eps, z_out, mu, logvar, B, e->cfg.z_dim);
@@ -482,7 +522,9 @@ static CBlock build_cblock(ipk_cenc* e, const std::string& p, int Cout, int CinS
 // Conv2dBlock.forward (util.py:256-273): conv -> GroupNorm(16) | InstanceNorm -> activation [-> + residual]
 static Vol run_cblock(ipk_cenc* e, const CBlock& b, const float* in, const Vol& v, float* tmp, float* out, int B, int act, const float* add,
                       cudaStream_t st) {
-  const Vol o = run_conv3d(b.conv, in, v, tmp, B, st);
+  Vol o;
+  ActVol ain; ain.f = const_cast<float*>(in);
+  run_conv3d(b.conv, ain, v, tmp, B, nullptr, &o, st);
   const long long P = (long long)o.voxels();
   IPK_CUDA(cudaMemsetAsync(e->sums, 0, (size_t)B * o.C * 2 * sizeof(double), st));
   NormApply s; s.x = tmp; s.F = B; s.C = o.C; s.P = P; s.stats_out = e->sums;

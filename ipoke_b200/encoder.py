@@ -28,7 +28,7 @@ class _NativeEncPlan:
 class ResNetMotionEncoder(nn.Module):
     """dic: the first stage's config['architecture'] (+ img_size, max_frames, full_seq as SpadeCondMotionModel sets them,
     first_stage_motion_model.py:478-480): z_dim, ENC_M_channels, img_size, max_frames, full_seq [, min_spatial_size,
-    deterministic].  Extra key: ipk_max_batch."""
+    deterministic].  Extra keys: ipk_max_batch, ipk_precision ("fp32" = bf16x3 tcgen05 Conv3d (default), "bf16", "fp32_simt")."""
 
     def __init__(self, dic):
         super().__init__()
@@ -42,6 +42,7 @@ class ResNetMotionEncoder(nn.Module):
         for k, m in tree._modules.items():
             self.add_module(k, m)
         self.max_batch = int(dic.get("ipk_max_batch", 32))
+        self.precision = dic.get("ipk_precision", "fp32")
         self._plan = None
         self._plan_key = None
         self._plist = None
@@ -70,6 +71,7 @@ class ResNetMotionEncoder(nn.Module):
         for i, ch in enumerate(self._cfg["ENC_M_channels"]):
             c.channels[i] = ch
         c.min_spatial_size, c.max_batch = self._cfg["min_spatial_size"], self.max_batch
+        c.precision = _lib.precision_code(self.precision)
         h = ctypes.c_void_p()
         with torch.cuda.device(device):
             _lib.check(L.ipk_enc_create(ctypes.byref(c), ctypes.byref(h)), "ipk_enc_create")
