@@ -348,9 +348,10 @@ void conv3d_tc_run(const ConvW& w, const Conv3dShape& s, const void* in_hi, cons
   a.nkb = w.Kpad / C3T_BK; a.Npad = w.Npad; a.N = w.N;
   a.out = out; a.cstride = s.Cout; a.stats = stats;
   // activation map: dims (C, W, H, T, B); element strides carry the spatial conv stride
-  const cuuint64_t cs = (cuuint64_t)s.Cin * 2;
+  const cuuint64_t cs = s.stride_x > 0 ? (cuuint64_t)s.stride_x : (cuuint64_t)s.Cin * 2;
+  const cuuint64_t rs = s.stride_y > 0 ? (cuuint64_t)s.stride_y : cs * s.Wi;
   cuuint64_t gd[5] = {(cuuint64_t)s.Cin, (cuuint64_t)s.Wi, (cuuint64_t)s.Hi, (cuuint64_t)s.Ti, (cuuint64_t)B};
-  cuuint64_t gs[4] = {cs, cs * s.Wi, cs * s.Wi * s.Hi, cs * s.Wi * s.Hi * s.Ti};
+  cuuint64_t gs[4] = {cs, rs, rs * s.Hi, rs * s.Hi * s.Ti};
   cuuint32_t bx[5] = {(cuuint32_t)C3T_BK, (cuuint32_t)((a.bw - 1) * s.sx + 1), (cuuint32_t)((a.bh - 1) * s.sy + 1), 1u, (cuuint32_t)a.bb};
   cuuint32_t es[5] = {1u, (cuuint32_t)s.sx, (cuuint32_t)s.sy, 1u, 1u};
   const CUtensorMap mA_hi = encode_map(in_hi, 5, gd, gs, bx, es);

@@ -8,6 +8,9 @@ struct Conv3dShape {
   int Cin, Cout;                 // channels as stored
   int Ti, Hi, Wi;                // input volume
   int kt, ky, kx, st, sy, sx, pt, py, px;
+  // optional byte strides of the input view (0 = dense NDHWC): element (c, x, y) of a time plane sits at c*2 + x*stride_x + y*stride_y.
+  // stride_x < Cin*2 gives an OVERLAPPED view: the x taps of a small-channel input folded into K (see encoder.cu: stem).
+  long long stride_x = 0, stride_y = 0;
 };
 
 // Cin, Cout multiples of 64; output rows tile into 128-voxel boxes of one time step (W_out a power of two <= 128 or a multiple of 128)

@@ -138,6 +138,49 @@ __global__ void ncdhw_to_ndhwc4_kernel(const float* __restrict__ in, float* __re
   }
 }
 
+// Tensor-core stem (Conv3d 3 -> C0, (3,7,7), stride 2, pad (1,3,3)): the 7 x-taps are folded into K.  The input is stored as bf16
+// planes [B][T][H][Wp][8] (3 channels + 5 zeros per pixel, 3 zero pixels of left padding, Wp = W + 8), so the 8 pixels x 8 channels
+// starting at padded pixel 2*ox are 64 CONTIGUOUS elements = one 128-byte K block of output column ox; the TMA map views the rows with
+// an overlapped x stride of 2 pixels (32 B).  The conv then has 3 x 7 (dt, dy) taps of K = 64 (56 used), y / t padding by OOB fill.
+constexpr int STEM_CP = 8, STEM_XPAD = 3;
+__global__ void stem_input_planes_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int B, int T,
+                                         int H, int W, int Wp) {
+  const long long rows = (long long)B * T * H, total = rows * Wp;
+  const long long V = (long long)T * H * W;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int xp = (int)(e % Wp);
+    const long long row = e / Wp;                      // (b, t, y)
+    const long long b = row / ((long long)T * H), ty = row % ((long long)T * H);
+    const int x = xp - STEM_XPAD;
+    float v[3] = {0.f, 0.f, 0.f};
+    if (x >= 0 && x < W) {
+      const float* ip = in + (size_t)b * 3 * V + (size_t)ty * W + x;
+      v[0] = ip[0]; v[1] = ip[V]; v[2] = ip[2 * V];
+    }
+    uint32_t h[4] = {0, 0, 0, 0}, l[4] = {0, 0, 0, 0};
+    __nv_bfloat16 hb[3], lb[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { hb[c] = __float2bfloat16_rn(v[c]); lb[c] = __float2bfloat16_rn(v[c] - __bfloat162float(hb[c])); }
+    h[0] = (uint32_t)__bfloat16_as_ushort(hb[0]) | ((uint32_t)__bfloat16_as_ushort(hb[1]) << 16); h[1] = (uint32_t)__bfloat16_as_ushort(hb[2]);
+    l[0] = (uint32_t)__bfloat16_as_ushort(lb[0]) | ((uint32_t)__bfloat16_as_ushort(lb[1]) << 16); l[1] = (uint32_t)__bfloat16_as_ushort(lb[2]);
+    ((uint4*)hi)[e] = make_uint4(h[0], h[1], h[2], h[3]);
+    if (lo) ((uint4*)lo)[e] = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+// w: OIDHW [Cout][3][3][7][7] -> planes [tap = dt*7 + dy][Npad][64] with k = dx*8 + c
+__global__ void pack_stem_tc_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int Cout, int Npad) {
+  const int total = 21 * Cout * 21;                    // (tap, n, dx*3 + c)
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int j = e % 21, n = (e / 21) % Cout, tap = e / (21 * Cout);
+    const int dx = j / 3, c = j % 3, dt = tap / 7, dy = tap % 7;
+    const float v = w[((((size_t)n * 3 + c) * 3 + dt) * 7 + dy) * 7 + dx];
+    const size_t di = ((size_t)tap * Npad + n) * 64 + dx * STEM_CP + c;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[di] = h;
+    if (lo) lo[di] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
 // x [B][C][P] (NCHW, C <= 4) -> [B][P][4] (missing channels zero)
 __global__ void nchw_to_nhwc4_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int C, long long P) {
   const long long total = (long long)B * P;
@@ -178,6 +221,9 @@ struct ipk_enc {
   DevPool pool;
   Arena ws;
   Conv3dDesc stem;
+  ConvW stem_tc;             // tensor-core stem: 21 (dt, dy) taps x K = 64 (x taps folded into K), see stem_input_planes_kernel
+  bool stem_on_tc = false;
+  __nv_bfloat16 *Xp_hi = nullptr, *Xp_lo = nullptr;
   float *stem_gw = nullptr, *stem_gb = nullptr;
   std::vector<EncBlock> blocks;
   ConvW heads;               // conv_mu | conv_var fused along N (2-D 3x3, fp32 FFMA engine)
@@ -327,6 +373,17 @@ extern "C" int ipk_enc_finalize(ipk_enc* e, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const ipk_enc_config& c = e->cfg;
   e->stem = build_conv3d(e, "conv1.weight", c.channels[0], 3, 3, 7, 7, 2, 2, 2, 1, 3, 3, st);
+  if (c.precision != IPK_PREC_FP32_SIMT && c.channels[0] % 64 == 0) {
+    const int S = c.img_size;
+    Conv3dShape ss{64, c.channels[0], c.max_frames + 1, S, S / 2, 3, 7, 1, 2, 2, 1, 1, 3, 0, 2 * STEM_CP * 2, (long long)(S + 8) * STEM_CP * 2};
+    if (conv3d_tc_supported(ss)) {
+      e->stem_tc = conv_alloc(e->pool, c.precision, 21, 64, c.channels[0], false);
+      pack_stem_tc_kernel<<<cdiv(21 * c.channels[0] * 21, 256), 256, 0, st>>>((const float*)eneed(e, "conv1.weight", (int64_t)c.channels[0] * 3 * 147).p,
+                                                                              e->stem_tc.w_hi, e->stem_tc.w_lo, c.channels[0], e->stem_tc.Npad);
+      IPK_LAUNCH_CHECK();
+      e->stem_on_tc = true;
+    }
+  }
   e->stem_gw = ecopy(e, "bn1.weight", c.channels[0], st);
   e->stem_gb = ecopy(e, "bn1.bias", c.channels[0], st);
   auto plan = stage_plan(c);
@@ -377,10 +434,15 @@ extern "C" int ipk_enc_finalize(ipk_enc* e, void* stream) {
   auto rb = [](size_t b) { return (b + 255) / 256 * 256; };
   const bool planes = c.precision != IPK_PREC_FP32_SIMT;
   const bool lo = c.precision == IPK_PREC_FP32_SPLIT;
-  e->ws.init((6 + (planes ? 3 : 0)) * rb(B * maxe * 4) + rb(B * 64 * 2 * z * 4) + rb(B * 1024 * 2 * 8) + rb(B * 1024 * 2 * 4) + 65536);
+  const size_t xp_elems = (size_t)(c.max_frames + 1) * c.img_size * (c.img_size + 8) * STEM_CP;
+  e->ws.init((6 + (planes ? 3 : 0)) * rb(B * maxe * 4) + (e->stem_on_tc ? 2 * rb(B * xp_elems * 2) : 0) + rb(B * 64 * 2 * z * 4) + rb(B * 1024 * 2 * 8) + rb(B * 1024 * 2 * 4) + 65536);
   e->X4 = e->ws.alloc<float>(B * maxe);
   e->bufC = e->ws.alloc<float>(B * maxe);
   e->bufD = e->ws.alloc<float>(B * maxe);
+  if (e->stem_on_tc) {
+    e->Xp_hi = e->ws.alloc<__nv_bfloat16>(B * xp_elems);
+    if (lo) e->Xp_lo = e->ws.alloc<__nv_bfloat16>(B * xp_elems);
+  }
   for (ActVol* a : {&e->actA, &e->actB, &e->actX}) {
     a->f = e->ws.alloc<float>(B * maxe);
     if (planes) {
@@ -406,14 +468,35 @@ extern "C" int ipk_enc_forward(ipk_enc* e, const float* X, const float* eps, flo
   cudaStream_t st = (cudaStream_t)stream;
   const int S = e->cfg.img_size;
   Vol v{T, S, S, 4};
-  {
+  ActVol x = e->actA;
+  if (e->stem_on_tc) {
+    // stem on tcgen05: padded bf16 planes of X, x taps folded into K (see stem_input_planes_kernel), GroupNorm statistics fused
+    const int Wp = S + 8;
+    {
+      ProfScope ps("enc.stem.planes", st);
+      const long long tot = (long long)B * T * S * Wp;
+      stem_input_planes_kernel<<<(int)std::min<long long>((tot + 255) / 256, 148 * 32), 256, 0, st>>>(X, e->Xp_hi, e->Xp_lo, B, T, S, S, Wp);
+      IPK_LAUNCH_CHECK();
+    }
+    const Conv3dShape ss{64, e->stem.Cout, T, S, S / 2, 3, 7, 1, 2, 2, 1, 1, 3, 0, 2 * STEM_CP * 2, (long long)Wp * STEM_CP * 2};
+    const Vol o = conv3d_out(e->stem, v);
+    IPK_CUDA(cudaMemsetAsync(e->sums, 0, (size_t)B * o.C * 2 * sizeof(double), st));
+    {
+      ProfScope ps("enc.conv3d.tc", st);
+      conv3d_tc_run(e->stem_tc, ss, e->Xp_hi, e->Xp_lo, B, e->bufC, e->sums, st);
+    }
+    ProfScope ps("enc.group_norm", st);
+    const long long P = (long long)o.voxels();
+    finalize_stats(e->sums, e->mr, B, P, o.C, 16, 1e-5f, st);
+    NormApply n; n.x = e->bufC; n.F = B; n.C = o.C; n.P = P; n.mr = e->mr; n.w = e->stem_gw; n.b = e->stem_gb; n.act = ACT_RELU;
+    n.out_f32 = x.f; n.out_hi = x.hi; n.out_lo = x.lo;
+    norm_apply(n, st);
+    v = o;
+  } else {
+    // stem: Conv3d(3 -> C0, (3,7,7), stride 2, pad (1,3,3)) + GroupNorm(16) + ReLU on the FFMA kernel
     const long long V = (long long)v.voxels();
     ncdhw_to_ndhwc4_kernel<<<(int)std::min<long long>(((long long)B * V + 255) / 256, 148 * 32), 256, 0, st>>>(X, e->X4, B, V);
     IPK_LAUNCH_CHECK();
-  }
-  // stem: Conv3d(3 -> C0, (3,7,7), stride 2, pad (1,3,3)) + GroupNorm(16) + ReLU
-  ActVol x = e->actA;
-  {
     ActVol in; in.f = e->X4;
     v = conv_gn(e, e->stem, in, v, e->bufC, B, e->stem_gw, e->stem_gb, nullptr, true, x, st);
   }
