@@ -57,29 +57,32 @@ __host__ __device__ inline int mma_hsb(int C) { const int n = (4 * C + 15) / 16;
 __host__ __device__ inline int mma_koff(int k) { return ((k & 7) >> 1) * 16 + (((k >> 3) << 1) | (k & 1)) * 2; }
 __host__ __device__ inline int mma_wst_slots(int C) { return 2 * 6 * ((C + 15) / 16); }     // staged conv fragments (uint4) per thread
 
-__host__ __device__ inline SegOffsets seg_layout(int C, bool has_mcf, bool mma) {
+// mode: 0 = FFMA paths, 1 = register-resident mma path (C <= 32), 2 = streamed mma path (32 < C <= 64)
+__host__ __device__ inline SegOffsets seg_layout(int C, bool has_mcf, int mode) {
   const int Cs = (C + 3) / 4 * 4;
   const int C2s = (2 * C + 3) / 4 * 4;
-  const bool fast = C <= FAST_MAXC;
+  const bool fast = C <= FAST_MAXC && mode != 2;
+  const bool mma = mode == 1;
+  const bool big = has_mcf && mode == 2;
   SegOffsets o;
   size_t off = (size_t)64 * Cs;                       // s
   o.tmp = off; off += (size_t)64 * Cs;
   o.hterm = off; off += has_mcf ? (size_t)(fast ? 2 : 1) * 64 * C2s : 0;
   const bool use_mma = has_mcf && fast && mma;
   o.pc = off; off += (has_mcf && fast && !use_mma) ? (size_t)2 * 8 * 128 : 0;
-  o.act = off; off += (has_mcf && !use_mma) ? (size_t)8 * ((seg_hidmax(C) + 3) / 4 * 4) : 0;
-  o.p1 = off; off += (has_mcf && !use_mma) ? (fast ? (size_t)4 * 8 * 64 : (size_t)8 * C2s) : 0;
+  o.act = off; off += (has_mcf && !use_mma && !big) ? (size_t)8 * ((seg_hidmax(C) + 3) / 4 * 4) : 0;
+  o.p1 = off; off += (has_mcf && !use_mma && !big) ? (fast ? (size_t)4 * 8 * 64 : (size_t)8 * C2s) : 0;
   o.red = off; off += 32;
-  o.ring = off; off += use_mma ? (size_t)(3 * 10 * mma_xsb(C)) / 4 : 0;
-  o.actb = off; off += use_mma ? (size_t)(8 * mma_hsb(C)) / 4 : 0;
+  o.ring = off; off += (use_mma || big) ? (size_t)(3 * 10 * mma_xsb(C)) / 4 : 0;
+  o.actb = off; off += (use_mma || big) ? (size_t)(8 * mma_hsb(C)) / 4 : 0;
   off = (off + 3) / 4 * 4;
   o.wst = off; off += use_mma ? (size_t)mma_wst_slots(C) * SEG_THREADS * 4 : 0;     // [slot][thread] uint4
   o.total = off;
   return o;
 }
 
-size_t flow_segment_smem_bytes(int C, bool has_mcf, bool mma) {
-  return seg_layout(C, has_mcf, mma).total * sizeof(float);
+size_t flow_segment_smem_bytes(int C, bool has_mcf, int mode) {
+  return seg_layout(C, has_mcf, mode).total * sizeof(float);
 }
 
 __device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) {
@@ -457,6 +460,158 @@ __device__ __forceinline__ void mcf_mma(const MicroOp& op, const MicroOp* next, 
   }
 }
 
+// ---------------------------------------------------------------------------------------------- streamed mma MCF (32 < C <= 64)
+// Same contractions, operand ring and fragment packing as mcf_mma, but hid = 4C <= 256 hidden units are 16 m-tiles and K = 6C is
+// up to 24 k-tiles: the A fragments no longer fit in registers, so every warp streams the fragments of its m-tiles
+// {warp, warp + 8} from L2 each line (coalesced 512-byte warp loads, one (tap row, dv) group = up to 8 fragments prefetched
+// while the previous group's MMAs issue).  The conditioning term is loaded at the start of the MCF.
+struct BigFrag { uint4 hi[4], lo[4]; };
+__device__ __forceinline__ void big_load_group(BigFrag& f, const uint4* __restrict__ wp, size_t plane, int kt0, int nct) {
+#pragma unroll
+  for (int ct = 0; ct < 4; ++ct)
+    if (ct < nct) {
+      f.hi[ct] = __ldg(wp + (size_t)(kt0 + ct) * 32);
+      f.lo[ct] = __ldg(wp + plane + (size_t)(kt0 + ct) * 32);
+    }
+}
+
+template <bool FWD>
+__device__ __forceinline__ void mcf_mma_big(const MicroOp& op, const SegSmem& sm, int Cs, int b, float& ld) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int order = op.i0, C = op.i1, hid = op.i3;
+  const int nct = (C + 15) >> 4, nkt = 6 * nct;
+  const int nmt = (hid + 15) >> 4, nkt1 = nmt, nmt1 = (C + 3) >> 2;
+  const int XSB = mma_xsb(C), HSB = mma_hsb(C);
+  const int C2s = (2 * C + 3) / 4 * 4;
+  const int pb = order == 1 ? 56 : (order == 3 ? 7 : 0);
+  const int pu = order == 0 ? 8 : (order == 1 ? -8 : (order == 2 ? 1 : -1));
+  const int pv = order < 2 ? 1 : 8;
+  const uint4* WA = (const uint4*)op.p0;
+  const size_t planeA = (size_t)nmt * nkt * 32;
+  const uint2* W1 = (const uint2*)op.p1;
+  const size_t plane1 = (size_t)nmt1 * nkt1 * 32;
+  float* hterm = sm.hterm;
+  {  // conditioning term of this MCF (precomputed GEMM, flow.cu): rows b*64 + p, C2s columns
+    const int q = C2s >> 2;
+    const float* src = op.p2 + (size_t)b * 64 * op.l0;
+    for (int i = tid; i < 64 * q; i += SEG_THREADS) {
+      const int p = i / q, j = i - p * q;
+      *(float4*)(hterm + p * C2s + 4 * j) = __ldg((const float4*)(src + (size_t)p * op.l0 + 4 * j));
+    }
+  }
+  if (FWD) {
+    for (int i = tid; i < 64 * Cs; i += SEG_THREADS) sm.tmp[i] = sm.s[i];
+  }
+  __syncthreads();
+
+  const int dpos = t * 2 + (g >> 2);
+  int slot2 = 1, slot1 = 2, slot0 = 0;
+  for (int u = 0; u < 8; ++u) {
+    if (u > 0) {
+      // ---- phase A: hidden = shifted conv of the last two finished lines, ELU -> act rows (bf16 hi/lo)
+      for (int mt = warp; mt < nmt; mt += SEG_THREADS / 32) {
+        float d[6][4];
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) d[i][j] = 0.f;
+        const uint4* wp = WA + (size_t)mt * nkt * 32 + lane;
+        const int g0 = u >= 2 ? 0 : 3;                    // first (tap row, dv) group with a real line behind it
+        BigFrag fa, fb;
+        big_load_group(fa, wp, planeA, g0 * nct, nct);
+#pragma unroll
+        for (int gi = 0; gi < 6; ++gi) {
+          if (gi < g0) continue;                           // warp-uniform
+          BigFrag& cur = (gi & 1) ? fb : fa;
+          BigFrag& nxt = (gi & 1) ? fa : fb;
+          if (gi + 1 < 6) big_load_group(nxt, wp, planeA, (gi + 1) * nct, nct);
+          const int rr = gi / 3, dvi = gi - rr * 3;
+          const unsigned char* rowp = sm.ring + ((rr == 0 ? slot2 : slot1) * 10 + g) * XSB + t * 16 + dvi * XSB;
+          const int ch = (dvi & 1) * 3;
+#pragma unroll
+          for (int ct = 0; ct < 4; ++ct)
+            if (ct < nct) {
+              const uint4 bq = *(const uint4*)(rowp + ct * 64);
+              mma_bf16(d[ch + 0], cur.hi[ct], bq.x, bq.y);
+              mma_bf16(d[ch + 1], cur.lo[ct], bq.x, bq.y);
+              mma_bf16(d[ch + 2], cur.hi[ct], bq.z, bq.w);
+            }
+        }
+        const int a_off0 = mt * 64 + mma_koff(g), a_off1 = mt * 64 + mma_koff(g + 8);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float h = ((d[0][j] + d[3][j]) + (d[1][j] + d[4][j])) + (d[2][j] + d[5][j]);
+          h = h > 0.f ? h : (exp2f(h * 1.4426950408889634f) - 1.0f);
+          const int pos = t * 2 + (j & 1);
+          if (mt * 16 + g + (j >> 1) * 8 < hid) {
+            unsigned char* ap = sm.actb + pos * HSB + ((j >> 1) ? a_off1 : a_off0);
+            const __nv_bfloat16 hi = __float2bfloat16_rn(h);
+            *(__nv_bfloat16*)ap = hi;
+            *(__nv_bfloat16*)(ap + 8) = __float2bfloat16_rn(h - __bfloat162float(hi));
+          }
+        }
+      }
+      __syncthreads();
+    }
+    // ---- phase C + D: 1x1 on the act rows + conditioning term, affine transform of line u (as in mcf_mma)
+    for (int mt1 = warp; mt1 < nmt1; mt1 += SEG_THREADS / 32) {
+      float d[6][4];
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) d[i][j] = 0.f;
+      if (u > 0) {
+        const unsigned char* ap = sm.actb + g * HSB + t * 16;
+        const uint2* wp1 = W1 + (size_t)mt1 * nkt1 * 32 + lane;
+#pragma unroll 1
+        for (int k0 = 0; k0 < nkt1; k0 += 8) {
+          uint2 ah[8], al[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (k0 + k < nkt1) { ah[k] = __ldg(wp1 + (size_t)(k0 + k) * 32); al[k] = __ldg(wp1 + plane1 + (size_t)(k0 + k) * 32); }
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (k0 + k < nkt1) {
+              const uint4 bq = *(const uint4*)(ap + (k0 + k) * 64);
+              const int ch = (k & 1) * 3;
+              const uint4 ahi = make_uint4(ah[k].x, 0u, ah[k].y, 0u), alo = make_uint4(al[k].x, 0u, al[k].y, 0u);
+              mma_bf16(d[ch + 0], ahi, bq.x, bq.y);
+              mma_bf16(d[ch + 1], alo, bq.x, bq.y);
+              mma_bf16(d[ch + 2], ahi, bq.z, bq.w);
+            }
+        }
+      }
+      const float v0 = ((d[0][0] + d[3][0]) + (d[1][0] + d[4][0])) + (d[2][0] + d[5][0]);
+      const float v1 = ((d[0][1] + d[3][1]) + (d[1][1] + d[4][1])) + (d[2][1] + d[5][1]);
+      const bool is_mu = g < 4;
+      const float got = __shfl_xor_sync(0xffffffffu, is_mu ? v1 : v0, 16);
+      const int c = mt1 * 4 + (g & 3);
+      if (c < C) {
+        const int pix = pb + u * pu + dpos * pv;
+        const float mu = (is_mu ? v0 : got) + hterm[pix * C2s + c];
+        const float ls = (is_mu ? got : v1) + hterm[pix * C2s + C + c];
+        const float sc = FWD ? 1.0f + tanhf(0.5f * ls) : 2.0f * __frcp_rn(1.0f + exp2f(-1.4426950408889634f * ls));
+        float xin;
+        if (FWD) {
+          xin = sm.tmp[pix * Cs + c];
+          sm.s[pix * Cs + c] = sc * xin + mu;
+          ld += logf(sc);
+        } else {
+          xin = (sm.s[pix * Cs + c] - mu) * __frcp_rn(sc + 1e-12f);
+          sm.s[pix * Cs + c] = xin;
+        }
+        unsigned char* rp = sm.ring + (slot0 * 10 + dpos + 1) * XSB + (c >> 4) * 64 + mma_koff(c & 15);
+        const __nv_bfloat16 hi = __float2bfloat16_rn(xin);
+        *(__nv_bfloat16*)rp = hi;
+        *(__nv_bfloat16*)(rp + 8) = __float2bfloat16_rn(xin - __bfloat162float(hi));
+      }
+    }
+    __syncthreads();
+    { const int tmp = slot2; slot2 = slot1; slot1 = slot0; slot0 = tmp; }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- generic MCF (C > 32)
 template <bool FWD>
 __device__ void mcf_generic(const MicroOp& op, const SegSmem& sm, int Cs, int b, float& ld) {
@@ -624,7 +779,8 @@ __device__ __forceinline__ int next_mcf(const MicroOp* __restrict__ ops, int fro
   return -1;
 }
 
-template <bool FWD, bool MMA>
+// MODE: 0 = FFMA MCF paths, 1 = register-resident mma MCFs (C <= 32), 2 = streamed mma MCFs (32 < C <= 64)
+template <bool FWD, int MODE>
 __global__ void __launch_bounds__(SEG_THREADS, 1) flow_segment_kernel(const MicroOp* __restrict__ ops, int nops, int C, int has_mcf,
                                                                        float* __restrict__ state, int C0,
                                                                        float* __restrict__ logdet, int b0) {
@@ -633,9 +789,11 @@ __global__ void __launch_bounds__(SEG_THREADS, 1) flow_segment_kernel(const Micr
   const int b = blockIdx.x + b0;
   const int Cs = (C + 3) / 4 * 4;
   const int C2s = (2 * C + 3) / 4 * 4;
-  const bool fast = C <= FAST_MAXC;
+  constexpr bool MMA = MODE == 1;
+  constexpr bool BIG = MODE == 2;
+  const bool fast = !BIG && C <= FAST_MAXC;
   SegSmem sm;
-  const SegOffsets lo = seg_layout(C, has_mcf != 0, MMA);
+  const SegOffsets lo = seg_layout(C, has_mcf != 0, MODE);
   sm.s = smem; sm.tmp = smem + lo.tmp; sm.hterm = smem + lo.hterm; sm.pc = smem + lo.pc; sm.act = smem + lo.act;
   sm.p1 = smem + lo.p1; sm.red = smem + lo.red;
   sm.ring = (unsigned char*)(smem + lo.ring); sm.actb = (unsigned char*)(smem + lo.actb); sm.wst = (uint4*)(smem + lo.wst);
@@ -682,6 +840,15 @@ __global__ void __launch_bounds__(SEG_THREADS, 1) flow_segment_kernel(const Micr
     }
   }
 
+  if constexpr (BIG) {
+    if (has_mcf) {   // operand ring (zero halo, channel padding) and act rows start from zero
+      uint32_t* z = (uint32_t*)sm.ring;
+      const int nz = (int)(lo.wst - lo.ring);
+      for (int i = tid; i < nz; i += SEG_THREADS) z[i] = 0u;
+      __syncthreads();
+    }
+  }
+
   for (int oi = op_begin; oi < nops; ++oi) {
     const MicroOp op = ops[oi];
     switch (op.kind) {
@@ -716,7 +883,9 @@ __global__ void __launch_bounds__(SEG_THREADS, 1) flow_segment_kernel(const Micr
         break;
       }
       case MK_MCF: {
-        if (fast) {
+        if constexpr (BIG) {
+          mcf_mma_big<FWD>(op, sm, Cs, b, ld);
+        } else if (fast) {
           // registers hold this MCF's weights; its conditioning term is the (possibly still pending) cp.async group of
           // buffer hbuf.  Queue the NEXT MCF's conditioning term into the other buffer, then wait for ours.
           const int nn = next_mcf(ops, oi + 1, nops);
@@ -793,28 +962,33 @@ __global__ void __launch_bounds__(SEG_THREADS, 1) flow_segment_kernel(const Micr
 }
 
 void flow_segment_init() {
-  IPK_CUDA(cudaFuncSetAttribute(flow_segment_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  IPK_CUDA(cudaFuncSetAttribute(flow_segment_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  IPK_CUDA(cudaFuncSetAttribute(flow_segment_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  IPK_CUDA(cudaFuncSetAttribute(flow_segment_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  IPK_CUDA(cudaFuncSetAttribute(flow_segment_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  IPK_CUDA(cudaFuncSetAttribute(flow_segment_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  IPK_CUDA(cudaFuncSetAttribute(flow_segment_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  IPK_CUDA(cudaFuncSetAttribute(flow_segment_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  IPK_CUDA(cudaFuncSetAttribute(flow_segment_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  IPK_CUDA(cudaFuncSetAttribute(flow_segment_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 }
 
 void flow_segment_run(const SegmentLaunch& s, bool forward, float* state, int C0, float* logdet, int b0, int nb, cudaStream_t st) {
   const int B = nb;
   if (s.nops == 0 || B == 0) return;
-  const bool mma = s.mma && s.has_mcf && s.C <= FAST_MAXC;
-  size_t smem = flow_segment_smem_bytes(s.C, s.has_mcf, mma);
+  // tensor-core precisions: register-resident mma MCFs up to 32 channels, streamed mma MCFs up to MCF_MMA_MAXC, FFMA beyond
+  const int mode = (s.mma && s.has_mcf) ? (s.C <= FAST_MAXC ? 1 : (s.C <= MCF_MMA_MAXC ? 2 : 0)) : 0;
+  size_t smem = flow_segment_smem_bytes(s.C, s.has_mcf, mode);
   IPK_CHECK(smem <= 200 * 1024, IPK_ERR_UNSUPPORTED, "flow segment needs %zu bytes of shared memory (C=%d)", smem, s.C);
   const int hm = s.has_mcf ? 1 : 0;
   const MicroOp* ops = s.ops;
   const int nops = s.nops, C = s.C;
   auto go = [&](auto kernel) { launch_k(kernel, dim3(B), dim3(SEG_THREADS), smem, st, ops, nops, C, hm, state, C0, logdet, b0); };
   if (forward) {
-    if (mma) go(flow_segment_kernel<true, true>);
-    else go(flow_segment_kernel<true, false>);
+    if (mode == 1) go(flow_segment_kernel<true, 1>);
+    else if (mode == 2) go(flow_segment_kernel<true, 2>);
+    else go(flow_segment_kernel<true, 0>);
   } else {
-    if (mma) go(flow_segment_kernel<false, true>);
-    else go(flow_segment_kernel<false, false>);
+    if (mode == 1) go(flow_segment_kernel<false, 1>);
+    else if (mode == 2) go(flow_segment_kernel<false, 2>);
+    else go(flow_segment_kernel<false, 0>);
   }
 }
 

@@ -48,13 +48,13 @@ constexpr int MAX_NSPLIT = 9;   // upper bound on the split-K slices of a NICE c
 
 // state: [*][64][C0] fp32 NHWC (in place); logdet: [*] (forward only, accumulated); processes samples [b0, b0 + nb)
 void flow_segment_run(const SegmentLaunch& s, bool forward, float* state, int C0, float* logdet, int b0, int nb, cudaStream_t st);
-size_t flow_segment_smem_bytes(int C, bool has_mcf, bool mma);
+size_t flow_segment_smem_bytes(int C, bool has_mcf, int mode);   // mode 0 FFMA, 1 register-resident mma, 2 streamed mma
 // mma.sync A-fragment packing of one MCF (see flow_segment.cu); sizes in 32-bit words (hi + lo planes)
 size_t mcf_mma_conv_words(int C);
 size_t mcf_mma_1x1_words(int C);
 void pack_mcf_mma(const float* shift_w, const float* v, const float* os, uint32_t* conv_dst, uint32_t* x1_dst, int hid, int C,
                   int kh, int kw, int order, int row, cudaStream_t st);
-constexpr int MCF_MMA_MAXC = 32;
+constexpr int MCF_MMA_MAXC = 64;   // mma.sync MCF paths: register-resident fragments up to 32 channels, streamed from L2 up to 64
 void flow_segment_init();
 
 }  // namespace ipk
