@@ -502,7 +502,11 @@ extern "C" int ipk_enc_forward(ipk_enc* e, const float* X, const float* eps, flo
   }
   // BasicBlocks (motion_encoder.py:56-74): out = relu(gn2(conv2(relu(gn1(conv1(x))))) + residual)
   for (const EncBlock& blk : e->blocks) {
-    const ActVol y = e->actB;
+    ActVol y = e->actB;
+    {   // the mid-block activation feeds conv2 only: when that conv runs on tcgen05 it reads the bf16 planes, so skip the fp32 copy
+      const Vol o1 = conv3d_out(blk.c1, v);
+      if (blk.c2.tc && y.hi != nullptr && conv3d_tc_supported(shape_of(blk.c2, o1))) y.f = nullptr;
+    }
     const Vol o = conv_gn(e, blk.c1, x, v, e->bufC, B, blk.g1w, blk.g1b, nullptr, true, y, st);
     const float* res = x.f;
     if (blk.has_ds) {

@@ -519,7 +519,8 @@ __device__ __forceinline__ void mcf_mma_big(const MicroOp& op, const SegSmem& sm
         const uint4* wp = WA + (size_t)mt * nkt * 32 + lane;
         const int g0 = u >= 2 ? 0 : 3;                    // first (tap row, dv) group with a real line behind it
         BigFrag fa, fb;
-        big_load_group(fa, wp, planeA, g0 * nct, nct);
+        if (g0 & 1) big_load_group(fb, wp, planeA, g0 * nct, nct);      // group gi lives in fa (even gi) / fb (odd gi)
+        else big_load_group(fa, wp, planeA, g0 * nct, nct);
 #pragma unroll
         for (int gi = 0; gi < 6; ++gi) {
           if (gi < g0) continue;                           // warp-uniform
