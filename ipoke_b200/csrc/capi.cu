@@ -2,6 +2,7 @@
 #include <cstdarg>
 #include <mutex>
 #include <map>
+#include <tuple>
 #include "conv.cuh"
 #include "elementwise.cuh"
 
@@ -97,15 +98,88 @@ extern "C" const char* ipk_last_error(void) { return g_last_error.c_str(); }
 extern "C" int64_t ipk_launch_count(void) { return g_launches; }
 extern "C" void ipk_launch_count_reset(void) { g_launches = 0; }
 
+// ---- CUDA-graph replay of the whole sampling step.  A step is ~6 500 dependent launches; replaying them as one graph removes the
+// per-launch driver work from the critical path (the programmatic-dependent-launch edges are kept by stream capture).  A graph is
+// keyed by (plans, buffers, B, T): the first call with a key runs eagerly (lazy one-time setup: function attributes, tensor maps),
+// the second is captured on an internal stream -- torch's default stream is the legacy stream, which cannot capture -- and from
+// then on the instantiated graph is launched into the caller's stream.  IPK_GRAPH=0 disables it; the profiler path never uses it.
+namespace {
+struct GraphKey {
+  const void *f, *d, *a0, *a1, *a2, *a3; int B, T, kind;
+  bool operator<(const GraphKey& o) const {
+    return std::tie(f, d, a0, a1, a2, a3, B, T, kind) < std::tie(o.f, o.d, o.a0, o.a1, o.a2, o.a3, o.B, o.T, o.kind);
+  }
+};
+struct GraphEntry { cudaGraphExec_t exec = nullptr; int64_t launches = 0; int seen = 0; bool failed = false; };
+std::map<GraphKey, GraphEntry> g_graphs;
+std::mutex g_graphs_mu;
+cudaStream_t g_cap_st = nullptr;
+bool graph_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("IPK_GRAPH");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1 && !Prof::enabled();
+}
+// runs body(stream) eagerly, or captures / replays it; body must only enqueue work on the stream it is given
+template <typename Body>
+void run_graphed(const GraphKey& key, cudaStream_t st, Body&& body) {
+  if (!graph_enabled()) { body(st); return; }
+  std::lock_guard<std::mutex> lk(g_graphs_mu);
+  GraphEntry& e = g_graphs[key];
+  if (e.exec) {
+    IPK_CUDA(cudaGraphLaunch(e.exec, st));
+    g_launches += e.launches;
+    return;
+  }
+  if (e.failed || e.seen++ == 0) { body(st); return; }
+  if (!g_cap_st) IPK_CUDA(cudaStreamCreateWithFlags(&g_cap_st, cudaStreamNonBlocking));
+  const int64_t before = g_launches;
+  cudaGraph_t graph = nullptr;
+  IPK_CUDA(cudaStreamBeginCapture(g_cap_st, cudaStreamCaptureModeThreadLocal));
+  bool ok = true;
+  std::string err;
+  try { body(g_cap_st); } catch (const Error& ex) { ok = false; err = ex.what(); }
+  cudaError_t ce = cudaStreamEndCapture(g_cap_st, &graph);
+  if (ok && ce == cudaSuccess && graph) {
+    cudaGraphExec_t exec = nullptr;
+    ce = cudaGraphInstantiate(&exec, graph, 0);
+    if (ce == cudaSuccess) { e.exec = exec; e.launches = g_launches - before; }
+  }
+  if (graph) cudaGraphDestroy(graph);
+  g_launches = before;
+  if (!e.exec) {            // capture is an optimisation: fall back to eager launches for this key
+    cudaGetLastError();
+    e.failed = true;
+    body(st);
+    return;
+  }
+  IPK_CUDA(cudaGraphLaunch(e.exec, st));
+  g_launches += e.launches;
+}
+}  // namespace
+
+// plans call this from their destroy entry points: a recycled handle must not replay a stale graph
+void ipk_graphs_drop(const void* handle) {
+  std::lock_guard<std::mutex> lk(g_graphs_mu);
+  for (auto it = g_graphs.begin(); it != g_graphs.end();) {
+    if (it->first.f == handle || it->first.d == handle) {
+      if (it->second.exec) cudaGraphExecDestroy(it->second.exec);
+      it = g_graphs.erase(it);
+    } else ++it;
+  }
+}
+
 extern "C" int ipk_sample(ipk_flow* f, ipk_fs* d, const float* z, const float* cond, const float* x0, float* frames,
                           int32_t B, int32_t T, void* stream) {
   IPK_TRY
   IPK_CHECK(f && d && z && cond && x0 && frames, IPK_ERR_INVALID, "ipk_sample: null argument");
-  cudaStream_t st = (cudaStream_t)stream;
-  const float* motion = nullptr;   // flow state stays NHWC on device and feeds the GRU directly
-  int rc = ipk_flow_reverse_nhwc(f, z, cond, &motion, B, st);
-  if (rc != 0) return rc;
-  ipk_fs_decode_nhwc(d, motion, x0, frames, B, T, st);
+  run_graphed(GraphKey{f, d, z, cond, x0, frames, B, T, 0}, (cudaStream_t)stream, [&](cudaStream_t st) {
+    const float* motion = nullptr;   // flow state stays NHWC on device and feeds the GRU directly
+    ipk_flow_reverse_nhwc(f, z, cond, &motion, B, st);
+    ipk_fs_decode_nhwc(d, motion, x0, frames, B, T, st);
+  });
   IPK_CATCH
 }
 

@@ -25,6 +25,7 @@ struct UpBlock {
 };
 }  // namespace ipk
 
+void ipk_graphs_drop(const void* handle);   // capi.cu
 using namespace ipk;
 
 struct ipk_fs {
@@ -579,6 +580,7 @@ extern "C" int ipk_fs_gen(ipk_fs* d, const float* h, const float* x0, float* fra
 
 extern "C" int ipk_fs_destroy(ipk_fs* d) {
   if (!d) return IPK_OK;
+  ipk_graphs_drop(d);
   d->pool.release();
   d->ws.release();
   if (d->out_direct) out_conv_plan_destroy(d->out_direct);

@@ -50,6 +50,7 @@ struct McfPacked { float* Wc; float* W1x; int C, Cp, hid; int hcol; const float*
 
 }  // namespace ipk
 
+void ipk_graphs_drop(const void* handle);   // capi.cu
 using namespace ipk;
 
 struct ipk_flow {
@@ -587,6 +588,7 @@ extern "C" int ipk_flow_forward(ipk_flow* f, const float* x, const float* cond, 
 
 extern "C" int ipk_flow_destroy(ipk_flow* f) {
   if (!f) return IPK_OK;
+  ipk_graphs_drop(f);
   f->pool.release();
   f->ws.release();
   if (f->st2) cudaStreamDestroy(f->st2);
