@@ -186,6 +186,10 @@ int ipk_test_conv3x3(const float* in, const float* w, const float* bias, float* 
 /* ConvTranspose2d(3, stride 2, pad 1, output_pad 1), NHWC in[F,H,W,Cin], IOHW weights -> NHWC out[F,2H,2W,Cout] */
 int ipk_test_convT3x3(const float* in, const float* w, const float* bias, float* out, int32_t F, int32_t H, int32_t W,
                       int32_t Cin, int32_t Cout, int32_t precision, void* stream);
+/* Conv3d on the tcgen05 engine: NDHWC in[B,T,H,W,Cin], OIDHW w[Cout,Cin,kt,ky,kx] -> NDHWC out[B,To,Ho,Wo,Cout]; optional
+ * stats[B,Cout,2] (fp64 sum / sum of squares per sample and channel, the fused GroupNorm statistics).
+ * dims = {B,T,H,W,Cin,Cout, kt,ky,kx, st,sy,sx, pt,py,px}; precision IPK_PREC_FP32_SPLIT or IPK_PREC_BF16 */
+int ipk_test_conv3d(const float* in, const float* w, float* out, double* stats, const int32_t* dims, int32_t precision, void* stream);
 
 #ifdef __cplusplus
 }

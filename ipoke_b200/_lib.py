@@ -45,7 +45,7 @@ EXPORTS = [
     "ipk_fs_create", "ipk_fs_set_tensor", "ipk_fs_finalize", "ipk_fs_decode", "ipk_fs_gru_step", "ipk_fs_gen", "ipk_fs_destroy",
     "ipk_cenc_create", "ipk_cenc_set_tensor", "ipk_cenc_finalize", "ipk_cenc_forward", "ipk_cenc_destroy",
     "ipk_enc_create", "ipk_enc_set_tensor", "ipk_enc_finalize", "ipk_enc_forward", "ipk_enc_destroy",
-    "ipk_sample", "ipk_sample_host", "ipk_sample_host_u8", "ipk_frames_to_u8", "ipk_test_gemm", "ipk_test_conv3x3", "ipk_test_convT3x3",
+    "ipk_sample", "ipk_sample_host", "ipk_sample_host_u8", "ipk_frames_to_u8", "ipk_test_gemm", "ipk_test_conv3x3", "ipk_test_convT3x3", "ipk_test_conv3d",
 ]
 
 _lib = None
@@ -98,6 +98,7 @@ def lib():
     L.ipk_test_gemm.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
     L.ipk_test_conv3x3.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     L.ipk_test_convT3x3.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
+    L.ipk_test_conv3d.argtypes = [vp, vp, vp, vp, vp, i32, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name.startswith(("ipk_flow_", "ipk_fs_", "ipk_enc_", "ipk_cenc_", "ipk_sample", "ipk_frames_", "ipk_test_")):

@@ -4,6 +4,7 @@
 #include <map>
 #include <tuple>
 #include "conv.cuh"
+#include "conv3d_tc.cuh"
 #include "elementwise.cuh"
 
 namespace ipk {
@@ -332,4 +333,27 @@ extern "C" int ipk_test_conv3x3(const float* in, const float* w, const float* bi
 extern "C" int ipk_test_convT3x3(const float* in, const float* w, const float* bias, float* out, int32_t F, int32_t H, int32_t W,
                                  int32_t Cin, int32_t Cout, int32_t precision, void* stream) {
   return test_conv_impl(in, w, bias, out, F, H, W, Cin, Cout, precision, true, (cudaStream_t)stream);
+}
+
+// Conv3d on the tcgen05 engine (conv3d_tc.cu): NDHWC in[B,T,H,W,Cin] fp32, OIDHW w[Cout,Cin,kt,ky,kx] -> NDHWC out[B,To,Ho,Wo,Cout] and
+// the fused per-(sample, channel) statistics stats[B,Cout,2] (sum, sum of squares; fp64).  dims = {B,T,H,W,Cin,Cout, kt,ky,kx, st,sy,sx, pt,py,px}
+extern "C" int ipk_test_conv3d(const float* in, const float* w, float* out, double* stats, const int32_t* dims, int32_t precision, void* stream) {
+  IPK_TRY
+  cudaStream_t st = (cudaStream_t)stream;
+  IPK_CHECK(in && w && out && dims, IPK_ERR_INVALID, "ipk_test_conv3d: null argument");
+  IPK_CHECK(precision == IPK_PREC_FP32_SPLIT || precision == IPK_PREC_BF16, IPK_ERR_UNSUPPORTED, "ipk_test_conv3d: tensor-core precisions only");
+  const int B = dims[0], T = dims[1], H = dims[2], W = dims[3], Cin = dims[4], Cout = dims[5];
+  Conv3dShape sh{Cin, Cout, T, H, W, dims[6], dims[7], dims[8], dims[9], dims[10], dims[11], dims[12], dims[13], dims[14]};
+  IPK_CHECK(conv3d_tc_supported(sh), IPK_ERR_UNSUPPORTED, "ipk_test_conv3d: shape not supported by the tensor-core engine");
+  DevPool pool;
+  Tmp tmp;
+  ConvW cw = conv_alloc(pool, precision, dims[6] * dims[7] * dims[8], Cin, Cout, false);
+  conv3d_tc_pack(cw, w, Cout, Cin, st);
+  void* lo = nullptr;
+  void* hi = make_operand(tmp, in, (long long)B * T * H * W, Cin, precision, &lo, st);
+  if (stats) IPK_CUDA(cudaMemsetAsync(stats, 0, (size_t)B * Cout * 2 * sizeof(double), st));
+  conv3d_tc_run(cw, sh, hi, lo, B, out, stats, st);
+  IPK_CUDA(cudaStreamSynchronize(st));
+  pool.release();
+  IPK_CATCH
 }

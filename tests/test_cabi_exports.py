@@ -71,7 +71,7 @@ def test_struct_layout_matches_header():
     L = _lib()
     assert ctypes.sizeof(L.FlowConfig) == 4 * (4 + 32 + 5)
     assert ctypes.sizeof(L.FsConfig) == 4 * (4 + 8 + 4)
-    assert ctypes.sizeof(L.EncConfig) == 4 * (5 + 8 + 2)
+    assert ctypes.sizeof(L.EncConfig) == 4 * (5 + 8 + 3)
     assert ctypes.sizeof(L.CencConfig) == 4 * 6
     src = open(HEADER).read()
     assert "#define IPK_MAX_LEVELS 32" in src and "#define IPK_MAX_DEC 8" in src

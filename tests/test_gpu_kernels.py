@@ -58,3 +58,41 @@ def test_convT3x3(Fr, H, W, Cin, Cout, prec, name, tol):
     ref = F.conv_transpose2d(x.permute(0, 3, 1, 2).double(), w.double(), b.double(), stride=2, padding=1, output_padding=1).permute(0, 2, 3, 1)
     err = (out.double() - ref).abs().max().item()
     assert err < tol * max(1.0, ref.abs().max().item()), f"{name} convT: max err {err}"
+
+
+# (B, T, H, W, Cin, Cout, kernel, stride, pad): the encoder's layer shapes plus ragged batches (B not a multiple of the batch box),
+# odd T, temporal stride without padding (downsample 1x1x1), and single-time-step volumes where 2/3 of the taps are skipped
+CONV3D = [
+    (2, 6, 32, 32, 64, 128, (3, 3, 3), (2, 1, 1), (1, 1, 1)),
+    (3, 3, 32, 32, 128, 128, (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    (2, 3, 32, 32, 128, 256, (3, 3, 3), (2, 2, 2), (1, 1, 1)),
+    (3, 2, 16, 16, 256, 256, (3, 3, 3), (2, 2, 2), (1, 1, 1)),
+    (5, 1, 8, 8, 256, 256, (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    (3, 5, 16, 16, 64, 64, (1, 1, 1), (2, 2, 2), (0, 0, 0)),
+    (1, 4, 128, 128, 64, 64, (3, 3, 3), (1, 2, 2), (1, 1, 1)),
+]
+
+
+@pytest.mark.parametrize("shape", CONV3D)
+@pytest.mark.parametrize("prec,name,tol", PRECS[1:])
+def test_conv3d_tc(shape, prec, name, tol):
+    """conv3d_tc_kernel (5-D TMA boxes with element strides, temporal-padding taps skipped, fused statistics) vs torch conv3d in fp64."""
+    L = _lib()
+    B, T, H, W, Cin, Cout, k, s, p = shape
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + T * 100 + Cin + Cout)
+    x = torch.randn(B, T, H, W, Cin, device="cuda", generator=g)
+    w = torch.randn(Cout, Cin, *k, device="cuda", generator=g) / (Cin * k[0] * k[1] * k[2]) ** 0.5
+    ref = F.conv3d(x.permute(0, 4, 1, 2, 3).double(), w.double(), None, stride=s, padding=p).permute(0, 2, 3, 4, 1).contiguous()
+    out = torch.full(ref.shape, float("nan"), device="cuda", dtype=torch.float32)
+    stats = torch.zeros((B, Cout, 2), device="cuda", dtype=torch.float64)
+    dims = (ctypes.c_int32 * 15)(B, T, H, W, Cin, Cout, *k, *s, *p)
+    L.check(L.lib().ipk_test_conv3d(x.data_ptr(), w.data_ptr(), out.data_ptr(), stats.data_ptr(), dims, prec, None), "ipk_test_conv3d")
+    scale = max(1.0, ref.abs().max().item())
+    err = (out.double() - ref).abs().max().item()
+    assert err < tol * scale, f"{name} conv3d {shape}: max err {err}"
+    # fused GroupNorm statistics = sums of the values the kernel wrote
+    s1 = out.double().sum(dim=(1, 2, 3))
+    s2 = (out.double() ** 2).sum(dim=(1, 2, 3))
+    n = ref[0, ..., 0].numel()
+    assert (stats[..., 0] - s1).abs().max().item() < 1e-4 * n ** 0.5 * scale
+    assert (stats[..., 1] - s2).abs().max().item() < 1e-4 * n * scale

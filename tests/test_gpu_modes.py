@@ -102,3 +102,27 @@ def test_sample_host_uint8_matches_float_path():
     u8 = s.sample_host(z, cond, x0, T, uint8=True)
     assert u8.dtype == torch.uint8 and tuple(u8.shape) == (B, T, S, S, 3)
     assert np.array_equal(u8.numpy(), _ref_u8(f32))
+
+
+def test_training_step_forward_half_loss_parity():
+    """BASELINE configs[3] (h36m shapes: C0 = 64), forward half of the second-stage training step
+    (second_stage_video.py:345-350, loss.py:13-31): X -> enc_motion (no grad) -> flow forward + log-det -> FlowLoss.
+    Stated tolerance: loss relative error 1e-5 in fp32 mode; measured ~1e-6."""
+    import ipoke_b200 as ipk
+    B, T, S, c0 = 2, 10, 64, 64
+    s, enc, sds, cfgs = _build(c0, S, B, T)
+    g = torch.Generator().manual_seed(41)
+    X = torch.rand((B, T + 1, 3, S, S), generator=g) * 2 - 1
+    poke, _ = FO.synth_pokes(B, S, seed=8)
+    eps = torch.randn((B, c0, 8, 8), generator=g)
+    z_in, _ = ipk.encode_first_stage(enc, X.cuda(), eps=eps.cuda())
+    cond = s.make_cond(X[:, 0].cuda(), poke.cuda())
+    out, logdet = s.forward_density(z_in, cond)
+    loss = ipk.flow_nll(out, logdet).item()
+    with torch.no_grad():
+        z_ref, _, _ = O.encoder_forward(sds["enc"], cfgs["enc"], X.transpose(1, 2), eps)
+        out_ref, ld_ref = O.flow_forward(sds["flow"], cfgs["flow"], z_ref, _cond(sds, cfgs, X[:, 0], poke))
+        loss_ref = O.flow_nll(out_ref, ld_ref).item()
+    rel = abs(loss - loss_ref) / abs(loss_ref)
+    print(f"training forward half: loss {loss:.6f} vs {loss_ref:.6f} (rel {rel:.2e}), logdet max-abs {maxabs(logdet, ld_ref):.2e}")
+    assert rel < 1e-5
