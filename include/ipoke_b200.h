@@ -161,6 +161,24 @@ int ipk_cenc_finalize(ipk_cenc* e, void* stream);
 int ipk_cenc_forward(ipk_cenc* e, const float* x, float* out, float* mean, int32_t B, void* stream);
 int ipk_cenc_destroy(ipk_cenc* e);
 
+/* ---- second-stage training step of the flow (BASELINE configs[3]): forward_density + FlowLoss + backward
+ *      models/second_stage_video.py:345-350, models/modules/INN/loss.py:13-31; optimizer: second_stage_video.py:633-660 ----
+ * Tensors are registered by their checkpoint names with a gradient destination each (fp32 tensors; integer buffers pass NULL).
+ * ipk_flowtrain_step re-packs the weights from the current parameter values, runs the density direction keeping every op's input on a
+ * tape, writes loss = mean_B(0.5 sum z^2) - mean_B(logdet) to *loss_out (device) and OVERWRITES every gradient buffer with dloss/dparam.
+ * precision: IPK_PREC_FP32_SPLIT (tcgen05 bf16x3 contractions) or IPK_PREC_FP32_SIMT. */
+typedef struct ipk_flowtrain ipk_flowtrain;
+int ipk_flowtrain_create(const ipk_flow_config* cfg, ipk_flowtrain** out);
+int ipk_flowtrain_set_tensor(ipk_flowtrain* f, const char* name, const void* param, float* grad, int64_t numel, int dtype);
+int ipk_flowtrain_finalize(ipk_flowtrain* f, void* stream);
+int ipk_flowtrain_step(ipk_flowtrain* f, const float* x, const float* cond, float* loss_out, float* z_out, float* logdet_out,
+                       int32_t B, void* stream);
+int ipk_flowtrain_destroy(ipk_flowtrain* f);
+/* torch.optim.Adam (amsgrad when max_exp_avg_sq != NULL) in place on a contiguous fp32 shard; step counts from 1; the gradient is
+ * multiplied by grad_scale first (1 / world_size after a summing reduce-scatter). */
+int ipk_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq, int64_t n, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale, void* stream);
+
 /* ---- whole sampling step with DEVICE buffers: flow inverse -> GRU + decoder ---- */
 int ipk_sample(ipk_flow* f, ipk_fs* d, const float* z, const float* cond, const float* x0, float* frames,
                int32_t B, int32_t T, void* stream);

@@ -46,6 +46,7 @@ EXPORTS = [
     "ipk_cenc_create", "ipk_cenc_set_tensor", "ipk_cenc_finalize", "ipk_cenc_forward", "ipk_cenc_destroy",
     "ipk_enc_create", "ipk_enc_set_tensor", "ipk_enc_finalize", "ipk_enc_forward", "ipk_enc_destroy",
     "ipk_sample", "ipk_sample_host", "ipk_sample_host_u8", "ipk_frames_to_u8", "ipk_test_gemm", "ipk_test_conv3x3", "ipk_test_convT3x3", "ipk_test_conv3d",
+    "ipk_flowtrain_create", "ipk_flowtrain_set_tensor", "ipk_flowtrain_finalize", "ipk_flowtrain_step", "ipk_flowtrain_destroy", "ipk_adam_step",
 ]
 
 _lib = None
@@ -99,9 +100,16 @@ def lib():
     L.ipk_test_conv3x3.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     L.ipk_test_convT3x3.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     L.ipk_test_conv3d.argtypes = [vp, vp, vp, vp, vp, i32, vp]
+    f32 = ctypes.c_float
+    L.ipk_flowtrain_create.argtypes = [ctypes.POINTER(FlowConfig), ctypes.POINTER(vp)]
+    L.ipk_flowtrain_set_tensor.argtypes = [vp, cp, vp, vp, i64, ctypes.c_int]
+    L.ipk_flowtrain_finalize.argtypes = [vp, vp]
+    L.ipk_flowtrain_step.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp]
+    L.ipk_flowtrain_destroy.argtypes = [vp]
+    L.ipk_adam_step.argtypes = [vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
-        if name.startswith(("ipk_flow_", "ipk_fs_", "ipk_enc_", "ipk_cenc_", "ipk_sample", "ipk_frames_", "ipk_test_")):
+        if name.startswith(("ipk_flow_", "ipk_fs_", "ipk_enc_", "ipk_cenc_", "ipk_sample", "ipk_frames_", "ipk_test_", "ipk_flowtrain_", "ipk_adam_")):
             fn.restype = ctypes.c_int
     _lib = L
     return L

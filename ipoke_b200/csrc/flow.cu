@@ -13,6 +13,7 @@
 #include "conv.cuh"
 #include "elementwise.cuh"
 #include "flow_segment.cuh"
+#include "flow_plan.cuh"
 
 namespace ipk {
 
@@ -24,18 +25,6 @@ struct NiceLayer {
   int* d_iz = nullptr;
   int* d_ip = nullptr;
   float* bias3 = nullptr;  // [2*n_p]
-};
-
-enum LKind { L_ACTNORM, L_SHUFFLE, L_MCF, L_NICE };
-struct LogicalOp {
-  LKind kind;
-  int C;               // active channels of the level
-  std::string prefix;  // state-dict prefix
-  int order = 0;       // MCF order
-  int coff = 0, cnt = 0;  // actnorm range
-  bool fwd_idx = false;   // shuffle: use forward_shuffle_idx
-  int factor = 2; bool skip = false; bool up = true;  // NICE
-  int nice_id = -1;
 };
 
 struct Stage {          // one segment launch followed (optionally) by one NICE network
@@ -97,9 +86,7 @@ static const TensorRef& need(ipk_flow* f, const std::string& name, int64_t numel
   return it->second;
 }
 
-struct LevelInfo { int L, C, steps, prior_factor, prior_out, z1; };
-
-static std::vector<LevelInfo> levels_of(const ipk_flow_config& c) {
+std::vector<LevelInfo> levels_of(const ipk_flow_config& c) {
   // MultiScaleInternal.__init__ channel bookkeeping (macow2.py:825-871)
   std::vector<LevelInfo> v;
   int C = c.flow_in_channels, factor = c.factor, step = C / c.factor;
@@ -114,7 +101,7 @@ static std::vector<LevelInfo> levels_of(const ipk_flow_config& c) {
 }
 
 // channel index lists of NICE2d.split (macow2.py:301-317,364-377)
-static void nice_indices(int C, int factor, bool skip, bool up, std::vector<int>& iz, std::vector<int>& ip) {
+void nice_indices(int C, int factor, bool skip, bool up, std::vector<int>& iz, std::vector<int>& ip) {
   if (skip && (C % 2 == 1)) skip = false;
   int cout = C / factor, cin = C - cout;
   int z1c = up ? cin : cout;
@@ -255,9 +242,9 @@ static void unit_ops(std::vector<LogicalOp>& v, const std::string& p, int C, boo
   v.insert(v.end(), u.begin(), u.end());
 }
 
-static std::vector<LogicalOp> logical_program(ipk_flow* f, bool fwd) {
+std::vector<LogicalOp> logical_program(const ipk_flow_config& cfg, bool fwd) {
   std::vector<LogicalOp> prog;
-  auto lv = levels_of(f->cfg);
+  auto lv = levels_of(cfg);
   auto add_level = [&](const LevelInfo& li) {
     std::vector<LogicalOp> ops;  // forward order; reversed afterwards for the inverse
     const int C = li.C;
@@ -503,8 +490,8 @@ extern "C" int ipk_flow_finalize(ipk_flow* f, void* stream) {
   IPK_CHECK(!f->finalized, IPK_ERR_STATE, "flow already finalized");
   cudaStream_t st = (cudaStream_t)stream;
   flow_segment_init();
-  auto pf = logical_program(f, true);
-  auto pi = logical_program(f, false);
+  auto pf = logical_program(f->cfg, true);
+  auto pi = logical_program(f->cfg, false);
   f->prog_fwd = compile_program(f, pf, st);
   f->prog_inv = compile_program(f, pi, st);
   // one GEMM for the conditioning terms of all MCFs (always error-compensated on the tensor-core engines: K = h_channels only)

@@ -1,0 +1,146 @@
+"""Second-stage training step of the flow on the native library (BASELINE configs[3]).
+
+Mirrors PokeMotionModel.training_step (models/second_stage_video.py:345-350, 596-631): `forward_density` -> FlowLoss
+(models/modules/INN/loss.py:13-31) -> backward -> Adam(amsgrad) (`configure_optimizers`, :633-660).  The reference runs this under
+PyTorch-Lightning DDP (bucketed gradient all-reduce, replicated optimizer state); here the flow's parameters live in ONE flat fp32
+buffer, the native step (`ipk_flowtrain_step`) writes the flat gradient, and the optimizer is sharded: one `reduce_scatter` of the
+flat gradient over NCCL, Adam on each rank's shard (`ipk_adam_step`), one `all_gather` of the parameters.
+"""
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .flow import SupervisedMacowTransformer
+
+
+class _NativeTrainPlan:
+    def __init__(self, handle):
+        self.handle = handle
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _lib.lib().ipk_flowtrain_destroy(self.handle)
+        except Exception:
+            pass
+        self.handle = None
+
+
+def shard_range(n, world, rank):
+    """Contiguous equal shards of a flat buffer padded to a multiple of `world`: returns (padded_n, lo, hi)."""
+    per = (n + world - 1) // world
+    return per * world, rank * per, (rank + 1) * per
+
+
+class FlowTrainer:
+    """flow: ipoke_b200.SupervisedMacowTransformer on a CUDA device.  After construction the module's parameters are views into
+    `self.flat_params`, so sampling through the same module sees every optimizer update."""
+
+    def __init__(self, flow: SupervisedMacowTransformer, max_batch=32, precision=None, group=None):
+        dev = next(flow.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("ipoke_b200 FlowTrainer runs on CUDA only (no CPU fallback)")
+        self.flow, self.device, self.group = flow, dev, group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self.precision = precision or flow.precision
+        self.max_batch = int(max_batch)
+        named = [(k, p) for k, p in flow.named_parameters() if p.dtype.is_floating_point]
+        self.names = [k for k, _ in named]
+        n = sum(p.numel() for _, p in named)
+        self.numel = n
+        self.padded, self.lo, self.hi = shard_range(n, self.world, self.rank)
+        self.flat_params = torch.zeros(self.padded, device=dev, dtype=torch.float32)
+        self.flat_grads = torch.zeros(self.padded, device=dev, dtype=torch.float32)
+        self.offsets, off = {}, 0
+        for k, p in named:
+            view = self.flat_params[off:off + p.numel()].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+            self.offsets[k] = (off, p.numel(), tuple(p.shape))
+            off += p.numel()
+        flow.invalidate()
+        self.exp_avg = torch.zeros(self.hi - self.lo, device=dev, dtype=torch.float32)
+        self.exp_avg_sq = torch.zeros_like(self.exp_avg)
+        self.max_exp_avg_sq = torch.zeros_like(self.exp_avg)
+        self.shard_grad = torch.zeros_like(self.exp_avg) if self.world > 1 else None
+        self.steps = 0
+        self._plan = None
+
+    def grad(self, name):
+        off, n, shape = self.offsets[name]
+        return self.flat_grads[off:off + n].view(shape)
+
+    def _ensure_plan(self):
+        if self._plan is not None:
+            return self._plan
+        L, cfg = _lib.lib(), self.flow._cfg
+        c = _lib.FlowConfig()
+        c.flow_in_channels, c.flow_mid_channels, c.h_channels = cfg["flow_in_channels"], cfg["flow_mid_channels"], cfg["h_channels"]
+        c.n_levels = len(cfg["num_steps"])
+        for i, s in enumerate(cfg["num_steps"]):
+            c.num_steps[i] = s
+        c.factor = cfg["factor"]
+        c.kernel_h, c.kernel_w = cfg["kernel_size"]
+        c.precision = _lib.precision_code(self.precision)
+        c.max_batch = self.max_batch
+        h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(L.ipk_flowtrain_create(ctypes.byref(c), ctypes.byref(h)), "ipk_flowtrain_create")
+            plan = _NativeTrainPlan(h)
+            self._keep = []
+            for k, v in self.flow.state_dict().items():
+                if k.endswith("initialized"):
+                    if int(v) == 0:
+                        raise RuntimeError(f"ipoke_b200 FlowTrainer: '{k}' is 0 -- run the data-dependent init of the reference first or load an "
+                                           "initialised checkpoint (macow2.py:503-505, macow_utils.py:248-250)")
+                    continue
+                if k in self.offsets:
+                    off, n, _ = self.offsets[k]
+                    pp, gp = self.flat_params[off:off + n], self.flat_grads[off:off + n]
+                    _lib.check(L.ipk_flowtrain_set_tensor(h, k.encode(), ctypes.c_void_p(pp.data_ptr()), ctypes.c_void_p(gp.data_ptr()), n, _lib.DT_F32),
+                               f"ipk_flowtrain_set_tensor({k})")
+                else:
+                    t = v.detach().contiguous()
+                    self._keep.append(t)
+                    _lib.check(L.ipk_flowtrain_set_tensor(h, k.encode(), ctypes.c_void_p(t.data_ptr()), None, t.numel(), _lib.dtype_code(t)),
+                               f"ipk_flowtrain_set_tensor({k})")
+            _lib.check(L.ipk_flowtrain_finalize(h, _lib.current_stream_ptr()), "ipk_flowtrain_finalize")
+        self._plan = plan
+        return plan
+
+    def step(self, flow_input, cond, return_latent=False):
+        """forward_density + FlowLoss + backward: returns the loss (0-dim CUDA tensor); gradients land in `flat_grads`."""
+        x = flow_input.detach().float().contiguous()
+        c = cond.detach().float().contiguous()
+        B = x.shape[0]
+        if B > self.max_batch:
+            raise ValueError(f"batch {B} exceeds the trainer's max_batch {self.max_batch}")
+        plan = self._ensure_plan()
+        loss = torch.zeros((), device=self.device, dtype=torch.float32)
+        z = torch.empty_like(x) if return_latent else None
+        ld = torch.empty(B, device=self.device, dtype=torch.float32) if return_latent else None
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().ipk_flowtrain_step(plan.handle, x.data_ptr(), c.data_ptr(), loss.data_ptr(), z.data_ptr() if z is not None else None,
+                                                     ld.data_ptr() if ld is not None else None, B, _lib.current_stream_ptr()), "ipk_flowtrain_step")
+        return (loss, z, ld) if return_latent else loss
+
+    def optimizer_step(self, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, amsgrad=True):
+        """torch.optim.Adam semantics on the flat parameter buffer, sharded over the ranks of `group`."""
+        self.steps += 1
+        L = _lib.lib()
+        if self.world > 1:
+            dist.reduce_scatter_tensor(self.shard_grad, self.flat_grads, op=dist.ReduceOp.SUM, group=self.group)
+            g = self.shard_grad
+        else:
+            g = self.flat_grads
+        p = self.flat_params[self.lo:self.hi]
+        with torch.cuda.device(self.device):
+            _lib.check(L.ipk_adam_step(p.data_ptr(), g.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                                       self.max_exp_avg_sq.data_ptr() if amsgrad else None, p.numel(), float(lr), float(betas[0]), float(betas[1]),
+                                       float(eps), float(weight_decay), int(self.steps), 1.0 / self.world, _lib.current_stream_ptr()), "ipk_adam_step")
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.flat_params, p.contiguous(), group=self.group)
+        self.flow.invalidate()          # the inference plan re-packs from the updated parameters on its next use

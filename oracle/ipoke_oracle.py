@@ -461,6 +461,24 @@ def flow_nll(z: Tensor, logdet: Tensor) -> Tensor:
     return (0.5 * (z ** 2).flatten(1).sum(dim=1)).mean() - logdet.mean()
 
 
+def flow_trainable_keys(sd) -> List[str]:
+    """The parameters the second-stage optimizer updates (flow.parameters(), second_stage_video.py:633): every floating-point
+    tensor of the flow checkpoint; the uint8 `initialized` flags and int64 shuffle indices are buffers."""
+    return [k for k, v in sd.items() if v.is_floating_point()]
+
+
+def flow_loss_and_grads(sd, cfg, x: Tensor, cond: Tensor) -> Tuple[Tensor, Dict[str, Tensor]]:
+    """Second-stage training step without the optimizer (second_stage_video.py:345-350 forward_density, loss.py:13-31 FlowLoss,
+    then loss.backward()): loss = mean_B(0.5 * sum z^2) - mean_B(logdet) and its gradient w.r.t. every trainable flow tensor,
+    by autograd over the restated forward (the reference differentiates the same ops)."""
+    leaf = {k: (v.detach().clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    z, ld = flow_forward(leaf, cfg, x, cond)
+    loss = flow_nll(z, ld)
+    keys = flow_trainable_keys(sd)
+    grads = torch.autograd.grad(loss, [leaf[k] for k in keys], allow_unused=True)
+    return loss.detach(), {k: (g if g is not None else torch.zeros_like(sd[k])) for k, g in zip(keys, grads)}
+
+
 # ----------------------------------------------------------------------------------------------
 # first-stage decoder (ConvGRU + SPADE decoder)
 # ----------------------------------------------------------------------------------------------

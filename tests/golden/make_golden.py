@@ -143,6 +143,48 @@ def run_i3d_case(name, spec, out_dir):
           f"pre {(opa - pa).abs().max().item():.1e} fd {fd_ref:.4f} vs oracle {FO.fvd_from_activations(f1, f2):.4f}")
 
 
+GRAD_CASES = {
+    # name: (cfg kwargs, B, weight seed, input seed)   second-stage training step: loss + gradients
+    "flowgrad_tiny": (dict(flow_in_channels=16, flow_mid_channels=64, h_channels=16, num_steps=[2, 1, 1], factor=4), 3, 1, 11),
+    "flowgrad_c32_hd128": (dict(flow_in_channels=32, flow_mid_channels=128, h_channels=128, num_steps=[2, 1, 1] + [1] * 12), 4, 3, 13),
+    "flowgrad_c64_hd128": (dict(flow_in_channels=64, flow_mid_channels=128, h_channels=128, num_steps=[1] * 15), 2, 4, 14),
+}
+
+
+def run_grad_case(name, spec, out_dir):
+    """loss.backward() of the reference flow + FlowLoss on a seeded latent; all gradients are kept as (norm, 64 sampled entries)
+    per tensor plus a handful in full, and compared with the oracle's autograd in the same run."""
+    import importlib
+    kw, B, wseed, iseed = spec
+    cfg = O.flow_config(**kw)
+    sd = O.synth_flow_state_dict(cfg, seed=wseed)
+    x, cond, _ = O.synth_inputs(B, cfg["flow_in_channels"], cfg["h_channels"], 8, seed=iseed)
+    x = x * 0.8
+    m = ref_flow(cfg, sd)
+    ref_import.install()
+    FlowLoss = importlib.import_module("models.modules.INN.loss").FlowLoss
+    crit = FlowLoss(spatial_mean=False, logdet_weight=1.0)
+    out, logdet = m(x, cond, reverse=False)
+    loss, _ = crit(out, logdet)
+    loss.backward()
+    ref_grads = {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
+    loss_or, grads_or = O.flow_loss_and_grads(sd, cfg, x, cond)
+    keys = O.flow_trainable_keys(sd)
+    assert set(ref_grads) == set(keys), (set(keys) ^ set(ref_grads))
+    worst = max(((grads_or[k] - ref_grads[k]).abs().max().item() / (ref_grads[k].abs().max().item() + 1e-12)) for k in keys)
+    # compact summary: per tensor the L2 norm, the max-abs and NS sampled entries (flat index, value), stored as three arrays
+    NS = 16
+    gsel = torch.Generator().manual_seed(5)
+    norms = torch.tensor([ref_grads[k].double().norm().item() for k in keys], dtype=torch.float64)
+    maxabs = torch.tensor([ref_grads[k].abs().max().item() for k in keys], dtype=torch.float32)
+    idx = torch.stack([torch.randint(0, ref_grads[k].numel(), (NS,), generator=gsel) for k in keys])
+    val = torch.stack([ref_grads[k].flatten()[idx[i]] for i, k in enumerate(keys)])
+    fix = dict(kind="flowgrad", cfg_kwargs=kw, B=B, wseed=wseed, iseed=iseed, loss=loss.item(), keys=keys, norms=norms, maxabs=maxabs, idx=idx, val=val,
+               oracle_loss=loss_or.item(), oracle_vs_ref_worst_rel=worst, torch_version=torch.__version__)
+    torch.save(fix, os.path.join(out_dir, name + ".pt"))
+    print(f"{name}: loss {loss.item():.6f} oracle {loss_or.item():.6f}; {len(keys)} tensors, oracle-vs-ref worst relative grad error {worst:.2e}")
+
+
 def ref_flow(cfg, sd):
     Flow = ref_import.flow_cls()
     m = Flow(dict(cfg))
@@ -227,6 +269,9 @@ if __name__ == "__main__":
     for n, s in ENC_CASES.items():
         if a.only in (None, n):
             run_enc_case(n, s, HERE)
+    for n, s in GRAD_CASES.items():
+        if a.only in (None, n):
+            run_grad_case(n, s, HERE)
     for n, s in I3D_CASES.items():
         if a.only in (None, n):
             run_i3d_case(n, s, HERE)

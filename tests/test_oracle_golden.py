@@ -145,3 +145,21 @@ def test_synth_pokes_layout():
         ys, xs = torch.nonzero(nz, as_tuple=True)
         assert ys.float().mean().item() == centres[b, 0, 0].item() and xs.float().mean().item() == centres[b, 0, 1].item()
         assert 5 <= centres[b, 0, 0] < 59 and 5 <= centres[b, 0, 1] < 59
+
+
+@pytest.mark.parametrize("name", ["flowgrad_tiny", "flowgrad_c32_hd128"])
+def test_training_step_oracle_matches_reference_autograd(name):
+    """Second-stage training step (forward_density + FlowLoss + backward): the oracle's autograd over the restated forward vs
+    loss.backward() of the reference flow + FlowLoss (tests/golden/make_golden.py: run_grad_case)."""
+    fx = golden(name)
+    cfg = O.flow_config(**fx["cfg_kwargs"])
+    sd = O.synth_flow_state_dict(cfg, seed=fx["wseed"])
+    x, cond, _ = O.synth_inputs(fx["B"], cfg["flow_in_channels"], cfg["h_channels"], 8, seed=fx["iseed"])
+    loss, grads = O.flow_loss_and_grads(sd, cfg, x * 0.8, cond)
+    assert abs(loss.item() - fx["loss"]) < 1e-5 * abs(fx["loss"])
+    assert list(grads) == fx["keys"]
+    for i, k in enumerate(fx["keys"]):
+        g = grads[k]
+        scale = fx["maxabs"][i].item() + 1e-12
+        assert abs(g.double().norm().item() - fx["norms"][i].item()) < 1e-4 * fx["norms"][i].item() + 1e-9, k
+        assert (g.flatten()[fx["idx"][i]] - fx["val"][i]).abs().max().item() < 1e-4 * scale, k
