@@ -38,12 +38,12 @@ class FlowTrainer:
     """flow: ipoke_b200.SupervisedMacowTransformer on a CUDA device.  After construction the module's parameters are views into
     `self.flat_params`, so sampling through the same module sees every optimizer update."""
 
-    def __init__(self, flow: SupervisedMacowTransformer, max_batch=32, precision=None, group=None):
+    def __init__(self, flow: SupervisedMacowTransformer, max_batch=32, precision=None, group=None, distributed=True):
         dev = next(flow.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("ipoke_b200 FlowTrainer runs on CUDA only (no CPU fallback)")
         self.flow, self.device, self.group = flow, dev, group
-        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.world = dist.get_world_size(group) if (distributed and dist.is_available() and dist.is_initialized()) else 1
         self.rank = dist.get_rank(group) if self.world > 1 else 0
         self.precision = precision or flow.precision
         self.max_batch = int(max_batch)
