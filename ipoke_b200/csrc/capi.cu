@@ -126,8 +126,8 @@ bool graph_enabled() {
 }
 // runs body(stream) eagerly, or captures / replays it; body must only enqueue work on the stream it is given
 template <typename Body>
-void run_graphed(const GraphKey& key, cudaStream_t st, Body&& body) {
-  if (!graph_enabled()) { body(st); return; }
+void run_graphed(const GraphKey& key, cudaStream_t st, Body&& body, bool enabled) {
+  if (!enabled || Prof::enabled()) { body(st); return; }
   std::lock_guard<std::mutex> lk(g_graphs_mu);
   if (g_graphs.size() > 32 && !g_graphs.count(key)) {     // buffers keep changing: stop hoarding instantiated graphs
     for (auto& kv : g_graphs)
@@ -167,6 +167,12 @@ void run_graphed(const GraphKey& key, cudaStream_t st, Body&& body) {
 }
 }  // namespace
 
+namespace ipk {
+void run_graphed_step(const void* owner, int B, int kind, cudaStream_t st, const std::function<void(cudaStream_t)>& body, bool enabled) {
+  run_graphed(GraphKey{owner, nullptr, nullptr, nullptr, nullptr, nullptr, B, 0, kind}, st, body, enabled);
+}
+}  // namespace ipk
+
 // plans call this from their destroy entry points: a recycled handle must not replay a stale graph
 void ipk_graphs_drop(const void* handle) {
   std::lock_guard<std::mutex> lk(g_graphs_mu);
@@ -186,7 +192,7 @@ extern "C" int ipk_sample(ipk_flow* f, ipk_fs* d, const float* z, const float* c
     const float* motion = nullptr;   // flow state stays NHWC on device and feeds the GRU directly
     ipk_flow_reverse_nhwc(f, z, cond, &motion, B, st);
     ipk_fs_decode_nhwc(d, motion, x0, frames, B, T, st);
-  });
+  }, graph_enabled());
   IPK_CATCH
 }
 

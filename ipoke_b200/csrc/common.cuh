@@ -11,6 +11,7 @@
 #include <utility>
 #include <cstring>
 #include <cstdlib>
+#include <functional>
 
 #include "../../include/ipoke_b200.h"
 
@@ -183,6 +184,11 @@ struct DevPool {
     cur_cap = cur_off = total = 0;
   }
 };
+
+// CUDA-graph replay of a fixed launch sequence (capi.cu).  body(stream) must only enqueue work whose device pointers and shapes are
+// fully determined by (owner, B, kind).  The first call with a key runs eagerly (lazy one-time setup), the second is captured on an
+// internal stream and instantiated, later calls replay the graph into `st`.  enabled = false, or an active profiler, runs eagerly.
+void run_graphed_step(const void* owner, int B, int kind, cudaStream_t st, const std::function<void(cudaStream_t)>& body, bool enabled);
 
 #define IPK_TRY try {
 #define IPK_CATCH                                                                                \

@@ -360,7 +360,8 @@ struct ipk_flowtrain {
   // workspace (M = max_batch * 64 rows)
   float *tape = nullptr, *G = nullptr, *Gtmp = nullptr, *logdet = nullptr, *Ecache = nullptr;
   float *c1 = nullptr, *E = nullptr, *P = nullptr, *dP = nullptr, *a1 = nullptr, *a2 = nullptr, *da = nullptr, *col = nullptr, *dcol = nullptr, *stack = nullptr,
-        *wout = nullptr, *cond_nhwc = nullptr;
+        *wout = nullptr, *cond_nhwc = nullptr, *x_in = nullptr, *cond_in = nullptr, *loss_dev = nullptr, *z_dev = nullptr;
+  bool use_graph = true;
   void *opA = nullptr, *opA_lo = nullptr, *opB = nullptr, *opB_lo = nullptr, *opT = nullptr, *opT_lo = nullptr, *opW = nullptr, *opW_lo = nullptr;
   size_t opA_elems = 0, opT_elems = 0, opW_elems = 0;
   int ldc1 = 0, ldE = 0, ldP = 0, ldcol = 0, ldstack = 0, ldwout = 0;
@@ -662,6 +663,10 @@ extern "C" int ipk_flowtrain_create(const ipk_flow_config* cfg, ipk_flowtrain** 
   f->cfg = *cfg;
   f->C0 = cfg->flow_in_channels; f->Hd = cfg->flow_mid_channels; f->hch = cfg->h_channels; f->eng = cfg->precision;
   f->omode = cfg->precision == IPK_PREC_FP32_SIMT ? OUT_F32_NHWC : OUT_BF16_SPLIT;
+  {
+    const char* e = getenv("IPK_TRAIN_GRAPH");
+    f->use_graph = !(e && e[0] == '0');
+  }
   *out = f;
   IPK_CATCH
 }
@@ -762,7 +767,7 @@ extern "C" int ipk_flowtrain_finalize(ipk_flowtrain* f, void* stream) {
   f->opW_elems = std::max<size_t>(std::max<size_t>(Hd, f->ldE), f->ldcol) * M;
   auto rb = [](size_t b) { return (b + 255) / 256 * 256; };
   const size_t slot = M * f->C0;
-  size_t bytes = rb((f->ops.size() + 1) * slot * 4) + 2 * rb(slot * 4) + rb(f->cfg.max_batch * 4) + 2 * rb(M * hch * 4) + rb(M * f->ldc1 * 4) + rb(M * f->ldE * 4) +
+  size_t bytes = rb((f->ops.size() + 1) * slot * 4) + 4 * rb(slot * 4) + rb(f->cfg.max_batch * 4) + 3 * rb(M * hch * 4) + 4096 + rb(M * f->ldc1 * 4) + rb(M * f->ldE * 4) +
                  2 * rb(M * f->ldP * 4) + 3 * rb(M * Hd * 4) + 2 * rb(M * f->ldcol * 4) + rb(M * f->ldstack * 4) + rb(wout_rows * f->ldwout * 4) +
                  2 * rb(f->opA_elems * 4) + rb(f->opT_elems * 4) + rb(f->opW_elems * 4) + (1 << 16);
   f->ws.init(bytes);
@@ -770,6 +775,7 @@ extern "C" int ipk_flowtrain_finalize(ipk_flowtrain* f, void* stream) {
   f->G = f->ws.alloc<float>(slot); f->Gtmp = f->ws.alloc<float>(slot);
   f->logdet = f->ws.alloc<float>(f->cfg.max_batch);
   f->cond_nhwc = f->ws.alloc<float>(M * hch); f->Ecache = f->ws.alloc<float>(M * hch);
+  f->x_in = f->ws.alloc<float>(slot); f->cond_in = f->ws.alloc<float>(M * hch); f->z_dev = f->ws.alloc<float>(slot); f->loss_dev = f->ws.alloc<float>(64);
   f->c1 = f->ws.alloc<float>(M * f->ldc1); f->E = f->ws.alloc<float>(M * f->ldE);
   f->P = f->ws.alloc<float>(M * f->ldP); f->dP = f->ws.alloc<float>(M * f->ldP);
   f->a1 = f->ws.alloc<float>(M * Hd); f->a2 = f->ws.alloc<float>(M * Hd); f->da = f->ws.alloc<float>(M * Hd);
@@ -800,37 +806,48 @@ extern "C" int ipk_flowtrain_step(ipk_flowtrain* f, const float* x, const float*
   IPK_CHECK(f && f->finalized, IPK_ERR_STATE, "flow train: not finalized");
   IPK_CHECK(x && cond && loss_out, IPK_ERR_INVALID, "ipk_flowtrain_step: null buffer");
   IPK_CHECK(B > 0 && B <= f->cfg.max_batch, IPK_ERR_INVALID, "flow train: batch %d outside (0, %d]", B, f->cfg.max_batch);
-  cudaStream_t st = (cudaStream_t)stream;
+  cudaStream_t stream_ = (cudaStream_t)stream;
   const long long M = (long long)B * 64;
-  {
-    ProfScope ps("train.repack", st);
-    for (McfTrain& m : f->mcfs) repack_mcf(f, m, st);
-    for (NiceTrain& n : f->nices) repack_nice(f, n, st);
-  }
-  nchw_to_nhwc(x, f->tape, B, f->C0, 64, f->C0, st);
-  nchw_to_nhwc(cond, f->cond_nhwc, B, f->hch, 64, f->hch, st);
-  elu_kernel<<<gridn(M * f->hch), 256, 0, st>>>(f->cond_nhwc, f->Ecache, M * f->hch);
-  IPK_LAUNCH_CHECK();
-  IPK_CUDA(cudaMemsetAsync(f->logdet, 0, B * sizeof(float), st));
-  {
-    ProfScope ps("train.forward", st);
-    train_forward(f, B, st);
-  }
-  const float* zS = f->tape + f->ops.size() * ((size_t)f->cfg.max_batch * 64 * f->C0);
-  IPK_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
-  loss_kernel<<<64, 256, 0, st>>>(zS, f->G, M * f->C0, f->logdet, B, loss_out);
-  IPK_LAUNCH_CHECK();
-  if (z_out) nhwc_to_nchw(zS, z_out, B, f->C0, 64, f->C0, st);
-  if (logdet_out) IPK_CUDA(cudaMemcpyAsync(logdet_out, f->logdet, B * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  {
-    ProfScope ps("train.backward", st);
-    train_backward(f, B, st);
-  }
+  // inputs are staged into plan-owned buffers so that the step is a fixed launch sequence: ~30 000 small launches whose host-side
+  // cost dominates when issued one by one -> replayed as ONE CUDA graph from the third call on (IPK_TRAIN_GRAPH=0 disables)
+  IPK_CUDA(cudaMemcpyAsync(f->x_in, x, (size_t)B * f->C0 * 64 * sizeof(float), cudaMemcpyDeviceToDevice, stream_));
+  IPK_CUDA(cudaMemcpyAsync(f->cond_in, cond, (size_t)B * f->hch * 64 * sizeof(float), cudaMemcpyDeviceToDevice, stream_));
+  const size_t slot = (size_t)f->cfg.max_batch * 64 * f->C0;
+  const float* zS = f->tape + f->ops.size() * slot;
+  run_graphed_step(f, B, 1, stream_, [&](cudaStream_t st) {
+    {
+      ProfScope ps("train.repack", st);
+      for (McfTrain& m : f->mcfs) repack_mcf(f, m, st);
+      for (NiceTrain& n : f->nices) repack_nice(f, n, st);
+    }
+    nchw_to_nhwc(f->x_in, f->tape, B, f->C0, 64, f->C0, st);
+    nchw_to_nhwc(f->cond_in, f->cond_nhwc, B, f->hch, 64, f->hch, st);
+    elu_kernel<<<gridn(M * f->hch), 256, 0, st>>>(f->cond_nhwc, f->Ecache, M * f->hch);
+    IPK_LAUNCH_CHECK();
+    IPK_CUDA(cudaMemsetAsync(f->logdet, 0, B * sizeof(float), st));
+    {
+      ProfScope ps("train.forward", st);
+      train_forward(f, B, st);
+    }
+    IPK_CUDA(cudaMemsetAsync(f->loss_dev, 0, sizeof(float), st));
+    loss_kernel<<<64, 256, 0, st>>>(zS, f->G, M * f->C0, f->logdet, B, f->loss_dev);
+    IPK_LAUNCH_CHECK();
+    nhwc_to_nchw(zS, f->z_dev, B, f->C0, 64, f->C0, st);
+    {
+      ProfScope ps("train.backward", st);
+      train_backward(f, B, st);
+    }
+  }, f->use_graph);
+  IPK_CUDA(cudaMemcpyAsync(loss_out, f->loss_dev, sizeof(float), cudaMemcpyDeviceToDevice, stream_));
+  if (z_out) IPK_CUDA(cudaMemcpyAsync(z_out, f->z_dev, (size_t)B * f->C0 * 64 * sizeof(float), cudaMemcpyDeviceToDevice, stream_));
+  if (logdet_out) IPK_CUDA(cudaMemcpyAsync(logdet_out, f->logdet, B * sizeof(float), cudaMemcpyDeviceToDevice, stream_));
   IPK_CATCH
 }
 
+void ipk_graphs_drop(const void* handle);   // capi.cu
 extern "C" int ipk_flowtrain_destroy(ipk_flowtrain* f) {
   if (!f) return IPK_OK;
+  ipk_graphs_drop(f);
   f->pool.release();
   f->ws.release();
   delete f;

@@ -20,6 +20,7 @@ ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--small", action="store_true", help="Hd = 128 flow (plumbing check)")
 ap.add_argument("--check", action="store_true", help="compare the sharded update with a single-process update on the global batch (use with --small)")
 ap.add_argument("--precision", default="fp32")
+ap.add_argument("--ncu", action="store_true", help="one warm step, then one step between cudaProfilerStart/Stop (run under ncu --profile-from-start off)")
 a = ap.parse_args()
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
@@ -83,6 +84,13 @@ if a.check:
     print(f"rank {rank}: reduced-gradient shard vs single-process gradient: max rel err {dg:.3e}; max |dparam| {dp:.3e} (lr 1e-4); "
           f"parameters identical on all ranks: {same}; mean loss over ranks {lg.item():.6f} vs global-batch loss {loss2.item():.6f}", flush=True)
     assert dg < 1e-4 and dp <= 2.1e-4 and same and abs(lg.item() - loss2.item()) < 1e-4 * abs(loss2.item())
+elif a.ncu:
+    one_step(tr, X, cond, eps)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    one_step(tr, X, cond, eps)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
 else:
     for _ in range(2):
         loss = one_step(tr, X, cond, eps)

@@ -46,6 +46,12 @@ def test_training_step_matches_reference_autograd(name, precision, gtol):
           f"{worst:.2e} of max-abs ({worst_k}), worst norm error {worst_n:.2e}")
     assert rel < 1e-5
     assert worst < gtol and worst_n < gtol
+    # the step is replayed as a CUDA graph from its third call on: same loss, same gradients
+    g1 = tr.flat_grads.clone()
+    for _ in range(3):
+        loss3 = tr.step((x * 0.8).cuda(), cond.cuda())
+    assert abs(loss3.item() - loss.item()) < 1e-6 * abs(loss.item())
+    assert (tr.flat_grads - g1).abs().max().item() <= 1e-6 * g1.abs().max().item()
 
 
 def test_adam_matches_torch_and_loss_decreases():
