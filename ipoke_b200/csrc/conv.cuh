@@ -92,6 +92,11 @@ struct PackSrc {
 ConvW conv_alloc(DevPool& pool, int engine, int ntaps, int K, int N, bool with_bias);
 // dst[t][n_off + n][k] = src.w(n, k_src, ky, kx) * oscale[n] / gscale   for t in tap_src (tap_src[t] = ky*kw+kx)
 void conv_pack_into(ConvW& dst, int n_off, const PackSrc& src, const std::vector<int>& tap_src, cudaStream_t st);
+// the same as a job record (conv_pack_job_bytes() bytes, host memory) for conv_pack_run_jobs: many packings in ONE launch from a
+// device array of job records (training re-packs every layer of the flow every step)
+size_t conv_pack_job_bytes();
+void conv_pack_job(ConvW& dst, int n_off, const PackSrc& src, const std::vector<int>& tap_src, void* job_out);
+void conv_pack_run_jobs(const void* d_jobs, int njobs, cudaStream_t st);
 // dst.bias[n_off + i] = bias_src[i] + add
 void conv_pack_bias(ConvW& dst, int n_off, const float* bias_src, int n, float add, cudaStream_t st);
 

@@ -177,9 +177,9 @@ struct PackArgs {
   float* dst_f32; __nv_bfloat16* dst_hi; __nv_bfloat16* dst_lo;
 };
 
-__global__ void pack_kernel(const PackArgs a) {
+__device__ __forceinline__ void pack_elements(const PackArgs& a, long long first, long long step) {
   long long total = (long long)a.ntaps * a.N * a.K;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+  for (long long e = first; e < total; e += step) {
     int k = (int)(e % a.K);
     int n = (int)((e / a.K) % a.N);
     int t = (int)(e / ((long long)a.K * a.N));
@@ -198,6 +198,14 @@ __global__ void pack_kernel(const PackArgs a) {
       if (a.dst_lo) a.dst_lo[di] = __float2bfloat16_rn(v - __bfloat162float(hi));
     }
   }
+}
+__global__ void pack_kernel(const PackArgs a) {
+  pack_elements(a, blockIdx.x * (long long)blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
+}
+// many packing jobs in one launch (training re-packs every layer every step): blockIdx.y = job
+__global__ void pack_multi_kernel(const PackArgs* __restrict__ jobs) {
+  const PackArgs a = jobs[blockIdx.y];
+  pack_elements(a, blockIdx.x * (long long)blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
 }
 
 __global__ void pack_bias_kernel(float* dst, const float* src, int n, float add) {
@@ -223,6 +231,32 @@ ConvW conv_alloc(DevPool& pool, int engine, int ntaps, int K, int N, bool with_b
   }
   if (with_bias) w.bias = pool.alloc<float>(w.Npad, true);
   return w;
+}
+
+static PackArgs make_pack_args(ConvW& dst, int n_off, const PackSrc& src, const std::vector<int>& tap_src) {
+  IPK_CHECK((int)tap_src.size() == dst.ntaps && dst.ntaps <= MAX_TAPS, IPK_ERR_INVALID, "pack: tap count mismatch");
+  IPK_CHECK(n_off + src.N <= dst.Npad, IPK_ERR_INVALID, "pack: N overflow");
+  PackArgs a;
+  memset(&a, 0, sizeof(a));
+  a.w = src.w; a.N = src.N; a.Ksrc = src.Ksrc; a.kh = src.kh; a.kw = src.kw; a.transposed = src.transposed ? 1 : 0;
+  a.oscale = src.oscale; a.gscale = src.gscale; a.k_off = src.k_off; a.k_map = src.k_map;
+  a.ntaps = dst.ntaps;
+  for (int i = 0; i < dst.ntaps; ++i) a.tap_src[i] = tap_src[i];
+  a.K = dst.K; a.Kpad = dst.Kpad; a.Npad = dst.Npad; a.n_off = n_off;
+  a.dst_f32 = dst.w_f32; a.dst_hi = dst.w_hi; a.dst_lo = dst.w_lo;
+  return a;
+}
+size_t conv_pack_job_bytes() { return sizeof(PackArgs); }
+void conv_pack_job(ConvW& dst, int n_off, const PackSrc& src, const std::vector<int>& tap_src, void* job_out) {
+  const PackArgs a = make_pack_args(dst, n_off, src, tap_src);
+  memcpy(job_out, &a, sizeof(a));
+}
+void conv_pack_run_jobs(const void* d_jobs, int njobs, cudaStream_t st) {
+  for (int j0 = 0; j0 < njobs; j0 += 65535) {
+    const int nj = std::min(65535, njobs - j0);
+    pack_multi_kernel<<<dim3(48, nj), 256, 0, st>>>((const PackArgs*)d_jobs + j0);
+    IPK_LAUNCH_CHECK();
+  }
 }
 
 void conv_pack_into(ConvW& dst, int n_off, const PackSrc& src, const std::vector<int>& tap_src, cudaStream_t st) {

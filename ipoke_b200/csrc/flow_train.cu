@@ -247,6 +247,41 @@ __global__ void wn_apply_kernel(const float* __restrict__ v, const float* __rest
   __syncthreads();
   for (int k = threadIdx.x; k < row; k += blockDim.x) weff[(size_t)o * row + k] = v[(size_t)o * row + k] * scale;
 }
+struct WnJob { const float* v; const float* g; float* weff; int N, row; };
+// all weight-normed layers in one launch: blockIdx.y = job, blockIdx.x = output row
+__global__ void wn_apply_multi_kernel(const WnJob* __restrict__ jobs) {
+  const WnJob j = jobs[blockIdx.y];
+  const int o = blockIdx.x;
+  if (o >= j.N) return;
+  float s = 0.f;
+  for (int k = threadIdx.x; k < j.row; k += blockDim.x) { const float t = j.v[(size_t)o * j.row + k]; s = fmaf(t, t, s); }
+  __shared__ float r[32];
+  __shared__ float scale;
+#pragma unroll
+  for (int of = 16; of > 0; of >>= 1) s += __shfl_xor_sync(0xffffffffu, s, of);
+  if ((threadIdx.x & 31) == 0) r[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) a += r[i];
+    scale = j.g[o] / sqrtf(a);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < j.row; k += blockDim.x) j.weff[(size_t)o * j.row + k] = j.v[(size_t)o * j.row + k] * scale;
+}
+// P[m][j] = bias[j] + sum_s slices[s][m][j]   (split-K partial sums of a contraction)
+__global__ void sum_slices_kernel(const float* __restrict__ slices, long long slice_stride, int ns, const float* __restrict__ bias, float* __restrict__ P,
+                                  int ld, int N, long long M) {
+  const long long total = M * N;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(e % N);
+    const long long m = e / N;
+    float v = bias ? bias[j] : 0.f;
+    for (int s2 = 0; s2 < ns; ++s2) v += slices[s2 * slice_stride + m * ld + j];
+    P[m * ld + j] = v;
+  }
+}
+
 // dWeff element (o, k) lives at dW[o*so + (k / inner)*sk + (k % inner)*si]  ->  dg[o] = <dW, v>/||v||,  dv = g/||v|| (dW - v <dW,v>/||v||^2)
 __global__ void wn_bwd_kernel(const float* __restrict__ dW, long long so, long long sk, long long si, int inner, const float* __restrict__ v,
                               const float* __restrict__ g, float* __restrict__ dv, float* __restrict__ dg, int row) {
@@ -362,6 +397,9 @@ struct ipk_flowtrain {
   float *c1 = nullptr, *E = nullptr, *P = nullptr, *dP = nullptr, *a1 = nullptr, *a2 = nullptr, *da = nullptr, *col = nullptr, *dcol = nullptr, *stack = nullptr,
         *wout = nullptr, *cond_nhwc = nullptr, *x_in = nullptr, *cond_in = nullptr, *loss_dev = nullptr, *z_dev = nullptr;
   bool use_graph = true;
+  float* slices = nullptr;            // [9][M][ldP] split-K partial sums of the NICE conv3
+  void* d_pack_jobs = nullptr; int n_pack_jobs = 0;
+  WnJob* d_wn_jobs = nullptr; int n_wn_jobs = 0, wn_maxrows = 0;
   void *opA = nullptr, *opA_lo = nullptr, *opB = nullptr, *opB_lo = nullptr, *opT = nullptr, *opT_lo = nullptr, *opW = nullptr, *opW_lo = nullptr;
   size_t opA_elems = 0, opT_elems = 0, opW_elems = 0;
   int ldc1 = 0, ldE = 0, ldP = 0, ldcol = 0, ldstack = 0, ldwout = 0;
@@ -515,7 +553,15 @@ static void nice_net(ipk_flowtrain* f, const NiceTrain& n, const float* x, int B
   to_operand(f, f->a1, Hd, 0, M, Hd, Hd, f->opA, f->opA_lo, st);
   gemm(n.c2, f->opA, f->opA_lo, Hd, M, f->a2, Hd, nullptr, ACT_ELU, st);
   to_operand(f, f->a2, Hd, 0, M, Hd, Hd, f->opA, f->opA_lo, st);
-  conv8(n.c3, f->opA, f->opA_lo, Hd, B, taplist(taps3x3(), 1), f->P, f->ldP, n.c3.bias, st);
+  // conv3 (K = 9 * Hd, N <= 64): split-K over the taps so that 9x as many CTAs work on it, partial sums reduced with the bias
+  {
+    ConvIn in; in.p = f->opA; in.p_lo = f->opA_lo; in.cstride = Hd; in.F = B; in.H = 8; in.W = 8;
+    ConvOut o; o.p = f->slices; o.mode = OUT_F32_NHWC; o.cstride = f->ldP; o.Ho = 8; o.Wo = 8;
+    o.split_stride = (long long)f->cfg.max_batch * 64 * f->ldP;
+    const int ns = conv_run(n.c3, in, o, taplist(taps3x3(), 1), 9, st);
+    sum_slices_kernel<<<gridn(M * n.N3), 256, 0, st>>>(f->slices, o.split_stride, ns, n.c3.bias, f->P, f->ldP, n.N3, M);
+    IPK_LAUNCH_CHECK();
+  }
 }
 
 static void train_forward(ipk_flowtrain* f, int B, cudaStream_t st) {
@@ -751,6 +797,43 @@ extern "C" int ipk_flowtrain_finalize(ipk_flowtrain* f, void* stream) {
     }
     f->ops.push_back(t);
   }
+  // job tables of the per-step re-packing (all pointers are fixed from here on)
+  {
+    std::vector<WnJob> wn;
+    std::vector<char> jobs;
+    const size_t jb = conv_pack_job_bytes();
+    auto add = [&](ConvW& dst, const float* w, int N, int Ksrc, int ntaps, bool transposed) {
+      PackSrc s2; s2.w = w; s2.N = N; s2.Ksrc = Ksrc; s2.kh = ntaps; s2.kw = 1; s2.transposed = transposed;
+      jobs.resize(jobs.size() + jb);
+      conv_pack_job(dst, 0, s2, iota(ntaps), jobs.data() + jobs.size() - jb);
+    };
+    for (McfTrain& m : f->mcfs) {
+      const int kt = m.taps.n;
+      add(m.ws, m.v_ws, m.hid, m.C, kt, false);
+      add(m.wsT, m.v_ws, m.C, m.hid, kt, true);
+      add(m.w1, m.weff, m.C2, m.K1, 1, false);
+      add(m.w1T, m.weff, m.K1, m.C2, 1, true);
+      wn.push_back(WnJob{m.v1, m.g1, m.weff, m.C2, m.K1});
+      f->wn_maxrows = std::max(f->wn_maxrows, m.C2);
+    }
+    for (NiceTrain& n : f->nices) {
+      add(n.c1, n.w1, Hd, n.K1, 1, false);
+      add(n.c1T, n.w1, n.K1, Hd, 1, true);
+      add(n.c2, n.w2, Hd, Hd, 1, false);
+      add(n.c2T, n.w2, Hd, Hd, 1, true);
+      add(n.c3, n.weff3, n.N3, Hd, 9, false);
+      add(n.c3T, n.weff3, Hd, n.N3, 9, true);
+      wn.push_back(WnJob{n.v3, n.g3, n.weff3, n.N3, Hd * 9});
+      f->wn_maxrows = std::max(f->wn_maxrows, n.N3);
+    }
+    f->n_pack_jobs = (int)(jobs.size() / jb);
+    f->n_wn_jobs = (int)wn.size();
+    f->d_pack_jobs = f->pool.alloc<char>(std::max<size_t>(jobs.size(), 16));
+    f->d_wn_jobs = f->pool.alloc<WnJob>(std::max<size_t>(wn.size(), 1));
+    IPK_CUDA(cudaMemcpyAsync(f->d_pack_jobs, jobs.data(), jobs.size(), cudaMemcpyHostToDevice, st));
+    IPK_CUDA(cudaMemcpyAsync(f->d_wn_jobs, wn.data(), wn.size() * sizeof(WnJob), cudaMemcpyHostToDevice, st));
+    IPK_CUDA(cudaStreamSynchronize(st));
+  }
   // workspace
   const size_t M = (size_t)f->cfg.max_batch * 64;
   const int hidmax = 4 * Cmax, K1m = hidmax + hch;
@@ -768,7 +851,7 @@ extern "C" int ipk_flowtrain_finalize(ipk_flowtrain* f, void* stream) {
   auto rb = [](size_t b) { return (b + 255) / 256 * 256; };
   const size_t slot = M * f->C0;
   size_t bytes = rb((f->ops.size() + 1) * slot * 4) + 4 * rb(slot * 4) + rb(f->cfg.max_batch * 4) + 3 * rb(M * hch * 4) + 4096 + rb(M * f->ldc1 * 4) + rb(M * f->ldE * 4) +
-                 2 * rb(M * f->ldP * 4) + 3 * rb(M * Hd * 4) + 2 * rb(M * f->ldcol * 4) + rb(M * f->ldstack * 4) + rb(wout_rows * f->ldwout * 4) +
+                 2 * rb(M * f->ldP * 4) + 3 * rb(M * Hd * 4) + 2 * rb(M * f->ldcol * 4) + rb(M * f->ldstack * 4) + rb(wout_rows * f->ldwout * 4) + rb(9 * M * f->ldP * 4) +
                  2 * rb(f->opA_elems * 4) + rb(f->opT_elems * 4) + rb(f->opW_elems * 4) + (1 << 16);
   f->ws.init(bytes);
   f->tape = f->ws.alloc<float>((f->ops.size() + 1) * slot);
@@ -782,6 +865,7 @@ extern "C" int ipk_flowtrain_finalize(ipk_flowtrain* f, void* stream) {
   f->col = f->ws.alloc<float>(M * f->ldcol); f->dcol = f->ws.alloc<float>(M * f->ldcol);
   f->stack = f->ws.alloc<float>(M * f->ldstack);
   f->wout = f->ws.alloc<float>(wout_rows * f->ldwout);
+  f->slices = f->ws.alloc<float>(9 * M * f->ldP);
   // operand scratch: fp32 rows (SIMT) or two bf16 planes (tensor cores) share one allocation of 4 bytes per element
   auto planes = [&](size_t elems, void** hi, void** lo) {
     char* p = (char*)f->ws.alloc<float>(elems);
@@ -817,8 +901,12 @@ extern "C" int ipk_flowtrain_step(ipk_flowtrain* f, const float* x, const float*
   run_graphed_step(f, B, 1, stream_, [&](cudaStream_t st) {
     {
       ProfScope ps("train.repack", st);
-      for (McfTrain& m : f->mcfs) repack_mcf(f, m, st);
-      for (NiceTrain& n : f->nices) repack_nice(f, n, st);
+      // every layer of the flow in three launches: effective weight-normed weights, all packings, then the (tiny) bias copies
+      wn_apply_multi_kernel<<<dim3(f->wn_maxrows, f->n_wn_jobs), 128, 0, st>>>(f->d_wn_jobs);
+      IPK_LAUNCH_CHECK();
+      conv_pack_run_jobs(f->d_pack_jobs, f->n_pack_jobs, st);
+      for (McfTrain& m : f->mcfs) conv_pack_bias(m.w1, 0, m.b1, m.C2, 0.f, st);
+      for (NiceTrain& n : f->nices) conv_pack_bias(n.c3, 0, n.b3, n.N3, 0.f, st);
     }
     nchw_to_nhwc(f->x_in, f->tape, B, f->C0, 64, f->C0, st);
     nchw_to_nhwc(f->cond_in, f->cond_nhwc, B, f->hch, 64, f->hch, st);
