@@ -7,13 +7,17 @@
 // First cut of this row (parity first): in the density direction every op of the flow is a convolution or elementwise, so the
 // whole step is expressed as contractions on the shared engines (conv.cuh: tcgen05 bf16x3 in `fp32` mode, FFMA in `fp32_simt`)
 // plus small elementwise / gather kernels on global memory:
-//   * forward walks the logical op list, keeping the input state of every op on a tape ([M = B*64][C0] fp32 each);
-//   * backward walks it in reverse: each op recomputes its own network activations from the taped input, then
+//   * forward walks the logical op list, keeping the input state of every op on a tape ([M = B*64][C0] fp32 each) and each
+//     network's activations (MCF: pre-ELU hidden + params; coupling: im2col rows, both hidden activations, params; ~10 GB at
+//     B = 32, IPK_TRAIN_RECOMPUTE=1 recomputes them in the backward pass instead);
+//   * backward walks it in reverse:
 //       affine:   dx_t = dy s,  dmu = dy,  dls = (dy x_t - (1/B)/s) * s (2 - s) / 2        (s = 1 + tanh(ls/2), logdet = sum log s)
 //       dgrad:    the same engine with transposed (and tap-flipped) weight packings,
 //       wgrad:    dW[n][k] = sum_m dY[m][n] X[m][k] as a GEMM whose reduction runs over the M pixels (transposed operands),
 //       weight norm: (dv, dg) from dW_eff;  ActNorm / Shuffle / bias by direct reductions.
-//   Weights are re-packed from the master fp32 parameters at the start of every step (they change every optimizer step).
+//   Weights are re-packed from the master fp32 parameters at the start of every step (they change every optimizer step): one launch
+//   for all weight-norm scalings, one for all ~4 500 packings (job table built at finalize).  The step is a fixed sequence of ~30 000
+//   launches and is replayed as one CUDA graph from its third call on (IPK_TRAIN_GRAPH=0 disables).
 // The fused inference kernels (flow_segment.cu) are not used here; fusing this path is next-round work.
 #include <map>
 #include <string>
@@ -343,19 +347,36 @@ __global__ void loss_kernel(const float* __restrict__ S, float* __restrict__ G, 
   }
 }
 // Adam / AMSGrad (torch.optim.Adam semantics, second_stage_video.py:633-636): in place on a contiguous shard
+__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float* vmax, float lr, float b1, float b2, float eps, float wd, float bc1,
+                                         float bc2, float gscale) {
+  float gr = g * gscale;
+  if (wd != 0.f) gr = fmaf(wd, p, gr);
+  const float mm = b1 * m + (1.0f - b1) * gr;
+  const float vv = b2 * v + (1.0f - b2) * gr * gr;
+  m = mm;
+  v = vv;
+  float vh = vv;
+  if (vmax) { vh = fmaxf(*vmax, vv); *vmax = vh; }
+  p -= lr / bc1 * mm / (sqrtf(vh) / sqrtf(bc2) + eps);
+}
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, float* __restrict__ vmax,
                             long long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, float gscale) {
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
-    float gr = g[e] * gscale;
-    if (wd != 0.f) gr = fmaf(wd, p[e], gr);
-    const float mm = b1 * m[e] + (1.0f - b1) * gr;
-    const float vv = b2 * v[e] + (1.0f - b2) * gr * gr;
-    m[e] = mm;
-    v[e] = vv;
-    float vh = vv;
-    if (vmax) { vh = fmaxf(vmax[e], vv); vmax[e] = vh; }
-    p[e] -= lr / bc1 * mm / (sqrtf(vh) / sqrtf(bc2) + eps);
+  // HBM-bound (28 bytes per parameter with AMSGrad): 16-byte accesses when every buffer is 16-byte aligned, scalar tail
+  const bool vec = ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v | (uintptr_t)vmax) & 15) == 0);
+  const long long n4 = vec ? n / 4 : 0;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n4; e += (long long)gridDim.x * blockDim.x) {
+    float4 pp = ((float4*)p)[e], mm = ((float4*)m)[e], vv = ((float4*)v)[e];
+    const float4 gg = ((const float4*)g)[e];
+    float4 vm = vmax ? ((float4*)vmax)[e] : make_float4(0.f, 0.f, 0.f, 0.f);
+    adam_one(pp.x, gg.x, mm.x, vv.x, vmax ? &vm.x : nullptr, lr, b1, b2, eps, wd, bc1, bc2, gscale);
+    adam_one(pp.y, gg.y, mm.y, vv.y, vmax ? &vm.y : nullptr, lr, b1, b2, eps, wd, bc1, bc2, gscale);
+    adam_one(pp.z, gg.z, mm.z, vv.z, vmax ? &vm.z : nullptr, lr, b1, b2, eps, wd, bc1, bc2, gscale);
+    adam_one(pp.w, gg.w, mm.w, vv.w, vmax ? &vm.w : nullptr, lr, b1, b2, eps, wd, bc1, bc2, gscale);
+    ((float4*)p)[e] = pp; ((float4*)m)[e] = mm; ((float4*)v)[e] = vv;
+    if (vmax) ((float4*)vmax)[e] = vm;
   }
+  for (long long e = n4 * 4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+    adam_one(p[e], g[e], m[e], v[e], vmax ? vmax + e : nullptr, lr, b1, b2, eps, wd, bc1, bc2, gscale);
 }
 
 static inline int gridn(long long n) { return (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, 148LL * 16)); }
@@ -398,6 +419,10 @@ struct ipk_flowtrain {
         *wout = nullptr, *cond_nhwc = nullptr, *x_in = nullptr, *cond_in = nullptr, *loss_dev = nullptr, *z_dev = nullptr;
   bool use_graph = true;
   float* slices = nullptr;            // [9][M][ldP] split-K partial sums of the NICE conv3
+  // activations kept from the forward pass for the backward pass (IPK_TRAIN_RECOMPUTE=1 recomputes them instead, saving the memory):
+  // per MCF the pre-ELU hidden c1 and the params P; per coupling the im2col rows, both hidden activations and P
+  bool keep_acts = true;
+  std::vector<float*> sv_mc1, sv_mP, sv_ncol, sv_na1, sv_na2, sv_nP;
   void* d_pack_jobs = nullptr; int n_pack_jobs = 0;
   WnJob* d_wn_jobs = nullptr; int n_wn_jobs = 0, wn_maxrows = 0;
   void *opA = nullptr, *opA_lo = nullptr, *opB = nullptr, *opB_lo = nullptr, *opT = nullptr, *opT_lo = nullptr, *opW = nullptr, *opW_lo = nullptr;
@@ -498,38 +523,9 @@ static void wgrad(ipk_flowtrain* f, int N, const float* X, int ldx, int Kx, int 
   gemm(w, f->opT, f->opT_lo, M, N, out, ldo, nullptr, ACT_NONE, st);
 }
 
-// ---- (re)packing of one layer from the master parameters ----------------------------------------------------------------
-static void pack_plain(ConvW& dst, const float* w, int N, int Ksrc, int ntaps, bool transposed, const int* k_map, int k_off, cudaStream_t st) {
-  PackSrc s; s.w = w; s.N = N; s.Ksrc = Ksrc; s.kh = ntaps; s.kw = 1; s.transposed = transposed; s.k_map = k_map; s.k_off = k_off;
-  conv_pack_into(dst, 0, s, iota(ntaps), st);
-}
-
 }  // namespace ipk
 
 namespace ipk {
-
-static void repack_mcf(ipk_flowtrain* f, McfTrain& m, cudaStream_t st) {
-  const int kt = m.taps.n;
-  pack_plain(m.ws, m.v_ws, m.hid, m.C, kt, false, nullptr, 0, st);
-  pack_plain(m.wsT, m.v_ws, m.C, m.hid, kt, true, nullptr, 0, st);
-  wn_apply_kernel<<<m.C2, 128, 0, st>>>(m.v1, m.g1, m.weff, m.K1);
-  IPK_LAUNCH_CHECK();
-  pack_plain(m.w1, m.weff, m.C2, m.K1, 1, false, nullptr, 0, st);
-  conv_pack_bias(m.w1, 0, m.b1, m.C2, 0.f, st);
-  pack_plain(m.w1T, m.weff, m.K1, m.C2, 1, true, nullptr, 0, st);
-}
-static void repack_nice(ipk_flowtrain* f, NiceTrain& n, cudaStream_t st) {
-  const int Hd = f->Hd;
-  pack_plain(n.c1, n.w1, Hd, n.K1, 1, false, nullptr, 0, st);
-  pack_plain(n.c1T, n.w1, n.K1, Hd, 1, true, nullptr, 0, st);
-  pack_plain(n.c2, n.w2, Hd, Hd, 1, false, nullptr, 0, st);
-  pack_plain(n.c2T, n.w2, Hd, Hd, 1, true, nullptr, 0, st);
-  wn_apply_kernel<<<n.N3, 256, 0, st>>>(n.v3, n.g3, n.weff3, Hd * 9);
-  IPK_LAUNCH_CHECK();
-  pack_plain(n.c3, n.weff3, n.N3, Hd, 9, false, nullptr, 0, st);
-  conv_pack_bias(n.c3, 0, n.b3, n.N3, 0.f, st);
-  pack_plain(n.c3T, n.weff3, Hd, n.N3, 9, true, nullptr, 0, st);
-}
 
 // ---- network forward passes (also the recomputation inside backward) ------------------------------------------------------
 // MCFBlock on the taped input x [M][C0]: leaves c1 (pre-ELU hidden), E = [ELU(c1) | ELU(cond)] and P = params in the workspace
@@ -582,22 +578,36 @@ static void train_forward(ipk_flowtrain* f, int B, cudaStream_t st) {
       IPK_LAUNCH_CHECK();
     } else if (op.kind == L_MCF) {
       const McfTrain& m = f->mcfs[op.a];
+      float *c1s = f->c1, *Ps = f->P;
+      if (f->keep_acts) { f->c1 = f->sv_mc1[op.a]; f->P = f->sv_mP[op.a]; }
       mcf_net(f, m, x, B, st);
       affine_fwd_kernel<<<B, 256, 0, st>>>(y, f->C0, nullptr, m.C, f->P, f->ldP, f->logdet);
       IPK_LAUNCH_CHECK();
+      f->c1 = c1s; f->P = Ps;
     } else {
       const NiceTrain& n = f->nices[op.a];
+      float *cols = f->col, *a1s = f->a1, *a2s = f->a2, *Ps = f->P;
+      if (f->keep_acts) { f->col = f->sv_ncol[op.a]; f->a1 = f->sv_na1[op.a]; f->a2 = f->sv_na2[op.a]; f->P = f->sv_nP[op.a]; }
       nice_net(f, n, x, B, st);
       affine_fwd_kernel<<<B, 256, 0, st>>>(y, f->C0, n.d_ip, n.n_p, f->P, f->ldP, f->logdet);
       IPK_LAUNCH_CHECK();
+      f->col = cols; f->a1 = a1s; f->a2 = a2s; f->P = Ps;
     }
   }
 }
 
-static void mcf_backward(ipk_flowtrain* f, McfTrain& m, const float* x, int B, cudaStream_t st) {
+static void mcf_backward(ipk_flowtrain* f, McfTrain& m, int ai, const float* x, int B, cudaStream_t st) {
   const int M = B * 64;
   const float invB = 1.0f / (float)B;
-  mcf_net(f, m, x, B, st);                                                    // c1, E, P of this MCF
+  float *c1s = f->c1, *Ps = f->P;
+  struct Restore { ipk_flowtrain* f; float *c1, *P; ~Restore() { f->c1 = c1; f->P = P; } } restore{f, c1s, Ps};
+  if (f->keep_acts) {        // c1 and P come from the forward pass; only E = [ELU(c1) | ELU(cond)] is rebuilt
+    f->c1 = f->sv_mc1[ai]; f->P = f->sv_mP[ai];
+    elu_concat_kernel<<<gridn((long long)M * m.K1), 256, 0, st>>>(f->c1, f->ldc1, m.hid, f->Ecache, f->hch, f->E, f->ldE, M);
+    IPK_LAUNCH_CHECK();
+  } else {
+    mcf_net(f, m, x, B, st);                                                  // c1, E, P of this MCF
+  }
   affine_bwd_kernel<<<gridn((long long)M * m.C), 256, 0, st>>>(x, f->G, f->C0, nullptr, m.C, f->P, f->dP, f->ldP, invB, M);
   IPK_LAUNCH_CHECK();
   colsum_kernel<<<m.C2, 256, 0, st>>>(f->dP, f->ldP, M, m.g_b1);
@@ -633,10 +643,12 @@ static void mcf_backward(ipk_flowtrain* f, McfTrain& m, const float* x, int B, c
   }
 }
 
-static void nice_backward(ipk_flowtrain* f, NiceTrain& n, const float* x, int B, cudaStream_t st) {
+static void nice_backward(ipk_flowtrain* f, NiceTrain& n, int ai, const float* x, int B, cudaStream_t st) {
   const int M = B * 64, Hd = f->Hd;
   const float invB = 1.0f / (float)B;
-  nice_net(f, n, x, B, st);                                                   // col, a1, a2, P
+  struct Restore { ipk_flowtrain* f; float *col, *a1, *a2, *P; ~Restore() { f->col = col; f->a1 = a1; f->a2 = a2; f->P = P; } } restore{f, f->col, f->a1, f->a2, f->P};
+  if (f->keep_acts) { f->col = f->sv_ncol[ai]; f->a1 = f->sv_na1[ai]; f->a2 = f->sv_na2[ai]; f->P = f->sv_nP[ai]; }
+  else nice_net(f, n, x, B, st);                                              // col, a1, a2, P
   affine_bwd_kernel<<<gridn((long long)M * n.n_p), 256, 0, st>>>(x, f->G, f->C0, n.d_ip, n.n_p, f->P, f->dP, f->ldP, invB, M);
   IPK_LAUNCH_CHECK();
   colsum_kernel<<<n.N3, 256, 0, st>>>(f->dP, f->ldP, M, n.g_b3);
@@ -687,8 +699,8 @@ static void train_backward(ipk_flowtrain* f, int B, cudaStream_t st) {
         IPK_LAUNCH_CHECK();
         std::swap(f->G, f->Gtmp);
         break;
-      case L_MCF: mcf_backward(f, f->mcfs[op.a], x, B, st); break;
-      default: nice_backward(f, f->nices[op.a], x, B, st); break;
+      case L_MCF: mcf_backward(f, f->mcfs[op.a], op.a, x, B, st); break;
+      default: nice_backward(f, f->nices[op.a], op.a, x, B, st); break;
     }
   }
 }
@@ -712,6 +724,8 @@ extern "C" int ipk_flowtrain_create(const ipk_flow_config* cfg, ipk_flowtrain** 
   {
     const char* e = getenv("IPK_TRAIN_GRAPH");
     f->use_graph = !(e && e[0] == '0');
+    const char* r = getenv("IPK_TRAIN_RECOMPUTE");
+    f->keep_acts = !(r && r[0] == '1');
   }
   *out = f;
   IPK_CATCH
@@ -876,6 +890,13 @@ extern "C" int ipk_flowtrain_finalize(ipk_flowtrain* f, void* stream) {
   planes(f->opA_elems, &f->opB, &f->opB_lo);
   planes(f->opT_elems, &f->opT, &f->opT_lo);
   planes(f->opW_elems, &f->opW, &f->opW_lo);
+  if (f->keep_acts) {
+    for (size_t i = 0; i < f->mcfs.size(); ++i) { f->sv_mc1.push_back(f->pool.alloc<float>(M * f->ldc1)); f->sv_mP.push_back(f->pool.alloc<float>(M * f->ldP)); }
+    for (size_t i = 0; i < f->nices.size(); ++i) {
+      f->sv_ncol.push_back(f->pool.alloc<float>(M * f->ldcol)); f->sv_na1.push_back(f->pool.alloc<float>(M * Hd));
+      f->sv_na2.push_back(f->pool.alloc<float>(M * Hd)); f->sv_nP.push_back(f->pool.alloc<float>(M * f->ldP));
+    }
+  }
   IPK_CUDA(cudaMemsetAsync(f->ws.base, 0, f->ws.off, st));
   IPK_CUDA(cudaStreamSynchronize(st));
   f->finalized = true;
