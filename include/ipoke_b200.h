@@ -96,7 +96,7 @@ typedef struct ipk_enc_config {
 
 /* ConvEncoder(nf_in, nf_max, n_stages, variational=False) as wired by FirstStageWrapper (fully_conv_models.py:9-22). */
 typedef struct ipk_cenc_config {
-  int32_t nf_in;                      /* 2 (poke map) or 3 (image); 5 with poke_and_image is not supported yet */
+  int32_t nf_in;                      /* 2 (poke map), 3 (image) or 5 (poke map + image, embed_poke_and_image)   */
   int32_t nf_max;
   int32_t spatial;                    /* input H = W                                       */
   int32_t min_spatial_size;

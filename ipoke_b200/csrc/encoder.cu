@@ -191,6 +191,16 @@ __global__ void nchw_to_nhwc4_kernel(const float* __restrict__ in, float* __rest
   }
 }
 
+// x [B][C][P] (NCHW, C <= Cp) -> [B][P][Cp] (missing channels zero), Cp a multiple of 4
+__global__ void nchw_to_nhwc_pad_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int C, int Cp, long long P) {
+  const long long total = (long long)B * P * Cp;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(e % Cp);
+    const long long bp = e / Cp, b = bp / P, p = bp % P;
+    out[e] = c < C ? in[((size_t)b * C + c) * P + p] : 0.f;
+  }
+}
+
 // heads [B*64][2z] (mu | logvar) + eps [B][z][64] -> z, mu, logvar NCHW [B][z][64]     (reparameterize, motion_encoder.py:218-222)
 __global__ void reparam_kernel(const float* __restrict__ heads, const float* __restrict__ eps, float* __restrict__ zo, float* __restrict__ mu,
                                float* __restrict__ lv, int B, int z) {
@@ -633,7 +643,7 @@ static std::vector<int> cenc_widths(const ipk_cenc_config& c) {
 extern "C" int ipk_cenc_create(const ipk_cenc_config* cfg, ipk_cenc** out) {
   IPK_TRY
   IPK_CHECK(cfg && out, IPK_ERR_INVALID, "ipk_cenc_create: null argument");
-  IPK_CHECK(cfg->nf_in >= 1 && cfg->nf_in <= 4, IPK_ERR_UNSUPPORTED, "cond encoder: nf_in must be 1..4 (got %d)", cfg->nf_in);
+  IPK_CHECK(cfg->nf_in >= 1 && cfg->nf_in <= 8, IPK_ERR_UNSUPPORTED, "cond encoder: nf_in must be 1..8 (got %d)", cfg->nf_in);
   IPK_CHECK(cfg->nf_max % 16 == 0 && cfg->nf_max >= 32, IPK_ERR_UNSUPPORTED, "cond encoder: nf_max must be a multiple of 16 >= 32");
   IPK_CHECK(cfg->n_stages >= 1 && cfg->n_stages <= 8 && cfg->spatial == (cfg->min_spatial_size << cfg->n_stages), IPK_ERR_INVALID,
             "cond encoder: spatial %d != min_spatial_size %d << n_stages %d", cfg->spatial, cfg->min_spatial_size, cfg->n_stages);
@@ -679,7 +689,7 @@ extern "C" int ipk_cenc_finalize(ipk_cenc* e, void* stream) {
     e->blocks.push_back(r);
   }
   const size_t B = c.max_batch;
-  const size_t maxe = std::max<size_t>((size_t)c.spatial * c.spatial * 4, (size_t)(c.spatial / 2) * (c.spatial / 2) * std::max(w[0], c.nf_max));
+  const size_t maxe = std::max<size_t>((size_t)c.spatial * c.spatial * round_up(c.nf_in, 4), (size_t)(c.spatial / 2) * (c.spatial / 2) * std::max(w[0], c.nf_max));
   auto rb = [](size_t b) { return (b + 255) / 256 * 256; };
   e->ws.init(5 * rb(B * maxe * 4) + rb(B * 1024 * 2 * 8) + rb(B * 1024 * 2 * 4) + 65536);
   e->X4 = e->ws.alloc<float>(B * maxe);
@@ -704,10 +714,12 @@ extern "C" int ipk_cenc_forward(ipk_cenc* e, const float* x, float* out, float* 
   const int S = e->cfg.spatial;
   {
     const long long P = (long long)S * S;
-    nchw_to_nhwc4_kernel<<<(int)std::min<long long>(((long long)B * P + 255) / 256, 148 * 32), 256, 0, st>>>(x, e->X4, B, e->cfg.nf_in, P);
+    if (e->cfg.nf_in <= 4) nchw_to_nhwc4_kernel<<<(int)std::min<long long>(((long long)B * P + 255) / 256, 148 * 32), 256, 0, st>>>(x, e->X4, B, e->cfg.nf_in, P);
+    else   // poke map + start frame (embed_poke_and_image, second_stage_video.py:265-266): 5 channels, stored padded to 8
+      nchw_to_nhwc_pad_kernel<<<(int)std::min<long long>(((long long)B * P * 8 + 255) / 256, 148 * 32), 256, 0, st>>>(x, e->X4, B, e->cfg.nf_in, 8, P);
     IPK_LAUNCH_CHECK();
   }
-  Vol v{1, S, S, 4};
+  Vol v{1, S, S, round_up(e->cfg.nf_in, 4)};
   float* cur = e->bufA;
   v = run_cblock(e, e->stem, e->X4, v, e->bufB, cur, B, ACT_ELU, nullptr, st);
   for (size_t i = 0; i < e->blocks.size(); ++i) {

@@ -126,3 +126,55 @@ def test_training_step_forward_half_loss_parity():
     rel = abs(loss - loss_ref) / abs(loss_ref)
     print(f"training forward half: loss {loss:.6f} vs {loss_ref:.6f} (rel {rel:.2e}), logdet max-abs {maxabs(logdet, ld_ref):.2e}")
     assert rel < 1e-5
+
+
+def test_poke_and_image_embedder_five_channels():
+    """embed_poke_and_image (second_stage_video.py:265-266): the poke embedder sees cat[poke, X[:,0]] = 5 channels."""
+    import ipoke_b200 as ipk
+    cfg = O.cond_encoder_config(nf_in=5, spatial=64)
+    sd = O.synth_cond_encoder_state_dict(cfg, seed=12)
+    g = torch.Generator().manual_seed(2)
+    x0 = torch.rand((3, 3, 64, 64), generator=g) * 2 - 1
+    poke, _ = FO.synth_pokes(3, 64, seed=6)
+    inp = torch.cat([poke, x0], dim=1)
+    m = ipk.ConvEncoder(5, 64, cfg["n_stages"], ipk_max_batch=3)
+    m.load_state_dict(sd, strict=True)
+    out, mean, _ = m.cuda().eval()(inp.cuda())
+    with torch.no_grad():
+        ref_out, ref_mean = O.cond_encoder_forward(sd, cfg, inp)
+    assert maxabs(out, ref_out) < 1e-4 and maxabs(mean, ref_mean) < 1e-4
+
+
+def test_config1_plants64_full_size_sampling_pipeline():
+    """BASELINE configs[0]: plants_64 `--test samples` plumbing at full model size -- 10-frame 64x64, batch 2, C0 = 32, Hd = 2048
+    (1.05 B parameters), seed 42: poke + start frame -> conditioning encoders -> z ~ N(0, I) from the CPU generator -> flow inverse
+    -> ConvGRU + SPADE decoder, through PokeMotionSampler.forward_sample, against the CPU reference path (oracle)."""
+    import ipoke_b200 as ipk
+    B, T, S = 2, 10, 64
+    fcfg = O.flow_config(flow_in_channels=32, flow_mid_channels=2048, h_channels=128)
+    dcfg = O.first_stage_config(z_dim=32, spatial=S)
+    icfg, pcfg = O.cond_encoder_config(nf_in=3, spatial=S), O.cond_encoder_config(nf_in=2, spatial=S)
+    fsd, dsd = O.synth_flow_state_dict(fcfg, seed=0), O.synth_first_stage_state_dict(dcfg, seed=1)
+    isd, psd = O.synth_cond_encoder_state_dict(icfg, seed=2), O.synth_cond_encoder_state_dict(pcfg, seed=3)
+    fc = dict(fcfg); fc.update(ipk_precision="fp32", ipk_max_batch=B)
+    dc = dict(dcfg); dc.update(ipk_precision="fp32", ipk_max_batch=B, ipk_max_frames=T)
+    flow = ipk.SupervisedMacowTransformer(fc); flow.load_state_dict(fsd, strict=True)
+    fs = ipk.SpadeCondMotionDecoder(dc); fs.load_state_dict(dsd, strict=True)
+    img = ipk.ConvEncoder(3, 64, icfg["n_stages"], ipk_max_batch=B); img.load_state_dict(isd, strict=True)
+    pk = ipk.ConvEncoder(2, 64, pcfg["n_stages"], ipk_max_batch=B); pk.load_state_dict(psd, strict=True)
+    s = ipk.PokeMotionSampler(flow.cuda().eval(), fs.cuda().eval(), img.cuda().eval(), pk.cuda().eval())
+    g = torch.Generator().manual_seed(42)
+    X = torch.rand((B, T + 1, 3, S, S), generator=g) * 2 - 1
+    poke, _ = FO.synth_pokes(B, S, seed=42)
+    torch.manual_seed(42)
+    vids = s.forward_sample(X.cuda(), poke=poke.cuda(), n_samples=2, n_logged_vids=B)
+    torch.manual_seed(42)
+    with torch.no_grad():
+        cond = _cond(dict(img=isd, poke=psd), dict(img=icfg, poke=pcfg), X[:, 0], poke)
+        for v in vids:
+            z = torch.randn((B, 32, 8, 8))
+            ref = O.sample_videos(fsd, fcfg, dsd, dcfg, z, cond, X[:, 0], T)
+            assert tuple(v.shape) == (B, T, 3, S, S) and not v.is_cuda
+            e = maxabs(v, ref)
+            print(f"config 1 sample: per-frame max-abs vs CPU reference path {e:.2e}")
+            assert e < 1e-3
