@@ -224,13 +224,24 @@ def run_ours(a):
     z, cond, x0 = z_h.to(dev), cond_h.to(dev), x0_h.to(dev)
     gather_buf = [torch.empty((B, T, 3, S, S), device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
 
+    pending = []      # (NCCL work handle, frames tensor it reads) of the previous step's gather
+
+    def drain():
+        while pending:
+            w, _keep = pending.pop(0)
+            w.wait()
+
     def step():
         out = sampler.sample(z, cond, x0, T)
         if world > 1:
-            dist.gather(out, gather_buf, dst=0)      # the single collective on the data path
+            # the single collective on the data path.  It is issued asynchronously: the gather of step i runs on NCCL's stream while
+            # step i+1 computes (the frames of a step are a fresh tensor; the receive buffer is reused, so gathers stay in order)
+            drain()
+            pending.append((dist.gather(out, gather_buf, dst=0, async_op=True), out))
         return out
 
     def sync():
+        drain()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
