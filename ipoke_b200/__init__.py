@@ -10,4 +10,4 @@ from .parallel import shard_bounds, sharded_sample, global_noise  # noqa: F401
 from .sampler import PokeMotionSampler  # noqa: F401
 
 __version__ = "0.1.0"
-from .train import FlowTrainer, shard_range  # noqa: F401
+from .train import FlowTrainer, shard_range, sharded_update  # noqa: F401

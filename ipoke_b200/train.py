@@ -34,6 +34,27 @@ def shard_range(n, world, rank):
     return per * world, rank * per, (rank + 1) * per
 
 
+def sharded_update(flat_params, flat_grads, lo, hi, world, apply_fn, shard_grad=None, group=None):
+    """One data-parallel optimizer step on a flat parameter buffer (length a multiple of `world`): sum-reduce the flat gradient so that
+    each rank holds the sum of its shard [lo, hi), let `apply_fn(param_shard, grad_shard_sum)` update that shard in place (it scales
+    by 1 / world itself), then all-gather the shards so that every rank holds identical parameters.  NCCL: one reduce_scatter + one
+    all_gather; backends without reduce_scatter (gloo, the CPU tests) all-reduce and slice."""
+    if world == 1:
+        apply_fn(flat_params[lo:hi], flat_grads[lo:hi])
+        return
+    if dist.get_backend(group) == "nccl":
+        if shard_grad is None:
+            shard_grad = torch.empty(hi - lo, device=flat_grads.device, dtype=flat_grads.dtype)
+        dist.reduce_scatter_tensor(shard_grad, flat_grads, op=dist.ReduceOp.SUM, group=group)
+        g = shard_grad
+    else:
+        dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM, group=group)
+        g = flat_grads[lo:hi]
+    p = flat_params[lo:hi]
+    apply_fn(p, g)
+    dist.all_gather_into_tensor(flat_params, p.contiguous(), group=group)
+
+
 class FlowTrainer:
     """flow: ipoke_b200.SupervisedMacowTransformer on a CUDA device.  After construction the module's parameters are views into
     `self.flat_params`, so sampling through the same module sees every optimizer update."""
@@ -131,16 +152,12 @@ class FlowTrainer:
         """torch.optim.Adam semantics on the flat parameter buffer, sharded over the ranks of `group`."""
         self.steps += 1
         L = _lib.lib()
-        if self.world > 1:
-            dist.reduce_scatter_tensor(self.shard_grad, self.flat_grads, op=dist.ReduceOp.SUM, group=self.group)
-            g = self.shard_grad
-        else:
-            g = self.flat_grads
-        p = self.flat_params[self.lo:self.hi]
-        with torch.cuda.device(self.device):
-            _lib.check(L.ipk_adam_step(p.data_ptr(), g.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
-                                       self.max_exp_avg_sq.data_ptr() if amsgrad else None, p.numel(), float(lr), float(betas[0]), float(betas[1]),
-                                       float(eps), float(weight_decay), int(self.steps), 1.0 / self.world, _lib.current_stream_ptr()), "ipk_adam_step")
-        if self.world > 1:
-            dist.all_gather_into_tensor(self.flat_params, p.contiguous(), group=self.group)
+
+        def adam(p, g):
+            with torch.cuda.device(self.device):
+                _lib.check(L.ipk_adam_step(p.data_ptr(), g.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                                           self.max_exp_avg_sq.data_ptr() if amsgrad else None, p.numel(), float(lr), float(betas[0]), float(betas[1]),
+                                           float(eps), float(weight_decay), int(self.steps), 1.0 / self.world, _lib.current_stream_ptr()), "ipk_adam_step")
+
+        sharded_update(self.flat_params, self.flat_grads, self.lo, self.hi, self.world, adam, shard_grad=self.shard_grad, group=self.group)
         self.flow.invalidate()          # the inference plan re-packs from the updated parameters on its next use

@@ -79,3 +79,45 @@ def test_sharded_sample_gather_matches_single_process(world, B):
     x0 = torch.randn((B, 3, 4, 4), generator=g)
     ref = _fake_compute(z, cond, x0, 2)
     assert torch.equal(out, ref)
+
+
+# ---- training: the sharded optimizer step (reduce the flat gradient, update the local shard, all-gather the parameters) ----
+def _train_worker(rank, world, port, n, q):
+    from ipoke_b200.train import shard_range, sharded_update
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    padded, lo, hi = shard_range(n, world, rank)
+    g0 = torch.Generator().manual_seed(3)
+    params = torch.zeros(padded)
+    params[:n] = torch.randn(n, generator=g0)                              # identical on every rank
+    grads = torch.zeros(padded)
+    grads[:n] = torch.randn(n, generator=torch.Generator().manual_seed(100 + rank))      # per-rank gradient of the local batch
+
+    def sgd(p, g):                                                         # stand-in for ipk_adam_step: p -= lr * mean gradient
+        p -= 0.1 * g / world
+
+    sharded_update(params, grads, lo, hi, world, sgd)
+    q.put((rank, params[:n].clone()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 10), (2, 7), (3, 11)])
+def test_sharded_update_matches_single_process_mean_gradient(world, n):
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_train_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get() for _ in range(world))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    ref = torch.randn(n, generator=torch.Generator().manual_seed(3))
+    mean_g = sum(torch.randn(n, generator=torch.Generator().manual_seed(100 + r)) for r in range(world)) / world
+    ref = ref - 0.1 * mean_g
+    for r in range(world):
+        assert torch.allclose(got[r], ref, atol=1e-6), r                   # the global-batch update ...
+        assert torch.equal(got[r], got[0])                                 # ... and bit-identical parameters on every rank
