@@ -59,3 +59,25 @@ def fill_first_stage_(fs_module, seed=0):
             b.copy_(torch.nn.functional.normalize(torch.randn(b.shape, generator=gen, device=dev), dim=0, eps=1e-12))
     fs_module.invalidate()
     return fs_module
+
+
+@torch.no_grad()
+def fill_encoder_(enc_module, seed=0):
+    """3-D conv video encoder (motion_encoder.py:150-241): Conv3d kaiming-normal fan_out (:192-194), GroupNorm weight ~ 1 + 0.1 N(0,1),
+    bias ~ 0.05 N(0,1), 2-D heads nn.Conv2d default."""
+    dev = next(enc_module.parameters()).device
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    for name, p in enc_module.named_parameters():
+        if p.dim() == 5:
+            fan_out = p.shape[0] * p.shape[2] * p.shape[3] * p.shape[4]
+            p.copy_(torch.randn(p.shape, generator=gen, device=dev) * math.sqrt(2.0 / fan_out))
+        elif p.dim() == 4:
+            p.copy_((torch.rand(p.shape, generator=gen, device=dev) * 2 - 1) / math.sqrt(p.shape[1] * 9))
+        elif name.startswith(("conv_mu", "conv_var")):
+            p.copy_((torch.rand(p.shape, generator=gen, device=dev) * 2 - 1) / math.sqrt(256 * 9))
+        elif name.endswith("weight"):
+            p.copy_(1.0 + 0.1 * torch.randn(p.shape, generator=gen, device=dev))
+        else:
+            p.copy_(0.05 * torch.randn(p.shape, generator=gen, device=dev))
+    enc_module.invalidate()
+    return enc_module
