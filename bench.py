@@ -466,7 +466,7 @@ class TrainRun:
         with torch.device(dev):
             flow = ipk.SupervisedMacowTransformer(flow_cfg(C0, precision, batch))
         self.flow = synth.fill_flow_(flow.to(dev).eval(), seed=0)
-        ecfg = dict(z_dim=C0, img_size=128, max_frames=10, full_seq=True, ENC_M_channels=[64, 128, 256, 256], min_spatial_size=8,
+        ecfg = dict(z_dim=C0, img_size=128, max_frames=10, full_seq=True, ENC_M_channels=[64, 128, 256, 256, 256], min_spatial_size=8,
                     ipk_max_batch=batch, ipk_precision=precision)
         enc = ipk.ResNetMotionEncoder(ecfg)
         enc = synth.fill_encoder_(enc.to(dev).eval(), seed=1)
