@@ -104,6 +104,9 @@ typedef struct ipk_cenc_config {
   int32_t max_batch;
 } ipk_cenc_config;
 
+/* Devices: a plan belongs to the CUDA device that was current when it was created (its packed weights and workspaces live there);
+ * call every entry point of that plan with the same device current.  One process may hold plans on several devices: one-time setup
+ * (kernel attributes, SM counts, the staging buffers of ipk_sample_host, graph-capture streams) is kept per device ordinal. */
 typedef struct ipk_flow ipk_flow;
 typedef struct ipk_fs ipk_fs;
 typedef struct ipk_enc ipk_enc;
@@ -131,6 +134,12 @@ int ipk_flow_reverse(ipk_flow* f, const float* z, const float* cond, float* out,
 /* density direction: x -> z[B,C0,8,8], logdet[B] */
 int ipk_flow_forward(ipk_flow* f, const float* x, const float* cond, float* z, float* logdet, int32_t B, void* stream);
 int ipk_flow_destroy(ipk_flow* f);
+/* data-dependent initialisation of a freshly constructed flow (every `initialized` buffer 0): ActNorm2dFlow.init
+ * (models/modules/INN/macow2.py:503-505,526-539: per-channel mean / UNBIASED std of the ActNorm's input over (B,H,W), +1e-6) and
+ * Conv2dWeightNorm.init (models/modules/INN/macow_utils.py:231-250; zero_init=True at :281,:423 -> weight_g = 0, bias = 0).
+ * Call between ipk_flow_set_tensor and ipk_flow_finalize: the registered log_scale / bias / weight_g tensors are OVERWRITTEN in place
+ * (they are the caller's parameters); the caller then sets its `initialized` buffers to 1.  x[B,C0,8,8], B > 1. */
+int ipk_flow_data_init(ipk_flow* f, const float* x, int32_t B, void* stream);
 
 /* ---- first-stage decoder: latent ConvGRU + SPADE decoder ---- */
 int ipk_fs_create(const ipk_fs_config* cfg, ipk_fs** out);
@@ -173,11 +182,20 @@ int ipk_flowtrain_set_tensor(ipk_flowtrain* f, const char* name, const void* par
 int ipk_flowtrain_finalize(ipk_flowtrain* f, void* stream);
 int ipk_flowtrain_step(ipk_flowtrain* f, const float* x, const float* cond, float* loss_out, float* z_out, float* logdet_out,
                        int32_t B, void* stream);
+/* the same step split at the loss, for a caller that computes its own loss between the two halves (torch.autograd.Function around
+ * `out, logdet = self.flow(x, cond)` ... `loss.backward()`, models/second_stage_video.py:409-415):
+ *   forward : re-pack + density direction with the tape kept -> z[B,C0,8,8], logdet[B]
+ *   backward: upstream dz[B,C0,8,8], dlogdet[B] (NULL = zeros) -> every registered gradient buffer is OVERWRITTEN with dL/dparam;
+ *             dx_out (optional) receives dL/dx[B,C0,8,8].
+ *             Must follow a forward with the same B on the same plan. */
+int ipk_flowtrain_forward(ipk_flowtrain* f, const float* x, const float* cond, float* z_out, float* logdet_out, int32_t B, void* stream);
+int ipk_flowtrain_backward(ipk_flowtrain* f, const float* dz, const float* dlogdet, float* dx_out, int32_t B, void* stream);
 int ipk_flowtrain_destroy(ipk_flowtrain* f);
 /* torch.optim.Adam (amsgrad when max_exp_avg_sq != NULL) in place on a contiguous fp32 shard; step counts from 1; the gradient is
- * multiplied by grad_scale first (1 / world_size after a summing reduce-scatter). */
-int ipk_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq, int64_t n, float lr,
-                  float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale, void* stream);
+ * multiplied by grad_scale first (1 / world_size after a summing reduce-scatter).  Hyper-parameters are doubles: the bias corrections
+ * 1 - beta^step are evaluated in double precision like torch.optim.Adam does (models/second_stage_video.py:647-648 uses beta2 = 0.999). */
+int ipk_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq, int64_t n, double lr,
+                  double beta1, double beta2, double eps, double weight_decay, int32_t step, float grad_scale, void* stream);
 
 /* ---- whole sampling step with DEVICE buffers: flow inverse -> GRU + decoder ---- */
 int ipk_sample(ipk_flow* f, ipk_fs* d, const float* z, const float* cond, const float* x0, float* frames,

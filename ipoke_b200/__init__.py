@@ -5,9 +5,9 @@ from . import _lib  # noqa: F401
 from .cond_encoder import ConvEncoder, make_cond  # noqa: F401
 from .encoder import ResNetMotionEncoder, encode_first_stage  # noqa: F401
 from .first_stage import SpadeCondMotionDecoder, decode_first_stage  # noqa: F401
-from .flow import SupervisedMacowTransformer, flow_nll  # noqa: F401
+from .flow import SupervisedMacowTransformer, FlowLoss, flow_nll  # noqa: F401
 from .parallel import shard_bounds, sharded_sample, global_noise  # noqa: F401
 from .sampler import PokeMotionSampler  # noqa: F401
 
 __version__ = "0.1.0"
-from .train import FlowTrainer, shard_range, sharded_update  # noqa: F401
+from .train import FlowDensityFunction, FlowTrainer, shard_range, sharded_update  # noqa: F401

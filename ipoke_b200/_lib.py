@@ -41,12 +41,12 @@ class CencConfig(ctypes.Structure):
 
 EXPORTS = [
     "ipk_version", "ipk_last_error", "ipk_launch_count", "ipk_launch_count_reset", "ipk_prof_enable", "ipk_prof_report",
-    "ipk_flow_create", "ipk_flow_set_tensor", "ipk_flow_finalize", "ipk_flow_reverse", "ipk_flow_forward", "ipk_flow_destroy",
+    "ipk_flow_create", "ipk_flow_set_tensor", "ipk_flow_data_init", "ipk_flow_finalize", "ipk_flow_reverse", "ipk_flow_forward", "ipk_flow_destroy",
     "ipk_fs_create", "ipk_fs_set_tensor", "ipk_fs_finalize", "ipk_fs_decode", "ipk_fs_gru_step", "ipk_fs_gen", "ipk_fs_destroy",
     "ipk_cenc_create", "ipk_cenc_set_tensor", "ipk_cenc_finalize", "ipk_cenc_forward", "ipk_cenc_destroy",
     "ipk_enc_create", "ipk_enc_set_tensor", "ipk_enc_finalize", "ipk_enc_forward", "ipk_enc_destroy",
     "ipk_sample", "ipk_sample_host", "ipk_sample_host_u8", "ipk_frames_to_u8", "ipk_test_gemm", "ipk_test_conv3x3", "ipk_test_convT3x3", "ipk_test_conv3d",
-    "ipk_flowtrain_create", "ipk_flowtrain_set_tensor", "ipk_flowtrain_finalize", "ipk_flowtrain_step", "ipk_flowtrain_destroy", "ipk_adam_step",
+    "ipk_flowtrain_create", "ipk_flowtrain_set_tensor", "ipk_flowtrain_finalize", "ipk_flowtrain_step", "ipk_flowtrain_forward", "ipk_flowtrain_backward", "ipk_flowtrain_destroy", "ipk_adam_step",
 ]
 
 _lib = None
@@ -72,6 +72,7 @@ def lib():
     L.ipk_flow_create.argtypes = [ctypes.POINTER(FlowConfig), ctypes.POINTER(vp)]
     L.ipk_flow_set_tensor.argtypes = [vp, cp, vp, i64, ctypes.c_int]
     L.ipk_flow_finalize.argtypes = [vp, vp]
+    L.ipk_flow_data_init.argtypes = [vp, vp, i32, vp]
     L.ipk_flow_reverse.argtypes = [vp, vp, vp, vp, i32, vp]
     L.ipk_flow_forward.argtypes = [vp, vp, vp, vp, vp, i32, vp]
     L.ipk_flow_destroy.argtypes = [vp]
@@ -105,8 +106,11 @@ def lib():
     L.ipk_flowtrain_set_tensor.argtypes = [vp, cp, vp, vp, i64, ctypes.c_int]
     L.ipk_flowtrain_finalize.argtypes = [vp, vp]
     L.ipk_flowtrain_step.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp]
+    L.ipk_flowtrain_forward.argtypes = [vp, vp, vp, vp, vp, i32, vp]
+    L.ipk_flowtrain_backward.argtypes = [vp, vp, vp, vp, i32, vp]
     L.ipk_flowtrain_destroy.argtypes = [vp]
-    L.ipk_adam_step.argtypes = [vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, vp]
+    f64 = ctypes.c_double
+    L.ipk_adam_step.argtypes = [vp, vp, vp, vp, vp, i64, f64, f64, f64, f64, f64, i32, f32, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name.startswith(("ipk_flow_", "ipk_fs_", "ipk_enc_", "ipk_cenc_", "ipk_sample", "ipk_frames_", "ipk_test_", "ipk_flowtrain_", "ipk_adam_")):
@@ -167,3 +171,13 @@ def prof_report():
         tag, cnt, ms = line.split()
         out[tag] = (int(cnt), float(ms))
     return out
+
+
+def tensors_key(tensors):
+    """Cheap identity of a list of parameters / buffers for plan caching: the sum of their version counters (bumped by every in-place
+    update) and the xor of their storage addresses (a `.data` swap or a re-allocation does not bump the version)."""
+    ver = ptr = 0
+    for q in tensors:
+        ver += q._version
+        ptr ^= q.data_ptr()
+    return ver, ptr

@@ -64,8 +64,8 @@ class ConvEncoder(nn.Module):
             self.max_batch = int(batch)
             self.invalidate()
         if self._plist is None:
-            self._plist = list(self.parameters())
-        key = (device, self.max_batch, sum(q._version for q in self._plist))
+            self._plist = list(self.parameters()) + list(self.buffers())      # buffers: the spectral-norm u / v vectors
+        key = (device, self.max_batch) + _lib.tensors_key(self._plist)
         if self._plan is not None and self._plan_key == key:
             return self._plan
         if device.type != "cuda":

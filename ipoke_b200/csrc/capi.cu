@@ -115,7 +115,7 @@ struct GraphKey {
 struct GraphEntry { cudaGraphExec_t exec = nullptr; int64_t launches = 0; int seen = 0; bool failed = false; };
 std::map<GraphKey, GraphEntry> g_graphs;
 std::mutex g_graphs_mu;
-cudaStream_t g_cap_st = nullptr;
+cudaStream_t g_cap_sts[IPK_MAX_DEVICES] = {nullptr};     // capture stream per device
 bool graph_enabled() {
   static int on = -1;
   if (on < 0) {
@@ -141,6 +141,7 @@ void run_graphed(const GraphKey& key, cudaStream_t st, Body&& body, bool enabled
     return;
   }
   if (e.failed || e.seen++ == 0) { body(st); return; }
+  cudaStream_t& g_cap_st = g_cap_sts[current_device_slot()];
   if (!g_cap_st) IPK_CUDA(cudaStreamCreateWithFlags(&g_cap_st, cudaStreamNonBlocking));
   const int64_t before = g_launches;
   cudaGraph_t graph = nullptr;
@@ -208,7 +209,7 @@ struct HostStage {
     *cap = n;
   }
 };
-HostStage g_stage;
+HostStage g_stages[IPK_MAX_DEVICES];      // staging buffers / copy stream of ipk_sample_host, one set per device
 std::mutex g_stage_mu;
 }  // namespace
 
@@ -219,6 +220,7 @@ int ipk_fs_spatial(ipk_fs* d);
 static void sample_host_impl(ipk_flow* f, ipk_fs* d, const float* z_host, const float* cond_host, const float* x0_host,
                              float* frames_host, uint8_t* u8_host, int B, int T, cudaStream_t st) {
   std::lock_guard<std::mutex> lk(g_stage_mu);
+  HostStage& g_stage = g_stages[current_device_slot()];
   FlowDims fd = ipk_flow_dims(f);
   const int S = ipk_fs_spatial(d);
   const size_t nz = (size_t)B * fd.C0 * 64, nc = (size_t)B * fd.hch * 64, nx = (size_t)B * 3 * S * S, nf = (size_t)B * T * 3 * S * S;

@@ -113,6 +113,15 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bflo
   lo = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
 
+// ordinal of the calling thread's current device, folded into [0, 64): per-device one-time setup (function attributes, SM counts,
+// staging buffers) is keyed by it, so that one process may drive several GPUs through this library
+constexpr int IPK_MAX_DEVICES = 64;
+inline int current_device_slot() {
+  int d = 0;
+  IPK_CUDA(cudaGetDevice(&d));
+  return d & (IPK_MAX_DEVICES - 1);
+}
+
 inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 inline int64_t round_up64(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }

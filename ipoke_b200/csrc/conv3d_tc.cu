@@ -273,13 +273,14 @@ static CUtensorMap encode_map(const void* base, int rank, const cuuint64_t* gd, 
 }
 
 static int sm_count3() {
-  static int n = 0;
-  if (n == 0) {
+  static int n[IPK_MAX_DEVICES] = {0};
+  const int slot = current_device_slot();
+  if (n[slot] == 0) {
     int dev = 0;
     IPK_CUDA(cudaGetDevice(&dev));
-    IPK_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    IPK_CUDA(cudaDeviceGetAttribute(&n[slot], cudaDevAttrMultiProcessorCount, dev));
   }
-  return n;
+  return n[slot];
 }
 
 template <int BN, int NSPLIT>
@@ -287,11 +288,12 @@ static void launch_c3t(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const C
   constexpr int STAGE_BYTES = (NSPLIT == 3 ? 2 : 1) * (C3T_BM * C3T_BK * 2 + BN * C3T_BK * 2);
   a.stages = (int)std::min<size_t>(8, C3T_SMEM_BUDGET / STAGE_BYTES);
   const size_t smem = (size_t)a.stages * STAGE_BYTES + 1024 + C3T_EPI_WARPS * C3T_EPI_STAGE_BYTES;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[IPK_MAX_DEVICES] = {false};
+  const int slot = current_device_slot();
+  if (!attr_set[slot]) {
     IPK_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<BN, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(C3T_SMEM_BUDGET + 1024 + C3T_EPI_WARPS * C3T_EPI_STAGE_BYTES)));
-    attr_set = true;
+    attr_set[slot] = true;
   }
   const long long total = (long long)a.tiles_b * a.To * a.tiles_y * a.tiles_x * a.tiles_n;
   const unsigned grid = (unsigned)std::min<long long>(total, sm_count3());

@@ -487,13 +487,14 @@ static CUtensorMap make_map(const void* base, int rank, const long long* dims, c
 }
 
 static int sm_count() {
-  static int n = 0;
-  if (n == 0) {
+  static int n[IPK_MAX_DEVICES] = {0};
+  const int slot = current_device_slot();
+  if (n[slot] == 0) {
     int dev = 0;
     IPK_CUDA(cudaGetDevice(&dev));
-    IPK_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    IPK_CUDA(cudaDeviceGetAttribute(&n[slot], cudaDevAttrMultiProcessorCount, dev));
   }
-  return n;
+  return n[slot];
 }
 
 template <int BN, int NSPLIT, bool FUSED, bool HALO>
@@ -505,10 +506,11 @@ static void launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CU
   IPK_CHECK(stages >= 2, IPK_ERR_UNSUPPORTED, "conv_tc: pipeline needs at least two stages (stage %d bytes)", STAGE_BYTES);
   a.stages = stages;
   size_t smem = (size_t)stages * STAGE_BYTES + 1024 + TC_EPI_WARPS * TC_EPI_STAGE_BYTES;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[IPK_MAX_DEVICES] = {false};      // function attributes are per device
+  const int slot = current_device_slot();
+  if (!attr_set[slot]) {
     IPK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, NSPLIT, FUSED, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TC_SMEM_BUDGET + 1024 + TC_EPI_WARPS * TC_EPI_STAGE_BYTES)));
-    attr_set = true;
+    attr_set[slot] = true;
   }
   const long long total = (long long)a.tiles_m * a.tiles_n * (a.nsub > 1 ? a.nsub : a.nsplit);
   const unsigned grid = (unsigned)std::min<long long>(total, sm_count());     // persistent: one CTA per SM

@@ -484,6 +484,112 @@ extern "C" int ipk_flow_set_tensor(ipk_flow* f, const char* name, const void* de
   IPK_CATCH
 }
 
+// ---------------------------------------------------------------------------------- data-dependent initialisation
+// First forward of a freshly constructed flow (every `initialized` buffer 0): ActNorm2dFlow.init (macow2.py:503-505,526-539)
+// and Conv2dWeightNorm.init (macow_utils.py:231-250).  Both weight-normed convs of the flow are built with zero_init=True
+// (macow_utils.py:281,423), so their init is g <- init_scale / (std + 1e-6) = 0 and bias <- -mean * 0 = 0: every MCF and every
+// coupling is the identity during (and right after) the init pass, and the pass reduces to the ActNorms and Shuffles applied in
+// forward order, each ActNorm taking its statistics from the state that reaches it:
+//     out = x * exp(ls0) + b0;  mean, unbiased std over (B, H, W) per channel;  ls <- log(1 / (std + 1e-6));  b <- -mean / (std + 1e-6)
+// One CTA walks the whole op list on the [B*64][C0] state in global memory (one-off, ~600 ops on <= 1 MB of state).
+namespace ipk {
+struct InitOp { int kind, C, coff, cnt; float* ls; float* bias; const long long* idx; };
+
+__global__ void __launch_bounds__(1024, 1)
+flow_data_init_kernel(float* __restrict__ S, int C0, int M, const InitOp* __restrict__ ops, int nops) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int i = 0; i < nops; ++i) {
+    const InitOp op = ops[i];
+    if (op.kind == L_ACTNORM) {
+      for (int c = warp; c < op.cnt; c += nwarps) {
+        const float e0 = expf(op.ls[c]), b0 = op.bias[c];
+        double s = 0.0;
+        for (int m = lane; m < M; m += 32) s += (double)(S[(size_t)m * C0 + op.coff + c] * e0 + b0);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const double mean = s / (double)M;
+        double q = 0.0;
+        for (int m = lane; m < M; m += 32) {
+          const double d = (double)(S[(size_t)m * C0 + op.coff + c] * e0 + b0) - mean;
+          q += d * d;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        const float stdv = (float)sqrt(q / (double)(M > 1 ? M - 1 : 1));     // torch.std: unbiased
+        const float inv = 1.0f / (stdv + 1e-6f);
+        const float ls = logf(inv), b = -(float)mean * inv;
+        const float e1 = expf(ls);
+        for (int m = lane; m < M; m += 32) {
+          const size_t o = (size_t)m * C0 + op.coff + c;
+          S[o] = S[o] * e1 + b;                                               // forward with the fresh parameters (macow2.py:511)
+        }
+        if (lane == 0) { op.ls[c] = ls; op.bias[c] = b; }
+      }
+    } else if (op.kind == L_SHUFFLE) {
+      float tmp[96];
+      for (int m = threadIdx.x; m < M; m += blockDim.x) {
+        float* row = S + (size_t)m * C0;
+        for (int c = 0; c < op.C; ++c) tmp[c] = row[c];
+        for (int c = 0; c < op.C; ++c) row[c] = tmp[(int)op.idx[c]];
+      }
+    }
+    __syncthreads();
+  }
+}
+}  // namespace ipk
+
+// Runs on a created, NOT yet finalized plan whose tensors were registered with ipk_flow_set_tensor: the registered ActNorm
+// log_scale / bias and weight-norm weight_g / bias tensors are OVERWRITTEN in place (they are the caller's parameters); the caller
+// then sets its `initialized` buffers to 1 and finalizes the plan.
+extern "C" int ipk_flow_data_init(ipk_flow* f, const float* x, int32_t B, void* stream) {
+  IPK_TRY
+  IPK_CHECK(f && x, IPK_ERR_INVALID, "ipk_flow_data_init: null argument");
+  IPK_CHECK(!f->finalized, IPK_ERR_STATE, "ipk_flow_data_init: call before ipk_flow_finalize");
+  IPK_CHECK(B > 1, IPK_ERR_INVALID, "ipk_flow_data_init: the unbiased standard deviation needs more than one sample");
+  IPK_CHECK(f->C0 <= 96, IPK_ERR_UNSUPPORTED, "ipk_flow_data_init: more than 96 channels");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int M = B * 64;
+  std::vector<InitOp> ops;
+  for (const LogicalOp& o : logical_program(f->cfg, true)) {
+    InitOp io;
+    memset(&io, 0, sizeof(io));
+    io.kind = o.kind; io.C = o.C;
+    if (o.kind == L_ACTNORM) {
+      io.coff = o.coff; io.cnt = o.cnt;
+      io.ls = (float*)const_cast<void*>(need(f, o.prefix + "log_scale", o.cnt, IPK_F32).p);
+      io.bias = (float*)const_cast<void*>(need(f, o.prefix + "bias", o.cnt, IPK_F32).p);
+      ops.push_back(io);
+    } else if (o.kind == L_SHUFFLE) {
+      io.idx = (const long long*)need(f, o.prefix + "forward_shuffle_idx", o.C, IPK_I64).p;
+      ops.push_back(io);
+    } else {
+      // zero_init weight-normed conv of this MCF / coupling: g <- 0, bias <- 0
+      const std::string p = o.prefix + (o.kind == L_MCF ? "net.conv1x1.conv." : "net.conv3.conv.");
+      int n2;
+      if (o.kind == L_MCF) n2 = 2 * o.C;
+      else {
+        std::vector<int> iz, ip;
+        nice_indices(o.C, o.factor, o.skip, o.up, iz, ip);
+        n2 = 2 * (int)ip.size();
+      }
+      IPK_CUDA(cudaMemsetAsync(const_cast<void*>(need(f, p + "weight_g", n2, IPK_F32).p), 0, n2 * sizeof(float), st));
+      IPK_CUDA(cudaMemsetAsync(const_cast<void*>(need(f, p + "bias", n2, IPK_F32).p), 0, n2 * sizeof(float), st));
+    }
+  }
+  float* S = nullptr;
+  InitOp* d_ops = nullptr;
+  IPK_CUDA(cudaMalloc((void**)&S, (size_t)M * f->C0 * sizeof(float)));
+  IPK_CUDA(cudaMalloc((void**)&d_ops, ops.size() * sizeof(InitOp)));
+  IPK_CUDA(cudaMemcpyAsync(d_ops, ops.data(), ops.size() * sizeof(InitOp), cudaMemcpyHostToDevice, st));
+  nchw_to_nhwc(x, S, B, f->C0, 64, f->C0, st);
+  flow_data_init_kernel<<<1, 1024, 0, st>>>(S, f->C0, M, d_ops, (int)ops.size());
+  IPK_LAUNCH_CHECK();
+  IPK_CUDA(cudaStreamSynchronize(st));
+  cudaFree(S);
+  cudaFree(d_ops);
+  IPK_CATCH
+}
+
 extern "C" int ipk_flow_finalize(ipk_flow* f, void* stream) {
   IPK_TRY
   IPK_CHECK(f, IPK_ERR_INVALID, "null flow");

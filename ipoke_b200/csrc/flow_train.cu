@@ -151,9 +151,10 @@ __global__ void affine_fwd_kernel(float* __restrict__ S, int ld, const int* __re
     logdet[b] += v;
   }
 }
-// backward of y_t = s x_t + mu with logdet = sum log s and dL/dlogdet = -invB:  G_t <- dy s;  dP = (dy | (dy x_t - invB / s) s (2 - s) / 2)
+// backward of y_t = s x_t + mu with logdet = sum log s and dL/dlogdet_b = dld[b] (-1/B for FlowLoss):
+//   G_t <- dy s;  dP = (dy | (dy x_t + dld_b / s) s (2 - s) / 2)
 __global__ void affine_bwd_kernel(const float* __restrict__ X, float* __restrict__ G, int ld, const int* __restrict__ idx, int nt,
-                                  const float* __restrict__ P, float* __restrict__ dP, int ldp, float invB, long long M) {
+                                  const float* __restrict__ P, float* __restrict__ dP, int ldp, const float* __restrict__ dld, long long M) {
   const long long total = M * nt;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int j = (int)(e % nt);
@@ -163,7 +164,7 @@ __global__ void affine_bwd_kernel(const float* __restrict__ X, float* __restrict
     const float dy = G[m * ld + ch], x = X[m * ld + ch];
     G[m * ld + ch] = dy * sc;
     dP[m * ldp + j] = dy;
-    dP[m * ldp + nt + j] = (dy * x - invB / sc) * 0.5f * sc * (2.0f - sc);
+    dP[m * ldp + nt + j] = (dy * x + dld[m >> 6] / sc) * 0.5f * sc * (2.0f - sc);
   }
 }
 // ActNorm2dFlow.forward (macow2.py:507-513): y = x exp(ls) + b on channels [coff, coff + cnt); logdet += 64 sum ls
@@ -181,12 +182,13 @@ __global__ void actnorm_fwd_kernel(float* __restrict__ S, int ld, int coff, int 
     for (int b = threadIdx.x; b < B; b += blockDim.x) logdet[b] += 64.0f * tot;
   }
 }
-// one block per channel: dls = sum_m dy x exp(ls) - 64, db = sum_m dy, G <- dy exp(ls)
+// one block per channel: dls = sum_m dy x exp(ls) + 64 sum_b dld_b (= -64 for FlowLoss), db = sum_m dy, G <- dy exp(ls)
 __global__ void actnorm_bwd_kernel(const float* __restrict__ X, float* __restrict__ G, int ld, int coff, const float* __restrict__ ls,
-                                   float* __restrict__ dls, float* __restrict__ dbias, long long M) {
+                                   float* __restrict__ dls, float* __restrict__ dbias, const float* __restrict__ dld, long long M) {
   const int c = blockIdx.x;
   const float e = expf(ls[c]);
   float s1 = 0.f, s2 = 0.f;
+  for (long long b = threadIdx.x; b < (M >> 6); b += blockDim.x) s1 += 64.0f * dld[b];
   for (long long m = threadIdx.x; m < M; m += blockDim.x) {
     const float dy = G[m * ld + coff + c];
     s1 += dy * X[m * ld + coff + c] * e;
@@ -201,7 +203,7 @@ __global__ void actnorm_bwd_kernel(const float* __restrict__ X, float* __restric
   if (threadIdx.x == 0) {
     float a = 0.f, b = 0.f;
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += r1[i]; b += r2[i]; }
-    dls[c] = a - 64.0f;
+    dls[c] = a;
     dbias[c] = b;
   }
 }
@@ -324,9 +326,12 @@ __global__ void relayout_kernel(const float* __restrict__ src, long long so, lon
     grad[e] = src[o * so + (k / inner) * sk + (k % inner) * si];
   }
 }
-// z = S: dz = z / B -> G;  loss += (0.5 sum z^2 - sum_b logdet_b) / B     (one block; *loss zeroed by the caller)
-__global__ void loss_kernel(const float* __restrict__ S, float* __restrict__ G, long long n, const float* __restrict__ logdet, int B, float* __restrict__ loss) {
+// z = S: dz = z / B -> G;  dL/dlogdet_b = -1/B -> dld;  loss += (0.5 sum z^2 - sum_b logdet_b) / B     (*loss zeroed by the caller)
+__global__ void loss_kernel(const float* __restrict__ S, float* __restrict__ G, long long n, const float* __restrict__ logdet, int B, float* __restrict__ loss,
+                            float* __restrict__ dld) {
   const float invB = 1.0f / (float)B;
+  if (blockIdx.x == 0)
+    for (int b = threadIdx.x; b < B; b += blockDim.x) dld[b] = -invB;
   double acc = 0.0;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
     const float z = S[e];
@@ -347,20 +352,21 @@ __global__ void loss_kernel(const float* __restrict__ S, float* __restrict__ G, 
   }
 }
 // Adam / AMSGrad (torch.optim.Adam semantics, second_stage_video.py:633-636): in place on a contiguous shard
-__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float* vmax, float lr, float b1, float b2, float eps, float wd, float bc1,
-                                         float bc2, float gscale) {
+// step = lr / (1 - beta1^t), omb1 = 1 - beta1, omb2 = 1 - beta2, bc2s = sqrt(1 - beta2^t)
+__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float* vmax, float step, float b1, float b2, float omb1, float omb2, float eps,
+                                         float wd, float bc2s, float gscale) {
   float gr = g * gscale;
   if (wd != 0.f) gr = fmaf(wd, p, gr);
-  const float mm = b1 * m + (1.0f - b1) * gr;
-  const float vv = b2 * v + (1.0f - b2) * gr * gr;
+  const float mm = m + (gr - m) * omb1;                  // exp_avg.lerp_(grad, 1 - beta1)
+  const float vv = fmaf(omb2 * gr, gr, b2 * v);          // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
   m = mm;
   v = vv;
   float vh = vv;
   if (vmax) { vh = fmaxf(*vmax, vv); *vmax = vh; }
-  p -= lr / bc1 * mm / (sqrtf(vh) / sqrtf(bc2) + eps);
+  p -= step * (mm / (sqrtf(vh) / bc2s + eps));
 }
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, float* __restrict__ vmax,
-                            long long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, float gscale) {
+                            long long n, float lr, float b1, float b2, float omb1, float omb2, float eps, float wd, float bc2, float gscale) {
   // HBM-bound (28 bytes per parameter with AMSGrad): 16-byte accesses when every buffer is 16-byte aligned, scalar tail
   const bool vec = ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v | (uintptr_t)vmax) & 15) == 0);
   const long long n4 = vec ? n / 4 : 0;
@@ -368,15 +374,15 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     float4 pp = ((float4*)p)[e], mm = ((float4*)m)[e], vv = ((float4*)v)[e];
     const float4 gg = ((const float4*)g)[e];
     float4 vm = vmax ? ((float4*)vmax)[e] : make_float4(0.f, 0.f, 0.f, 0.f);
-    adam_one(pp.x, gg.x, mm.x, vv.x, vmax ? &vm.x : nullptr, lr, b1, b2, eps, wd, bc1, bc2, gscale);
-    adam_one(pp.y, gg.y, mm.y, vv.y, vmax ? &vm.y : nullptr, lr, b1, b2, eps, wd, bc1, bc2, gscale);
-    adam_one(pp.z, gg.z, mm.z, vv.z, vmax ? &vm.z : nullptr, lr, b1, b2, eps, wd, bc1, bc2, gscale);
-    adam_one(pp.w, gg.w, mm.w, vv.w, vmax ? &vm.w : nullptr, lr, b1, b2, eps, wd, bc1, bc2, gscale);
+    adam_one(pp.x, gg.x, mm.x, vv.x, vmax ? &vm.x : nullptr, lr, b1, b2, omb1, omb2, eps, wd, bc2, gscale);
+    adam_one(pp.y, gg.y, mm.y, vv.y, vmax ? &vm.y : nullptr, lr, b1, b2, omb1, omb2, eps, wd, bc2, gscale);
+    adam_one(pp.z, gg.z, mm.z, vv.z, vmax ? &vm.z : nullptr, lr, b1, b2, omb1, omb2, eps, wd, bc2, gscale);
+    adam_one(pp.w, gg.w, mm.w, vv.w, vmax ? &vm.w : nullptr, lr, b1, b2, omb1, omb2, eps, wd, bc2, gscale);
     ((float4*)p)[e] = pp; ((float4*)m)[e] = mm; ((float4*)v)[e] = vv;
     if (vmax) ((float4*)vmax)[e] = vm;
   }
   for (long long e = n4 * 4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
-    adam_one(p[e], g[e], m[e], v[e], vmax ? vmax + e : nullptr, lr, b1, b2, eps, wd, bc1, bc2, gscale);
+    adam_one(p[e], g[e], m[e], v[e], vmax ? vmax + e : nullptr, lr, b1, b2, omb1, omb2, eps, wd, bc2, gscale);
 }
 
 static inline int gridn(long long n) { return (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, 148LL * 16)); }
@@ -416,8 +422,9 @@ struct ipk_flowtrain {
   // workspace (M = max_batch * 64 rows)
   float *tape = nullptr, *G = nullptr, *Gtmp = nullptr, *logdet = nullptr, *Ecache = nullptr;
   float *c1 = nullptr, *E = nullptr, *P = nullptr, *dP = nullptr, *a1 = nullptr, *a2 = nullptr, *da = nullptr, *col = nullptr, *dcol = nullptr, *stack = nullptr,
-        *wout = nullptr, *cond_nhwc = nullptr, *x_in = nullptr, *cond_in = nullptr, *loss_dev = nullptr, *z_dev = nullptr;
+        *wout = nullptr, *cond_nhwc = nullptr, *x_in = nullptr, *cond_in = nullptr, *loss_dev = nullptr, *z_dev = nullptr, *dld = nullptr, *dz_in = nullptr;
   bool use_graph = true;
+  int fwd_batch = 0;                  // batch of the last ipk_flowtrain_forward whose tape is still valid
   float* slices = nullptr;            // [9][M][ldP] split-K partial sums of the NICE conv3
   // activations kept from the forward pass for the backward pass (IPK_TRAIN_RECOMPUTE=1 recomputes them instead, saving the memory):
   // per MCF the pre-ELU hidden c1 and the params P; per coupling the im2col rows, both hidden activations and P
@@ -598,7 +605,6 @@ static void train_forward(ipk_flowtrain* f, int B, cudaStream_t st) {
 
 static void mcf_backward(ipk_flowtrain* f, McfTrain& m, int ai, const float* x, int B, cudaStream_t st) {
   const int M = B * 64;
-  const float invB = 1.0f / (float)B;
   float *c1s = f->c1, *Ps = f->P;
   struct Restore { ipk_flowtrain* f; float *c1, *P; ~Restore() { f->c1 = c1; f->P = P; } } restore{f, c1s, Ps};
   if (f->keep_acts) {        // c1 and P come from the forward pass; only E = [ELU(c1) | ELU(cond)] is rebuilt
@@ -608,7 +614,7 @@ static void mcf_backward(ipk_flowtrain* f, McfTrain& m, int ai, const float* x, 
   } else {
     mcf_net(f, m, x, B, st);                                                  // c1, E, P of this MCF
   }
-  affine_bwd_kernel<<<gridn((long long)M * m.C), 256, 0, st>>>(x, f->G, f->C0, nullptr, m.C, f->P, f->dP, f->ldP, invB, M);
+  affine_bwd_kernel<<<gridn((long long)M * m.C), 256, 0, st>>>(x, f->G, f->C0, nullptr, m.C, f->P, f->dP, f->ldP, f->dld, M);
   IPK_LAUNCH_CHECK();
   colsum_kernel<<<m.C2, 256, 0, st>>>(f->dP, f->ldP, M, m.g_b1);
   IPK_LAUNCH_CHECK();
@@ -645,11 +651,10 @@ static void mcf_backward(ipk_flowtrain* f, McfTrain& m, int ai, const float* x, 
 
 static void nice_backward(ipk_flowtrain* f, NiceTrain& n, int ai, const float* x, int B, cudaStream_t st) {
   const int M = B * 64, Hd = f->Hd;
-  const float invB = 1.0f / (float)B;
   struct Restore { ipk_flowtrain* f; float *col, *a1, *a2, *P; ~Restore() { f->col = col; f->a1 = a1; f->a2 = a2; f->P = P; } } restore{f, f->col, f->a1, f->a2, f->P};
   if (f->keep_acts) { f->col = f->sv_ncol[ai]; f->a1 = f->sv_na1[ai]; f->a2 = f->sv_na2[ai]; f->P = f->sv_nP[ai]; }
   else nice_net(f, n, x, B, st);                                              // col, a1, a2, P
-  affine_bwd_kernel<<<gridn((long long)M * n.n_p), 256, 0, st>>>(x, f->G, f->C0, n.d_ip, n.n_p, f->P, f->dP, f->ldP, invB, M);
+  affine_bwd_kernel<<<gridn((long long)M * n.n_p), 256, 0, st>>>(x, f->G, f->C0, n.d_ip, n.n_p, f->P, f->dP, f->ldP, f->dld, M);
   IPK_LAUNCH_CHECK();
   colsum_kernel<<<n.N3, 256, 0, st>>>(f->dP, f->ldP, M, n.g_b3);
   IPK_LAUNCH_CHECK();
@@ -691,7 +696,7 @@ static void train_backward(ipk_flowtrain* f, int B, cudaStream_t st) {
     const float* x = f->tape + i * slot;
     switch (op.kind) {
       case L_ACTNORM:
-        actnorm_bwd_kernel<<<op.cnt, 256, 0, st>>>(x, f->G, f->C0, op.coff, op.ls, op.g_ls, op.g_bias, M);
+        actnorm_bwd_kernel<<<op.cnt, 256, 0, st>>>(x, f->G, f->C0, op.coff, op.ls, op.g_ls, op.g_bias, f->dld, M);
         IPK_LAUNCH_CHECK();
         break;
       case L_SHUFFLE:
@@ -864,13 +869,14 @@ extern "C" int ipk_flowtrain_finalize(ipk_flowtrain* f, void* stream) {
   f->opW_elems = std::max<size_t>(std::max<size_t>(Hd, f->ldE), f->ldcol) * M;
   auto rb = [](size_t b) { return (b + 255) / 256 * 256; };
   const size_t slot = M * f->C0;
-  size_t bytes = rb((f->ops.size() + 1) * slot * 4) + 4 * rb(slot * 4) + rb(f->cfg.max_batch * 4) + 3 * rb(M * hch * 4) + 4096 + rb(M * f->ldc1 * 4) + rb(M * f->ldE * 4) +
+  size_t bytes = rb((f->ops.size() + 1) * slot * 4) + 5 * rb(slot * 4) + rb(f->cfg.max_batch * 4) + rb(f->cfg.max_batch * 4) + 3 * rb(M * hch * 4) + 4096 + rb(M * f->ldc1 * 4) + rb(M * f->ldE * 4) +
                  2 * rb(M * f->ldP * 4) + 3 * rb(M * Hd * 4) + 2 * rb(M * f->ldcol * 4) + rb(M * f->ldstack * 4) + rb(wout_rows * f->ldwout * 4) + rb(9 * M * f->ldP * 4) +
                  2 * rb(f->opA_elems * 4) + rb(f->opT_elems * 4) + rb(f->opW_elems * 4) + (1 << 16);
   f->ws.init(bytes);
   f->tape = f->ws.alloc<float>((f->ops.size() + 1) * slot);
   f->G = f->ws.alloc<float>(slot); f->Gtmp = f->ws.alloc<float>(slot);
   f->logdet = f->ws.alloc<float>(f->cfg.max_batch);
+  f->dld = f->ws.alloc<float>(f->cfg.max_batch); f->dz_in = f->ws.alloc<float>(slot);
   f->cond_nhwc = f->ws.alloc<float>(M * hch); f->Ecache = f->ws.alloc<float>(M * hch);
   f->x_in = f->ws.alloc<float>(slot); f->cond_in = f->ws.alloc<float>(M * hch); f->z_dev = f->ws.alloc<float>(slot); f->loss_dev = f->ws.alloc<float>(64);
   f->c1 = f->ws.alloc<float>(M * f->ldc1); f->E = f->ws.alloc<float>(M * f->ldE);
@@ -903,6 +909,32 @@ extern "C" int ipk_flowtrain_finalize(ipk_flowtrain* f, void* stream) {
   IPK_CATCH
 }
 
+
+namespace ipk {
+// re-pack every layer from the master parameters, then the density direction keeping the tape (inputs staged in x_in / cond_in)
+static void train_repack_and_forward(ipk_flowtrain* f, int B, cudaStream_t st) {
+  const long long M = (long long)B * 64;
+  {
+    ProfScope ps("train.repack", st);
+    // every layer of the flow in three launches: effective weight-normed weights, all packings, then the (tiny) bias copies
+    wn_apply_multi_kernel<<<dim3(f->wn_maxrows, f->n_wn_jobs), 128, 0, st>>>(f->d_wn_jobs);
+    IPK_LAUNCH_CHECK();
+    conv_pack_run_jobs(f->d_pack_jobs, f->n_pack_jobs, st);
+    for (McfTrain& m : f->mcfs) conv_pack_bias(m.w1, 0, m.b1, m.C2, 0.f, st);
+    for (NiceTrain& n : f->nices) conv_pack_bias(n.c3, 0, n.b3, n.N3, 0.f, st);
+  }
+  nchw_to_nhwc(f->x_in, f->tape, B, f->C0, 64, f->C0, st);
+  nchw_to_nhwc(f->cond_in, f->cond_nhwc, B, f->hch, 64, f->hch, st);
+  elu_kernel<<<gridn(M * f->hch), 256, 0, st>>>(f->cond_nhwc, f->Ecache, M * f->hch);
+  IPK_LAUNCH_CHECK();
+  IPK_CUDA(cudaMemsetAsync(f->logdet, 0, B * sizeof(float), st));
+  {
+    ProfScope ps("train.forward", st);
+    train_forward(f, B, st);
+  }
+}
+}  // namespace ipk
+
 // One training step without the optimizer: forward (z, logdet, loss) and the gradient of the loss w.r.t. every registered fp32
 // tensor, written (not accumulated) into its gradient buffer.  x: [B][C0][8][8], cond: [B][h][8][8] (NCHW, device).
 extern "C" int ipk_flowtrain_step(ipk_flowtrain* f, const float* x, const float* cond, float* loss_out, float* z_out, float* logdet_out,
@@ -920,26 +952,9 @@ extern "C" int ipk_flowtrain_step(ipk_flowtrain* f, const float* x, const float*
   const size_t slot = (size_t)f->cfg.max_batch * 64 * f->C0;
   const float* zS = f->tape + f->ops.size() * slot;
   run_graphed_step(f, B, 1, stream_, [&](cudaStream_t st) {
-    {
-      ProfScope ps("train.repack", st);
-      // every layer of the flow in three launches: effective weight-normed weights, all packings, then the (tiny) bias copies
-      wn_apply_multi_kernel<<<dim3(f->wn_maxrows, f->n_wn_jobs), 128, 0, st>>>(f->d_wn_jobs);
-      IPK_LAUNCH_CHECK();
-      conv_pack_run_jobs(f->d_pack_jobs, f->n_pack_jobs, st);
-      for (McfTrain& m : f->mcfs) conv_pack_bias(m.w1, 0, m.b1, m.C2, 0.f, st);
-      for (NiceTrain& n : f->nices) conv_pack_bias(n.c3, 0, n.b3, n.N3, 0.f, st);
-    }
-    nchw_to_nhwc(f->x_in, f->tape, B, f->C0, 64, f->C0, st);
-    nchw_to_nhwc(f->cond_in, f->cond_nhwc, B, f->hch, 64, f->hch, st);
-    elu_kernel<<<gridn(M * f->hch), 256, 0, st>>>(f->cond_nhwc, f->Ecache, M * f->hch);
-    IPK_LAUNCH_CHECK();
-    IPK_CUDA(cudaMemsetAsync(f->logdet, 0, B * sizeof(float), st));
-    {
-      ProfScope ps("train.forward", st);
-      train_forward(f, B, st);
-    }
+    train_repack_and_forward(f, B, st);
     IPK_CUDA(cudaMemsetAsync(f->loss_dev, 0, sizeof(float), st));
-    loss_kernel<<<64, 256, 0, st>>>(zS, f->G, M * f->C0, f->logdet, B, f->loss_dev);
+    loss_kernel<<<64, 256, 0, st>>>(zS, f->G, M * f->C0, f->logdet, B, f->loss_dev, f->dld);
     IPK_LAUNCH_CHECK();
     nhwc_to_nchw(zS, f->z_dev, B, f->C0, 64, f->C0, st);
     {
@@ -950,6 +965,56 @@ extern "C" int ipk_flowtrain_step(ipk_flowtrain* f, const float* x, const float*
   IPK_CUDA(cudaMemcpyAsync(loss_out, f->loss_dev, sizeof(float), cudaMemcpyDeviceToDevice, stream_));
   if (z_out) IPK_CUDA(cudaMemcpyAsync(z_out, f->z_dev, (size_t)B * f->C0 * 64 * sizeof(float), cudaMemcpyDeviceToDevice, stream_));
   if (logdet_out) IPK_CUDA(cudaMemcpyAsync(logdet_out, f->logdet, B * sizeof(float), cudaMemcpyDeviceToDevice, stream_));
+  IPK_CATCH
+}
+
+
+// The same step split at the loss, for callers that compute their own loss (torch.autograd.Function around the flow module:
+// `out, logdet = self.flow(x, cond)` ... `loss.backward()`, models/second_stage_video.py:409-415):
+//   ipk_flowtrain_forward  : re-pack, density direction with the tape kept -> z [B][C0][8][8], logdet [B]
+//   ipk_flowtrain_backward : upstream gradients dz [B][C0][8][8] and dlogdet [B] (either may be null = zeros) -> every registered
+//                            gradient buffer is written (not accumulated); dx_out (optional) receives dL/dx [B][C0][8][8].
+//                            Must follow a forward of the same B on the same plan.
+extern "C" int ipk_flowtrain_forward(ipk_flowtrain* f, const float* x, const float* cond, float* z_out, float* logdet_out, int32_t B, void* stream) {
+  IPK_TRY
+  IPK_CHECK(f && f->finalized, IPK_ERR_STATE, "flow train: not finalized");
+  IPK_CHECK(x && cond && z_out && logdet_out, IPK_ERR_INVALID, "ipk_flowtrain_forward: null buffer");
+  IPK_CHECK(B > 0 && B <= f->cfg.max_batch, IPK_ERR_INVALID, "flow train: batch %d outside (0, %d]", B, f->cfg.max_batch);
+  cudaStream_t stream_ = (cudaStream_t)stream;
+  IPK_CUDA(cudaMemcpyAsync(f->x_in, x, (size_t)B * f->C0 * 64 * sizeof(float), cudaMemcpyDeviceToDevice, stream_));
+  IPK_CUDA(cudaMemcpyAsync(f->cond_in, cond, (size_t)B * f->hch * 64 * sizeof(float), cudaMemcpyDeviceToDevice, stream_));
+  const size_t slot = (size_t)f->cfg.max_batch * 64 * f->C0;
+  const float* zS = f->tape + f->ops.size() * slot;
+  run_graphed_step(f, B, 2, stream_, [&](cudaStream_t st) {
+    train_repack_and_forward(f, B, st);
+    nhwc_to_nchw(zS, f->z_dev, B, f->C0, 64, f->C0, st);
+  }, f->use_graph);
+  f->fwd_batch = B;
+  IPK_CUDA(cudaMemcpyAsync(z_out, f->z_dev, (size_t)B * f->C0 * 64 * sizeof(float), cudaMemcpyDeviceToDevice, stream_));
+  IPK_CUDA(cudaMemcpyAsync(logdet_out, f->logdet, B * sizeof(float), cudaMemcpyDeviceToDevice, stream_));
+  IPK_CATCH
+}
+
+extern "C" int ipk_flowtrain_backward(ipk_flowtrain* f, const float* dz, const float* dlogdet, float* dx_out, int32_t B, void* stream) {
+  IPK_TRY
+  IPK_CHECK(f && f->finalized, IPK_ERR_STATE, "flow train: not finalized");
+  IPK_CHECK(B > 0 && B == f->fwd_batch, IPK_ERR_STATE, "ipk_flowtrain_backward: batch %d does not match the preceding forward (%d)", B, f->fwd_batch);
+  cudaStream_t stream_ = (cudaStream_t)stream;
+  const size_t n = (size_t)B * f->C0 * 64;
+  if (dz) IPK_CUDA(cudaMemcpyAsync(f->dz_in, dz, n * sizeof(float), cudaMemcpyDeviceToDevice, stream_));
+  else IPK_CUDA(cudaMemsetAsync(f->dz_in, 0, n * sizeof(float), stream_));
+  if (dlogdet) IPK_CUDA(cudaMemcpyAsync(f->dld, dlogdet, B * sizeof(float), cudaMemcpyDeviceToDevice, stream_));
+  else IPK_CUDA(cudaMemsetAsync(f->dld, 0, B * sizeof(float), stream_));
+  run_graphed_step(f, B, 3, stream_, [&](cudaStream_t st) {
+    nchw_to_nhwc(f->dz_in, f->G, B, f->C0, 64, f->C0, st);
+    {
+      ProfScope ps("train.backward", st);
+      train_backward(f, B, st);
+    }
+    nhwc_to_nchw(f->G, f->dz_in, B, f->C0, 64, f->C0, st);      // dL/dx (the staging buffer is free again)
+  }, f->use_graph);
+  if (dx_out) IPK_CUDA(cudaMemcpyAsync(dx_out, f->dz_in, n * sizeof(float), cudaMemcpyDeviceToDevice, stream_));
+  f->fwd_batch = 0;
   IPK_CATCH
 }
 
@@ -965,14 +1030,16 @@ extern "C" int ipk_flowtrain_destroy(ipk_flowtrain* f) {
 
 // torch.optim.Adam(amsgrad) on a contiguous fp32 shard (second_stage_video.py:633-636); step counts from 1; vmax may be null (plain Adam).
 // grad_scale multiplies the gradient first (1 / world_size after a summing reduce-scatter).
-extern "C" int ipk_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq, int64_t n, float lr, float beta1,
-                             float beta2, float eps, float weight_decay, int32_t step, float grad_scale, void* stream) {
+extern "C" int ipk_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq, int64_t n, double lr, double beta1,
+                             double beta2, double eps, double weight_decay, int32_t step, float grad_scale, void* stream) {
   IPK_TRY
   IPK_CHECK(param && grad && exp_avg && exp_avg_sq && n >= 0 && step >= 1, IPK_ERR_INVALID, "ipk_adam_step: bad argument");
   if (n == 0) return IPK_OK;
-  const float bc1 = 1.0f - powf(beta1, (float)step), bc2 = 1.0f - powf(beta2, (float)step);
-  adam_kernel<<<gridn(n), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, max_exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2,
-                                                          grad_scale);
+  // torch.optim.adam._single_tensor_adam: step_size = lr / (1 - beta1^t) and sqrt(1 - beta2^t) are Python doubles, rounded to fp32 only
+  // when they meet the tensors (1 - powf(0.999f, 1) would already be off by 1e-5 relative)
+  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+  adam_kernel<<<gridn(n), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, max_exp_avg_sq, n, (float)(lr / bc1), (float)beta1, (float)beta2,
+                                                          (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps, (float)weight_decay, (float)sqrt(bc2), grad_scale);
   IPK_LAUNCH_CHECK();
   IPK_CATCH
 }

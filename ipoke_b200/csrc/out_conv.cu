@@ -129,10 +129,11 @@ OutConvPlan* out_conv_plan_create(const float* w_dev_packed, cudaStream_t st) {
   (void)st;
   OutConvPlan* p = new OutConvPlan();
   p->wpk = w_dev_packed;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[IPK_MAX_DEVICES] = {false};
+  const int slot = current_device_slot();
+  if (!attr_set[slot]) {
     IPK_CUDA(cudaFuncSetAttribute(out_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
+    attr_set[slot] = true;
   }
   return p;
 }

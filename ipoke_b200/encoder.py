@@ -57,8 +57,8 @@ class ResNetMotionEncoder(nn.Module):
             self.max_batch = int(batch)
             self.invalidate()
         if self._plist is None:
-            self._plist = list(self.parameters())
-        key = (device, self.max_batch, sum(q._version for q in self._plist))
+            self._plist = list(self.parameters()) + list(self.buffers())
+        key = (device, self.max_batch, self.precision) + _lib.tensors_key(self._plist)
         if self._plan is not None and self._plan_key == key:
             return self._plan
         if device.type != "cuda":
@@ -115,14 +115,16 @@ class ResNetMotionEncoder(nn.Module):
         return super()._apply(fn, *a, **k)
 
 
-def encode_first_stage(enc_motion, X, full_sequence=True, max_frames=10, eps=None):
+def encode_first_stage(enc_motion, X, full_sequence=True, max_frames=10, eps=None, full_seq=True):
     """PokeMotionModel.encode_first_stage (models/second_stage_video.py:352-359): X [B,T,3,H,W] -> (motion, mu).
-    The frame selection follows the reference: the whole clip when the first stage was trained on full sequences (or
-    max_frames < 16), else all but the last frame / all but the first."""
+    The frame selection follows the reference exactly:
+        full_seq (the second stage's flag):  X if the first stage was trained on full sequences or max_frames < 16, else X[:, :-1]
+        not full_seq:                        X if the first stage was trained on full sequences, else X[:, 1:]
+    full_sequence = first_stage_model.full_sequence, max_frames = config['data']['max_frames']."""
     with torch.no_grad():
-        if full_sequence or max_frames < 16:
-            X_in = X
+        if full_seq:
+            X_in = X if (full_sequence or max_frames < 16) else X[:, :-1]
         else:
-            X_in = X[:, :-1]
+            X_in = X if full_sequence else X[:, 1:]
         motion, mu, _ = enc_motion(X_in.transpose(1, 2), eps=eps)
     return motion, mu

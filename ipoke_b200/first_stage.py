@@ -104,8 +104,8 @@ class SpadeCondMotionDecoder(nn.Module):
             self.max_frames = max(self.max_frames, int(frames))
             self.invalidate()
         if self._plist is None:
-            self._plist = list(self.parameters())
-        key = (device, self.precision, self.max_batch, self.max_frames, sum(q._version for q in self._plist))
+            self._plist = list(self.parameters()) + list(self.buffers())      # buffers: the spectral-norm u / v vectors
+        key = (device, self.precision, self.max_batch, self.max_frames) + _lib.tensors_key(self._plist)
         if self._plan is not None and self._plan_key == key:
             return self._plan
         if device.type != "cuda":

@@ -23,6 +23,11 @@ class PokeMotionSampler:
         self.conditioner = conditioner
         self.poke_embedder = poke_embedder
         self._pinned = {}
+        # frame-selection flags of encode_first_stage (second_stage_video.py:352-359): the second stage's `full_seq`, the first stage's
+        # `full_sequence`, config['data']['max_frames']
+        self.full_seq = True
+        self.full_sequence = bool(getattr(first_stage_model, "full_sequence", True))
+        self.max_frames = 10
 
     def make_cond(self, x0, poke):
         """Conditioning half of make_flow_input (second_stage_video.py:268-287,311): cat[conditioner(x0), poke_embedder(poke)]."""
@@ -60,9 +65,12 @@ class PokeMotionSampler:
             self._pinned[name] = t
         return t
 
-    def sample_host(self, z, cond, x0, length, device=None, uint8=False):
+    def sample_host(self, z, cond, x0, length, device=None, uint8=False, reuse=False):
         """Same step with HOST tensors: inputs are staged through pinned memory, copied to the device, and the frames are
         copied back into a pinned host tensor (returned).  Synchronous.
+        The returned tensor is a FRESH pinned allocation per call (torch's caching host allocator recycles freed blocks, so a loop
+        that drops its results pays the page-locking once); reuse=True returns one cached buffer per output shape instead, which the
+        next call with the same shape OVERWRITES -- only for callers that consume the frames before calling again.
         uint8=True returns the post-processed sample instead: uint8 [B,T,S,S,3] = ((x + 1) * 127.5).permute(0,1,3,4,2) as
         the callers of forward_sample compute it on the host (second_stage_video.py:673-675), converted on the device."""
         device = torch.device(device if device is not None else "cuda:0")
@@ -79,12 +87,14 @@ class PokeMotionSampler:
         fplan = self.flow._ensure_plan(device, B)
         dplan = fs._ensure_plan(device, B, length)
         if uint8:
-            out = self._pin("frames_u8", (B, int(length), fs.spatial, fs.spatial, 3), torch.uint8)
+            shape = (B, int(length), fs.spatial, fs.spatial, 3)
+            out = self._pin("frames_u8", shape, torch.uint8) if reuse else torch.empty(shape, dtype=torch.uint8, pin_memory=True)
             with torch.cuda.device(device):
                 _lib.check(_lib.lib().ipk_sample_host_u8(fplan.handle, dplan.handle, zp.data_ptr(), cp.data_ptr(), xp.data_ptr(), out.data_ptr(),
                                                          B, int(length), _lib.current_stream_ptr()), "ipk_sample_host_u8")
             return out
-        out = self._pin("frames", (B, int(length), 3, fs.spatial, fs.spatial))
+        shape = (B, int(length), 3, fs.spatial, fs.spatial)
+        out = self._pin("frames", shape) if reuse else torch.empty(shape, dtype=torch.float32, pin_memory=True)
         with torch.cuda.device(device):
             _lib.check(_lib.lib().ipk_sample_host(fplan.handle, dplan.handle, zp.data_ptr(), cp.data_ptr(), xp.data_ptr(), out.data_ptr(),
                                                   B, int(length), _lib.current_stream_ptr()), "ipk_sample_host")
@@ -164,7 +174,8 @@ class PokeMotionSampler:
         if length is None:
             length = X_2.size(1) - 1
         with torch.no_grad():
-            z_1, *_ = encode_first_stage(enc_motion, X_1, eps=eps)
+            z_1, *_ = encode_first_stage(enc_motion, X_1, full_sequence=self.full_sequence, max_frames=self.max_frames, eps=eps,
+                                         full_seq=self.full_seq)
             p1 = torch.cat([poke_1, X_1[:, 0]], dim=1) if embed_poke_and_image else poke_1
             p1_src2 = torch.cat([poke_1, X_2[:, 0]], dim=1) if embed_poke_and_image else poke_1
             cond_1 = self.make_cond(X_1[:, 0], p1)

@@ -35,7 +35,7 @@ def fill_flow_(flow_module, seed=0, g_scale=0.05):
             b.copy_(torch.argsort(prev))
         elif name.endswith("initialized"):
             b.fill_(1)
-    flow_module.invalidate()
+    flow_module.invalidate(flags=True)
     return flow_module
 
 

@@ -226,8 +226,43 @@ def affine_params(params: Tensor) -> Tuple[Tensor, Tensor]:
     return mu, scale
 
 
+def actnorm_data_init(sd, p, x, init_scale=1.0):
+    """ActNorm2dFlow.init (macow2.py:526-539): per-channel mean / UNBIASED std of x * exp(ls0) + b0 over (B, H, W); writes
+    log_scale = log(init_scale / (std + 1e-6)), bias = -mean * inv_stdv and the `initialized` flag into sd (in place)."""
+    ls, b = sd[p + "log_scale"], sd[p + "bias"]
+    C = x.shape[1]
+    out = x * ls.exp() + b
+    out = out.transpose(0, 1).contiguous().view(C, -1)
+    mean = out.mean(dim=1).view(C, 1, 1)
+    std = out.std(dim=1).view(C, 1, 1)
+    inv_stdv = init_scale / (std + 1e-6)
+    sd[p + "log_scale"] = inv_stdv.log().to(ls.dtype)
+    sd[p + "bias"] = (-mean * inv_stdv).to(b.dtype)
+    sd[p + "initialized"] = torch.tensor(1, dtype=torch.uint8)
+
+
+def weightnorm_data_init(sd, p, x, padding, zero_init=True):
+    """p = prefix of the Conv2dWeightNorm module (its nn.Conv2d lives at p + 'conv.').  Conv2dWeightNorm.init (macow_utils.py:231-246) as called from forward (:248-250) with init_scale = 0 for zero_init layers (every
+    weight-normed conv of the flow: macow_utils.py:281,423): weight_g = init_scale / (std + 1e-6), bias = -mean * inv_stdv."""
+    v, g, b = sd[p + "conv.weight_v"], sd[p + "conv.weight_g"], sd[p + "conv.bias"]
+    out = F.conv2d(x, weight_norm_weight(v, g).to(x.dtype), b.to(x.dtype), padding=padding)
+    n = out.shape[1]
+    out = out.transpose(0, 1).contiguous().view(n, -1)
+    mean, std = out.mean(dim=1), out.std(dim=1)
+    inv_stdv = (0.0 if zero_init else 1.0) / (std + 1e-6)
+    sd[p + "conv.weight_g"] = inv_stdv.view(n, 1, 1, 1).to(g.dtype)
+    sd[p + "conv.bias"] = (-mean * inv_stdv).to(b.dtype)
+    sd[p + "initialized"] = torch.tensor(1, dtype=torch.uint8)
+
+
+def _uninitialised(sd, p):
+    return (p + "initialized") in sd and int(sd[p + "initialized"]) == 0
+
+
 def actnorm_fwd(sd, p, x):
-    """ActNorm2dFlow.forward (macow2.py:507-513)."""
+    """ActNorm2dFlow.forward (macow2.py:507-513); fires the data-dependent init first when `initialized` is 0 (:503-505)."""
+    if _uninitialised(sd, p):
+        actnorm_data_init(sd, p, x)
     ls, b = sd[p + "log_scale"].to(x.dtype), sd[p + "bias"].to(x.dtype)
     B, C, H, W = x.shape
     out = x * ls.exp() + b
@@ -271,6 +306,8 @@ def mcf_block(sd, p, x, h, order, shifted=True):
     c = F.conv2d(x, w)
     c = torch.cat([c, h], dim=1)
     c = F.elu(c)
+    if _uninitialised(sd, p + "net.conv1x1."):
+        weightnorm_data_init(sd, p + "net.conv1x1.", c, 0)
     w1 = weight_norm_weight(sd[p + "net.conv1x1.conv.weight_v"], sd[p + "net.conv1x1.conv.weight_g"]).to(x.dtype)
     return F.conv2d(c, w1, sd[p + "net.conv1x1.conv.bias"].to(x.dtype))
 
@@ -318,6 +355,8 @@ def nice_net(sd, p, z):
     out = F.elu(out)
     out = F.conv2d(out, sd[p + "net.conv2.weight"].to(z.dtype))
     out = F.elu(out)
+    if _uninitialised(sd, p + "net.conv3."):
+        weightnorm_data_init(sd, p + "net.conv3.", out, 1)
     w3 = weight_norm_weight(sd[p + "net.conv3.conv.weight_v"], sd[p + "net.conv3.conv.weight_g"]).to(z.dtype)
     return F.conv2d(out, w3, sd[p + "net.conv3.conv.bias"].to(z.dtype), padding=1)
 
@@ -459,6 +498,25 @@ def flow_reverse(sd, cfg, z: Tensor, cond: Tensor) -> Tensor:
 def flow_nll(z: Tensor, logdet: Tensor) -> Tensor:
     """FlowLoss.forward (loss.py:13-31) with logdet_weight = 1, spatial_mean = False: mean(0.5*sum z^2) - mean(logdet)."""
     return (0.5 * (z ** 2).flatten(1).sum(dim=1)).mean() - logdet.mean()
+
+
+def flow_loss_log(z: Tensor, logdet: Tensor, spatial_mean: bool = False, logdet_weight: float = 1.0):
+    """FlowLoss.forward with its log dict (loss.py:13-31, nll :75-79); draws torch.randn_like(z) from the default generator."""
+    def nll(s):
+        return 0.5 * torch.sum(torch.mean(s ** 2, dim=[2, 3]), dim=1) if spatial_mean else 0.5 * torch.sum(s ** 2, dim=[1, 2, 3])
+    nll_loss = torch.mean(nll(z))
+    nlogdet_loss = -torch.mean(logdet) / (z.shape[-2] * z.shape[-1]) if spatial_mean else -torch.mean(logdet)
+    loss = nll_loss + logdet_weight * nlogdet_loss
+    ref = torch.mean(nll(torch.randn_like(z)))
+    return loss, {"flow_loss": loss, "reference_nll_loss": ref, "nlogdet_loss": nlogdet_loss, "nll_loss": nll_loss, "logdet_weight": logdet_weight}
+
+
+def flow_data_init(sd, cfg, x: Tensor, cond: Tensor):
+    """First density-direction forward of a flow whose `initialized` buffers are 0: returns (initialised copy of sd, z, logdet).
+    The init fires layer by layer inside the forward, exactly where the reference's modules fire it."""
+    sd = dict(sd)
+    z, ld = flow_forward(sd, cfg, x, cond)
+    return sd, z, ld
 
 
 def flow_trainable_keys(sd) -> List[str]:

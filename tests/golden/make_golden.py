@@ -185,6 +185,64 @@ def run_grad_case(name, spec, out_dir):
     print(f"{name}: loss {loss.item():.6f} oracle {loss_or.item():.6f}; {len(keys)} tensors, oracle-vs-ref worst relative grad error {worst:.2e}")
 
 
+INIT_CASES = {
+    # name: (cfg kwargs, B, construction seed, input seed)   data-dependent init of a FRESH reference flow (first train() forward)
+    "flowinit_tiny": (dict(flow_in_channels=16, flow_mid_channels=64, h_channels=16, num_steps=[2, 1, 1], factor=4), 5, 7, 17),
+    "flowinit_c32": (dict(flow_in_channels=32, flow_mid_channels=64, h_channels=8, num_steps=[1] * 15), 3, 8, 18),
+}
+
+
+def run_init_case(name, spec, out_dir):
+    """A freshly constructed reference flow (every `initialized` buffer 0) runs its first density-direction forward in train() mode:
+    ActNorm2dFlow.init (macow2.py:526-539) and Conv2dWeightNorm.init (macow_utils.py:231-246) fire layer by layer.  Stored: the
+    state-dict before (fp16-exact weights are not needed -- it is small), every tensor the pass changed, and the outputs."""
+    kw, B, cseed, iseed = spec
+    cfg = O.flow_config(**kw)
+    Flow = ref_import.flow_cls()
+    torch.manual_seed(cseed)
+    m = Flow(dict(cfg))
+    sd0 = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(iseed)
+    x = torch.randn((B, cfg["flow_in_channels"], 8, 8), generator=g) * 1.7 + 0.3
+    cond = torch.randn((B, cfg["h_channels"], 8, 8), generator=g) * 0.5
+    m.train()
+    with torch.no_grad():
+        z, logdet = m(x, cond, reverse=False)
+        z2, logdet2 = m(x, cond, reverse=False)          # second call: already initialised, same result
+    assert torch.equal(z, z2) and torch.equal(logdet, logdet2)
+    sd1 = m.state_dict()
+    changed = {k: v.detach().clone() for k, v in sd1.items() if not torch.equal(v, sd0[k])}
+    n_flags = sum(1 for k in changed if k.endswith("initialized"))
+    # the pass only depends on the ActNorm parameters and the channel permutations (every coupling / MCF becomes the identity: zero_init),
+    # so only those are stored from the pre-init state; the test keeps its own random values for the conv weights
+    sd0 = {k: v for k, v in sd0.items() if k.endswith(("log_scale", "shuffle_idx")) or (k.endswith(".bias") and "actnorm" in k)}
+    fix = dict(kind="flowinit", cfg_kwargs=kw, B=B, cseed=cseed, iseed=iseed, sd0=sd0, changed=changed, x=x, cond=cond, z=z.clone(), logdet=logdet.clone(),
+               torch_version=torch.__version__)
+    torch.save(fix, os.path.join(out_dir, name + ".pt"))
+    kinds = sorted({k.rsplit(".", 1)[-1] for k in changed})
+    print(f"{name}: {len(sd0)} pre-init tensors kept, {len(changed)} changed ({n_flags} flags; kinds {kinds}); z std {z.std().item():.3f} logdet {logdet.tolist()}; "
+          f"file {os.path.getsize(os.path.join(out_dir, name + '.pt')) / 1e6:.2f} MB")
+
+
+def run_flowloss_case(out_dir):
+    """FlowLoss.forward (loss.py:13-31) incl. the RNG it consumes: values of the log dict under torch.manual_seed(123) and the next
+    randn draw after the call."""
+    import importlib
+    ref_import.install()
+    FlowLoss = importlib.import_module("models.modules.INN.loss").FlowLoss
+    g = torch.Generator().manual_seed(3)
+    z = torch.randn((4, 16, 8, 8), generator=g) * 1.2
+    logdet = torch.randn((4,), generator=g) * 5 - 20
+    out = {}
+    for sm in (False, True):
+        torch.manual_seed(123)
+        loss, log = FlowLoss(spatial_mean=sm, logdet_weight=1.0)(z, logdet)
+        nxt = torch.randn(3)
+        out[sm] = dict(loss=loss.item(), log={k: (v.item() if torch.is_tensor(v) else v) for k, v in log.items()}, next_randn=nxt)
+    torch.save(dict(kind="flowloss", z=z, logdet=logdet, out=out, torch_version=torch.__version__), os.path.join(out_dir, "flowloss.pt"))
+    print("flowloss:", out[False]["log"])
+
+
 def ref_flow(cfg, sd):
     Flow = ref_import.flow_cls()
     m = Flow(dict(cfg))
@@ -275,6 +333,11 @@ if __name__ == "__main__":
     for n, s in I3D_CASES.items():
         if a.only in (None, n):
             run_i3d_case(n, s, HERE)
+    for n, s in INIT_CASES.items():
+        if a.only in (None, n):
+            run_init_case(n, s, HERE)
+    if a.only in (None, "flowloss"):
+        run_flowloss_case(HERE)
     if a.full:
         for n, s in FULL_FLOW_CASES.items():
             if a.only in (None, n):

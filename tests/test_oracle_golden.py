@@ -163,3 +163,59 @@ def test_training_step_oracle_matches_reference_autograd(name):
         scale = fx["maxabs"][i].item() + 1e-12
         assert abs(g.double().norm().item() - fx["norms"][i].item()) < 1e-4 * fx["norms"][i].item() + 1e-9, k
         assert (g.flatten()[fx["idx"][i]] - fx["val"][i]).abs().max().item() < 1e-4 * scale, k
+
+
+def _fresh_state(fx):
+    """Pre-init state of the fixture's flow: the reference's ActNorm parameters / permutations, the oracle's synthetic conv weights (the
+    init pass does not depend on them: every weight-normed conv is zero_init), every `initialized` flag 0."""
+    cfg = O.flow_config(**fx["cfg_kwargs"])
+    sd = O.synth_flow_state_dict(cfg, seed=0)
+    for k, v in fx["sd0"].items():
+        assert sd[k].shape == v.shape, k
+        sd[k] = v.clone()
+    for k in list(sd):
+        if k.endswith("initialized"):
+            sd[k] = torch.tensor(0, dtype=torch.uint8)
+    return cfg, sd
+
+
+@pytest.mark.parametrize("name", ["flowinit_tiny", "flowinit_c32"])
+def test_data_dependent_init_oracle_matches_reference(name):
+    """ActNorm2dFlow.init / Conv2dWeightNorm.init as fired by the reference's first train() forward (macow2.py:503-505,526-539,
+    macow_utils.py:231-250): every tensor the reference changed, and the outputs of that forward."""
+    fx = golden(name)
+    cfg, sd = _fresh_state(fx)
+    with torch.no_grad():
+        sd1, z, ld = O.flow_data_init(sd, cfg, fx["x"], fx["cond"])
+    assert (z - fx["z"]).abs().max().item() < 1e-5 and (ld - fx["logdet"]).abs().max().item() < 1e-3
+    for k, v in fx["changed"].items():
+        assert (sd1[k].float() - v.float()).abs().max().item() < 1e-5, k
+    # nothing else moved, and every flag is set
+    for k, v in sd1.items():
+        if k.endswith("initialized"):
+            assert int(v) == 1
+        elif k.endswith(".conv.bias"):
+            assert float(v.abs().max()) == 0.0, k      # the reference's fresh bias is already 0, so it is not among `changed`
+        elif k not in fx["changed"]:
+            assert torch.equal(v, sd[k]), k
+
+
+def test_flow_loss_log_dict_and_rng_consumption():
+    """FlowLoss.forward (loss.py:13-31): all entries of the log dict, and the randn_like draw it takes from the default generator."""
+    fx = golden("flowloss")
+    import ipoke_b200 as ipk
+    for sm in (False, True):
+        want = fx["out"][sm]
+        for impl in ("oracle", "product"):
+            torch.manual_seed(123)
+            if impl == "oracle":
+                loss, log = O.flow_loss_log(fx["z"], fx["logdet"], spatial_mean=sm)
+            else:
+                loss, log = ipk.FlowLoss(spatial_mean=sm, logdet_weight=1.0)(fx["z"], fx["logdet"])     # host arithmetic on tiny tensors
+            nxt = torch.randn(3)
+            assert abs(loss.item() - want["loss"]) < 1e-4 * abs(want["loss"])
+            assert set(log) == set(want["log"])
+            for k, v in want["log"].items():
+                got = log[k].item() if torch.is_tensor(log[k]) else log[k]
+                assert abs(got - v) <= 1e-5 * max(1.0, abs(v)), (impl, k)
+            assert torch.equal(nxt, want["next_randn"]), impl
