@@ -17,7 +17,7 @@ $(OBJDIR)/%.o: $(SRC)/%.cu $(HEADERS)
 
 $(LIBDIR)/libipoke_b200.so: $(OBJECTS)
 	@mkdir -p $(LIBDIR)
-	$(NVCC) -shared $(ARCH) -o $@ $(OBJECTS) -lcudart
+	$(NVCC) -shared $(ARCH) -o $@ $(OBJECTS) -lcudart -ldl
 
 clean:
 	rm -rf build $(LIBDIR)

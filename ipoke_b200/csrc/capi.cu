@@ -3,11 +3,23 @@
 #include <mutex>
 #include <map>
 #include <tuple>
+#include <nvtx3/nvToolsExt.h>
 #include "conv.cuh"
 #include "conv3d_tc.cuh"
 #include "elementwise.cuh"
 
 namespace ipk {
+
+bool nvtx_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("IPK_NVTX");
+    on = (e && e[0] == '1') ? 1 : 0;
+  }
+  return on == 1;
+}
+void nvtx_push(const char* tag) { nvtxRangePushA(tag); }
+void nvtx_pop() { nvtxRangePop(); }
 
 thread_local std::string g_last_error;
 thread_local int64_t g_launches = 0;

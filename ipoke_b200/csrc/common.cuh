@@ -56,19 +56,33 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 bool pdl_enabled();   // IPK_PDL=0 disables (plain stream-ordered launches)
 
+// cluster_x > 1 launches thread-block clusters of that many CTAs along x (gridDim.x must be a multiple of it)
 template <typename... KArgs, typename... Args>
-inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+inline void launch_kc(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x, Args&&... args) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (cluster_x > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = (unsigned)cluster_x; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = na;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
   if (e != cudaSuccess) ::ipk::fail(IPK_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
   count_launch();
+}
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  launch_kc(kernel, grid, block, smem, st, 1, std::forward<Args>(args)...);
 }
 
 // ---------------------------------------------------------------- optional per-phase device timing
@@ -79,11 +93,22 @@ struct Prof {
   static void begin(const char* tag, cudaStream_t st);
   static void end(cudaStream_t st);
 };
+// Every ProfScope is also an NVTX range (domain-less push/pop, header-only nvtx3) when IPK_NVTX=1, so that nsys / ncu --nvtx timelines
+// carry the stage names (flow.nice.conv2, dec.up.convT.b3, train.backward, ...); without the variable the cost is one branch.
+bool nvtx_enabled();
+void nvtx_push(const char* tag);
+void nvtx_pop();
 struct ProfScope {
   cudaStream_t st;
-  bool on;
-  ProfScope(const char* tag, cudaStream_t s) : st(s), on(Prof::enabled()) { if (on) Prof::begin(tag, st); }
-  ~ProfScope() { if (on) Prof::end(st); }
+  bool on, nv;
+  ProfScope(const char* tag, cudaStream_t s) : st(s), on(Prof::enabled()), nv(nvtx_enabled()) {
+    if (nv) nvtx_push(tag);
+    if (on) Prof::begin(tag, st);
+  }
+  ~ProfScope() {
+    if (on) Prof::end(st);
+    if (nv) nvtx_pop();
+  }
 };
 
 // ---------------------------------------------------------------- activations

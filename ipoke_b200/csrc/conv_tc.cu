@@ -89,15 +89,21 @@ __device__ __forceinline__ void act_tile(float (&v)[NV], int act) {
 // (x = -1 .. 128, zero-filled outside) and the three dx taps are row-shifted views of that box (UMMA descriptor start advanced by
 // dx * 128 bytes) instead of three separate TMA loads: A traffic / 3.
 constexpr int TC_HALO_A_BYTES = 17 * 1024;      // 130 rows x 128 B = 16 640 B, padded to keep the regions 1024-byte aligned
-template <int BN, int NSPLIT, bool FUSED, bool HALO>
+// CG = 2 (CTA pair, launched as clusters of 2): the two CTAs own two consecutive M tiles of the same N tile; each loads its own A
+// tile and HALF of the W tile (BN / 2 rows), and the pair's leader issues cta_group::2 MMAs (M = 256, N = BN) that read both CTAs'
+// shared memory -- every W byte is fetched from L2 once per pair instead of once per CTA, which is what bounds these kernels
+// (measured: NICE conv2 sits at the chip's TMA throughput, not at the tensor pipe).  Each CTA's TMEM holds its own 128 rows x BN
+// columns, so the epilogue is the single-CTA one.
+template <int BN, int NSPLIT, bool FUSED, bool HALO, int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, const TcArgs a) {
   constexpr int A_BYTES = TC_BM * TC_BK * 2;         // 16 KB
-  constexpr int W_BYTES = BN * TC_BK * 2;
+  constexpr int WROWS = BN / CG;                     // W rows this CTA stages
+  constexpr int W_BYTES = WROWS * TC_BK * 2;
   constexpr int NPLANES = NSPLIT == 3 ? 2 : 1;
   constexpr int STAGE_BYTES = HALO ? NPLANES * (TC_HALO_A_BYTES + 3 * W_BYTES) : NPLANES * (A_BYTES + W_BYTES);
-  constexpr uint32_t IDESC = umma_idesc_bf16(TC_BM, BN);
+  constexpr uint32_t IDESC = umma_idesc_bf16(TC_BM * CG, BN);
   constexpr int MAX_STAGES = 8;
   constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   constexpr int EPI_CHUNK = BN >= 64 ? 32 : 16;      // columns per TMEM load
@@ -115,20 +121,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int stages = a.stages;
   const int txy = a.tiles_x * a.tiles_y;
-  const int tiles_mn = a.tiles_m * a.tiles_n;
+  // work units: (split / sub-convolution z, M-tile group, N tile); a group is CG consecutive M tiles, one per CTA of the pair
+  const int tiles_mg = (a.tiles_m + CG - 1) / CG;
+  const int tiles_mn = tiles_mg * a.tiles_n;
   const int total_tiles = tiles_mn * (a.nsub > 1 ? a.nsub : a.nsplit);
+  const uint32_t crank = CG == 2 ? cluster_ctarank() : 0u;
+  const int unit0 = (int)blockIdx.x / CG, unit_step = (int)gridDim.x / CG;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], TC_EPI_WARPS); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], CG * TC_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {  // TMEM allocation by one full warp; the same warp deallocates
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (warp == 1) {  // TMEM allocation by one full warp (of each CTA of a pair); the same warp deallocates
+    if constexpr (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();     // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
   pdl_wait();        // prologue above overlapped the previous kernel's tail; its outputs are visible from here on
@@ -139,12 +155,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      // loads of either CTA of a pair complete on the LEADER's full barrier, which expects the bytes of both
+      auto lda = [&](void* dst, const CUtensorMap* tm, int st_i, int c0, int c1, int c2, int c3) {
+        if constexpr (CG == 2) tma_load_4d_2cta(dst, tm, mapa_u32(smem_u32(&full_bar[st_i]), 0), c0, c1, c2, c3);
+        else tma_load_4d(dst, tm, &full_bar[st_i], c0, c1, c2, c3);
+      };
+      auto ldw = [&](void* dst, const CUtensorMap* tm, int st_i, int c0, int c1) {
+        if constexpr (CG == 2) tma_load_2d_2cta(dst, tm, mapa_u32(smem_u32(&full_bar[st_i]), 0), c0, c1);
+        else tma_load_2d(dst, tm, &full_bar[st_i], c0, c1);
+      };
+      for (int tile = unit0; tile < total_tiles; tile += unit_step) {
         const int z = tile / tiles_mn, rem = tile - z * tiles_mn;      // z: split-K slice, or sub-convolution when nsub > 1
-        const int mt = rem / a.tiles_n, nt = rem - mt * a.tiles_n;
+        const int mg = rem / a.tiles_n, nt = rem - mg * a.tiles_n;
+        const int mt = mg * CG + (int)crank;                            // beyond tiles_m: every box is out of bounds -> zero fill
         const int tf = mt / txy, r2 = mt - tf * txy;
         const int ty = r2 / a.tiles_x, tx = r2 - ty * a.tiles_x;
-        const int f0 = tf * a.bf, y0 = ty * a.bh, x0 = tx * a.bw, n0 = nt * BN;
+        const int f0 = tf * a.bf, y0 = ty * a.bh, x0 = tx * a.bw, n0 = nt * BN + (int)crank * WROWS;
         const TcSub& sb = a.sub[a.nsub > 1 ? z : 0];
         if constexpr (HALO) {
           // one stage per (input row dy, k-block): the 130-pixel row box of both planes + the weights of its three dx taps
@@ -152,14 +178,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             for (int kb = 0; kb < a.nkb; ++kb) {
               mbar_wait(&empty_bar[s], ph ^ 1);
               uint8_t* st = smem + (size_t)s * STAGE_BYTES;
-              mbar_expect_tx(&full_bar[s], NPLANES * (130 * 128 + 3 * W_BYTES));
-              tma_load_4d(st, &tmA_hi, &full_bar[s], kb * TC_BK, -1, y0 + dyi - 1, f0);
-              if (NSPLIT == 3) tma_load_4d(st + TC_HALO_A_BYTES, &tmA_lo, &full_bar[s], kb * TC_BK, -1, y0 + dyi - 1, f0);
+              if (crank == 0) mbar_expect_tx(&full_bar[s], CG * NPLANES * (130 * 128 + 3 * W_BYTES));
+              lda(st, &tmA_hi, s, kb * TC_BK, -1, y0 + dyi - 1, f0);
+              if (NSPLIT == 3) lda(st + TC_HALO_A_BYTES, &tmA_lo, s, kb * TC_BK, -1, y0 + dyi - 1, f0);
               uint8_t* wst = st + NPLANES * TC_HALO_A_BYTES;
               for (int dxi = 0; dxi < 3; ++dxi) {
                 const int wrow = (dyi * 3 + dxi) * a.Npad + n0;
-                tma_load_2d(wst + dxi * W_BYTES, &tmW_hi, &full_bar[s], kb * TC_BK, wrow);
-                if (NSPLIT == 3) tma_load_2d(wst + (3 + dxi) * W_BYTES, &tmW_lo, &full_bar[s], kb * TC_BK, wrow);
+                ldw(wst + dxi * W_BYTES, &tmW_hi, s, kb * TC_BK, wrow);
+                if (NSPLIT == 3) ldw(wst + (3 + dxi) * W_BYTES, &tmW_lo, s, kb * TC_BK, wrow);
               }
               if (++s == stages) { s = 0; ph ^= 1; }
             }
@@ -173,12 +199,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           {
             mbar_wait(&empty_bar[s], ph ^ 1);
             uint8_t* st = smem + (size_t)s * STAGE_BYTES;
-            mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-            tma_load_4d(st, &tmA_hi, &full_bar[s], kb * TC_BK, x0 + dx, y0 + dy, f0);
-            tma_load_2d(st + NPLANES * A_BYTES, &tmW_hi, &full_bar[s], kb * TC_BK, wrow);
+            if (crank == 0) mbar_expect_tx(&full_bar[s], CG * STAGE_BYTES);
+            lda(st, &tmA_hi, s, kb * TC_BK, x0 + dx, y0 + dy, f0);
+            ldw(st + NPLANES * A_BYTES, &tmW_hi, s, kb * TC_BK, wrow);
             if (NSPLIT == 3) {
-              tma_load_4d(st + A_BYTES, &tmA_lo, &full_bar[s], kb * TC_BK, x0 + dx, y0 + dy, f0);
-              tma_load_2d(st + NPLANES * A_BYTES + W_BYTES, &tmW_lo, &full_bar[s], kb * TC_BK, wrow);
+              lda(st + A_BYTES, &tmA_lo, s, kb * TC_BK, x0 + dx, y0 + dy, f0);
+              ldw(st + NPLANES * A_BYTES + W_BYTES, &tmW_lo, s, kb * TC_BK, wrow);
             }
             if (++s == stages) { s = 0; ph ^= 1; }
           }
@@ -187,13 +213,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (the pair's leader only when CG = 2) =====================
+    if (lane == 0 && crank == 0) {
       int s = 0;
       uint32_t ph = 0;
       int as = 0;
       uint32_t aph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t acc) {
+        if constexpr (CG == 2) umma_bf16_2cta(d, da, db, IDESC, acc);
+        else umma_bf16(d, da, db, IDESC, acc);
+      };
+      auto commit = [&](uint64_t* bar) {
+        if constexpr (CG == 2) umma_commit_2cta(bar);
+        else umma_commit(bar);
+      };
+      for (int tile = unit0; tile < total_tiles; tile += unit_step) {
         const int z = tile / tiles_mn;
         const int it_begin = a.nsub > 1 ? 0 : z * a.iters_per_split;
         const int iters = HALO ? 3 * a.nkb : min(a.sub[a.nsub > 1 ? z : 0].ntaps * a.nkb, it_begin + a.iters_per_split) - it_begin;
@@ -215,17 +249,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
               for (int k = 0; k < TC_BK / 16; ++k) {
                 const uint64_t koff = (uint64_t)((k * 32) >> 4);
-                umma_bf16(tacc, da_hi + koff, dw_hi + koff, IDESC, (it > 0 || dxi > 0 || k > 0) ? 1u : 0u);
+                mma(tacc, da_hi + koff, dw_hi + koff, (it > 0 || dxi > 0 || k > 0) ? 1u : 0u);
                 if (NSPLIT == 3) {
                   const uint64_t da_lo = umma_desc_sw128_off(sa + TC_HALO_A_BYTES + dxi * 128, boff);
                   const uint64_t dw_lo = umma_desc_sw128(sw + (3 + dxi) * W_BYTES);
-                  umma_bf16(tacc, da_lo + koff, dw_hi + koff, IDESC, 1u);
-                  umma_bf16(tacc, da_hi + koff, dw_lo + koff, IDESC, 1u);
+                  mma(tacc, da_lo + koff, dw_hi + koff, 1u);
+                  mma(tacc, da_hi + koff, dw_lo + koff, 1u);
                 }
               }
             }
-            umma_commit(&empty_bar[s]);
-            if (it == iters - 1) umma_commit(&tmem_full_bar[as]);
+            commit(&empty_bar[s]);
+            if (it == iters - 1) commit(&tmem_full_bar[as]);
             if (++s == stages) { s = 0; ph ^= 1; }
           }
           if (++as == 2) { as = 0; aph ^= 1; }
@@ -240,15 +274,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
             const uint64_t koff = (uint64_t)((k * 32) >> 4);   // 16 bf16 = 32 bytes along K inside the swizzle atom
-            umma_bf16(tacc, da_hi + koff, dw_hi + koff, IDESC, (it > 0 || k > 0) ? 1u : 0u);
+            mma(tacc, da_hi + koff, dw_hi + koff, (it > 0 || k > 0) ? 1u : 0u);
             if (NSPLIT == 3) {
               const uint64_t da_lo = umma_desc_sw128(sa + A_BYTES), dw_lo = umma_desc_sw128(sw + W_BYTES);
-              umma_bf16(tacc, da_lo + koff, dw_hi + koff, IDESC, 1u);
-              umma_bf16(tacc, da_hi + koff, dw_lo + koff, IDESC, 1u);
+              mma(tacc, da_lo + koff, dw_hi + koff, 1u);
+              mma(tacc, da_hi + koff, dw_lo + koff, 1u);
             }
           }
-          umma_commit(&empty_bar[s]);                 // frees the stage once the MMAs above have read it
-          if (it == iters - 1) umma_commit(&tmem_full_bar[as]);
+          commit(&empty_bar[s]);                      // frees the stage (in both CTAs of a pair) once the MMAs above have read it
+          if (it == iters - 1) commit(&tmem_full_bar[as]);
           if (++s == stages) { s = 0; ph ^= 1; }
         }
         if (++as == 2) { as = 0; aph ^= 1; }
@@ -262,14 +296,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const int xl = r % a.bw, yl = (r / a.bw) % a.bh, fl = r / (a.bw * a.bh);
     int as = 0;
     uint32_t aph = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    // the accumulator stage goes back to the MMA issuer: the leader's barrier collects the epilogue warps of both CTAs of a pair
+    const uint32_t tmem_empty_addr0 = CG == 2 ? mapa_u32(smem_u32(&tmem_empty_bar[0]), 0) : 0u;
+    for (int tile = unit0; tile < total_tiles; tile += unit_step) {
       const int z = tile / tiles_mn, rem = tile - z * tiles_mn;
-      const int mt = rem / a.tiles_n, nt = rem - mt * a.tiles_n;
+      const int mg = rem / a.tiles_n, nt = rem - mg * a.tiles_n;
+      const int mt = mg * CG + (int)crank;
       const int tf = mt / txy, r2 = mt - tf * txy;
       const int ty = r2 / a.tiles_x, tx = r2 - ty * a.tiles_x;
       const int f = tf * a.bf + fl, y = ty * a.bh + yl, x = tx * a.bw + xl;
       const int n0 = nt * BN;
-      const bool valid = (f < a.F) && (y < a.H) && (x < a.W);
+      const bool valid = (mt < a.tiles_m) && (f < a.F) && (y < a.H) && (x < a.W);
       const TcSub& sb = a.sub[a.nsub > 1 ? z : 0];
       const int oy = y * a.ymul + sb.yadd, ox = x * a.xmul + sb.xadd;
       const size_t opix = ((size_t)f * a.Ho + (size_t)oy) * a.Wo + (size_t)ox;
@@ -409,15 +446,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 hi[j] = *(const uint32_t*)&hh;
                 lo[j] = *(const uint32_t*)&ll;
               }
-              uint4* ph4 = (uint4*)((__nv_bfloat16*)od.out + ocol);
+              // a lane owns 64 contiguous bytes of its row per plane: 256-bit stores (STG.256) write whole 32-byte sectors, so L2 sees no
+              // partially written sectors (the 16-byte version left every sector to be completed by a second store instruction)
+              __nv_bfloat16* ph = (__nv_bfloat16*)od.out + ocol;
+              __nv_bfloat16* pl = od.mode == OUT_BF16_SPLIT ? (__nv_bfloat16*)od.out_lo + ocol : nullptr;
+              const bool wide = EPI_CHUNK == 32 && ncols == 32 && ((((uintptr_t)ph) | ((uintptr_t)pl)) & 31) == 0;
+              if (wide) {
 #pragma unroll
-              for (int j = 0; j < EPI_CHUNK / 8; ++j)
-                if (8 * j < ncols) ph4[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-              if (od.mode == OUT_BF16_SPLIT) {
-                uint4* pl4 = (uint4*)((__nv_bfloat16*)od.out_lo + ocol);
+                for (int j = 0; j < EPI_CHUNK / 16; ++j) {
+                  st_global_v8(ph + 16 * j, hi + 8 * j);
+                  if (pl) st_global_v8(pl + 16 * j, lo + 8 * j);
+                }
+              } else {
+                uint4* ph4 = (uint4*)ph;
 #pragma unroll
                 for (int j = 0; j < EPI_CHUNK / 8; ++j)
-                  if (8 * j < ncols) pl4[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                  if (8 * j < ncols) ph4[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                if (pl) {
+                  uint4* pl4 = (uint4*)pl;
+#pragma unroll
+                  for (int j = 0; j < EPI_CHUNK / 8; ++j)
+                    if (8 * j < ncols) pl4[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                }
               }
             }
           }
@@ -426,15 +476,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       // all TMEM reads of this warp are complete (wait::ld above): hand the accumulator stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_cluster(tmem_empty_addr0 + (uint32_t)(as * sizeof(uint64_t)));
+        else mbar_arrive(&tmem_empty_bar[as]);
+      }
       if (++as == 2) { as = 0; aph ^= 1; }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();      // the leader's MMAs read the peer's shared memory: nobody leaves before both are done
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if constexpr (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -497,11 +552,11 @@ static int sm_count() {
   return n[slot];
 }
 
-template <int BN, int NSPLIT, bool FUSED, bool HALO>
+template <int BN, int NSPLIT, bool FUSED, bool HALO, int CG>
 static void launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo, TcArgs& a,
                       cudaStream_t st) {
-  constexpr int STAGE_BYTES = HALO ? (NSPLIT == 3 ? 2 : 1) * (TC_HALO_A_BYTES + 3 * BN * TC_BK * 2)
-                                   : (NSPLIT == 3 ? 2 : 1) * (TC_BM * TC_BK * 2 + BN * TC_BK * 2);
+  constexpr int STAGE_BYTES = HALO ? (NSPLIT == 3 ? 2 : 1) * (TC_HALO_A_BYTES + 3 * (BN / CG) * TC_BK * 2)
+                                   : (NSPLIT == 3 ? 2 : 1) * (TC_BM * TC_BK * 2 + (BN / CG) * TC_BK * 2);
   int stages = (int)std::min<size_t>(8, TC_SMEM_BUDGET / STAGE_BYTES);
   IPK_CHECK(stages >= 2, IPK_ERR_UNSUPPORTED, "conv_tc: pipeline needs at least two stages (stage %d bytes)", STAGE_BYTES);
   a.stages = stages;
@@ -509,12 +564,13 @@ static void launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CU
   static bool attr_set[IPK_MAX_DEVICES] = {false};      // function attributes are per device
   const int slot = current_device_slot();
   if (!attr_set[slot]) {
-    IPK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, NSPLIT, FUSED, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TC_SMEM_BUDGET + 1024 + TC_EPI_WARPS * TC_EPI_STAGE_BYTES)));
+    IPK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, NSPLIT, FUSED, HALO, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TC_SMEM_BUDGET + 1024 + TC_EPI_WARPS * TC_EPI_STAGE_BYTES)));
     attr_set[slot] = true;
   }
-  const long long total = (long long)a.tiles_m * a.tiles_n * (a.nsub > 1 ? a.nsub : a.nsplit);
-  const unsigned grid = (unsigned)std::min<long long>(total, sm_count());     // persistent: one CTA per SM
-  launch_k(conv_tc_kernel<BN, NSPLIT, FUSED, HALO>, dim3(grid), dim3(TC_THREADS), smem, st, a_hi, a_lo, w_hi, w_lo, a);
+  const long long units = (long long)cdiv(a.tiles_m, CG) * a.tiles_n * (a.nsub > 1 ? a.nsub : a.nsplit);
+  // persistent: one CTA per SM (CG = 2: one CTA pair per SM pair, grid a multiple of the cluster size)
+  const unsigned grid = (unsigned)std::min<long long>(units * CG, (sm_count() / CG) * CG);
+  launch_kc(conv_tc_kernel<BN, NSPLIT, FUSED, HALO, CG>, dim3(grid), dim3(TC_THREADS), smem, st, CG, a_hi, a_lo, w_hi, w_lo, a);
 }
 
 static int conv_tc_impl(const ConvW& w, const ConvIn& in, const ConvOut& out, const ConvSub* subs, int nsub, int nsplit, cudaStream_t st) {
@@ -607,19 +663,26 @@ static int conv_tc_impl(const ConvW& w, const ConvIn& in, const ConvOut& out, co
       if (cost < best) { best = cost; BN = bn; }
     }
   }
+  a.tiles_m = a.tiles_x * a.tiles_y * tiles_f;
+  // CTA pairs (cta_group::2): two consecutive M tiles share one N tile and each CTA stages half of its weights (IPK_TC_CTA2=0 disables,
+  // =2 also pairs short main loops).
+  static const int cta2_env = []() { const char* e = getenv("IPK_TC_CTA2"); return e ? atoi(e) : 1; }();
+  // Measured on B200 (profiles/r02_cta2_ab.md): a win where the W tile dominates the stage bytes and the main loop is long (NICE conv2
+  // 19.2 -> 16.9 ms per step, N = K = 2048); a loss for narrow N tiles (A traffic dominates, and the pair's lock-step epilogue hand-off
+  // costs more than the halved W fetch saves) and for short main loops (NICE conv1, K <= 192: epilogue-bound).
+  const int CG = (cta2_env > 0 && a.tiles_m >= 2 && BN == 256 && (cta2_env > 1 || max_taps * a.nkb >= 8)) ? 2 : 1;
   long long wd[2] = {w.Kpad, (long long)w.ntaps * w.Npad};
   long long wsb[1] = {(long long)w.Kpad * 2};
-  int wb[2] = {TC_BK, BN};
+  int wb[2] = {TC_BK, BN / CG};
   CUtensorMap mW_hi = make_map(w.w_hi, 2, wd, wsb, wb);
   CUtensorMap mW_lo = split ? make_map(w.w_lo, 2, wd, wsb, wb) : mW_hi;
 
-  a.tiles_m = a.tiles_x * a.tiles_y * tiles_f;
   a.tiles_n = cdiv(w.Npad, BN);
   a.nsplit = nsplit;
   const bool fused = a.res != nullptr || a.stats != nullptr;
   // halo mode: full 3x3 tap set on a 128-wide image, one image row per tile, 64-column N tiles (the decoder's last conv2)
   static const int halo_env = []() { const char* e = getenv("IPK_TC_HALO"); return e ? atoi(e) : 2; }();     // 0 = off
-  bool halo = halo_env > 0 && nsub == 1 && nsplit == 1 && in.W == TC_BM && a.bw == TC_BM && subs[0].taps.n == 9 && BN == 64;
+  bool halo = halo_env > 0 && nsub == 1 && nsplit == 1 && in.W == TC_BM && a.bw == TC_BM && subs[0].taps.n == 9 && (BN == 64 || BN == 32);
   if (halo)
     for (int i = 0; i < 9; ++i)
       halo = halo && subs[0].taps.dy[i] == i / 3 - 1 && subs[0].taps.dx[i] == i % 3 - 1 && subs[0].taps.widx[i] == i;
@@ -628,32 +691,36 @@ static int conv_tc_impl(const ConvW& w, const ConvIn& in, const ConvOut& out, co
     int hb[4] = {TC_BK, 130, 1, 1};
     const CUtensorMap hA_hi = make_map(ahi, 4, ad, as, hb);
     const CUtensorMap hA_lo = split ? make_map((const __nv_bfloat16*)in.p_lo + in.coff, 4, ad, as, hb) : hA_hi;
-    if (fused) {
-      if (split) launch_tc<64, 3, true, true>(hA_hi, hA_lo, mW_hi, mW_lo, a, st);
-      else launch_tc<64, 1, true, true>(hA_hi, hA_lo, mW_hi, mW_lo, a, st);
-    } else {
-      if (split) launch_tc<64, 3, false, true>(hA_hi, hA_lo, mW_hi, mW_lo, a, st);
-      else launch_tc<64, 1, false, true>(hA_hi, hA_lo, mW_hi, mW_lo, a, st);
-    }
+#define IPK_TC_LAUNCH(bn, halo_, cg, mAh, mAl)                                              \
+    do {                                                                                  \
+      if (fused) {                                                                        \
+        if (split) launch_tc<bn, 3, true, halo_, cg>(mAh, mAl, mW_hi, mW_lo, a, st);      \
+        else launch_tc<bn, 1, true, halo_, cg>(mAh, mAl, mW_hi, mW_lo, a, st);            \
+      } else {                                                                            \
+        if (split) launch_tc<bn, 3, false, halo_, cg>(mAh, mAl, mW_hi, mW_lo, a, st);     \
+        else launch_tc<bn, 1, false, halo_, cg>(mAh, mAl, mW_hi, mW_lo, a, st);           \
+      }                                                                                   \
+    } while (0)
+    if (BN == 32) IPK_TC_LAUNCH(32, true, 1, hA_hi, hA_lo);        // the decoder's out_conv (N = 3)
+    else if (CG == 2) IPK_TC_LAUNCH(64, true, 2, hA_hi, hA_lo);
+    else IPK_TC_LAUNCH(64, true, 1, hA_hi, hA_lo);
     return nsplit;
   }
-#define IPK_TC_CASE(bn)                                                                 \
-  case bn:                                                                              \
-    if (fused) {                                                                        \
-      if (split) launch_tc<bn, 3, true, false>(mA_hi, mA_lo, mW_hi, mW_lo, a, st);      \
-      else launch_tc<bn, 1, true, false>(mA_hi, mA_lo, mW_hi, mW_lo, a, st);            \
-    } else {                                                                            \
-      if (split) launch_tc<bn, 3, false, false>(mA_hi, mA_lo, mW_hi, mW_lo, a, st);     \
-      else launch_tc<bn, 1, false, false>(mA_hi, mA_lo, mW_hi, mW_lo, a, st);           \
-    }                                                                                   \
-    break;
-  switch (BN) {
-    IPK_TC_CASE(32)
-    IPK_TC_CASE(64)
-    IPK_TC_CASE(128)
-    IPK_TC_CASE(256)
+  if (CG == 2) {
+    switch (BN) {
+      case 64: IPK_TC_LAUNCH(64, false, 2, mA_hi, mA_lo); break;
+      case 128: IPK_TC_LAUNCH(128, false, 2, mA_hi, mA_lo); break;
+      default: IPK_TC_LAUNCH(256, false, 2, mA_hi, mA_lo); break;
+    }
+  } else {
+    switch (BN) {
+      case 32: IPK_TC_LAUNCH(32, false, 1, mA_hi, mA_lo); break;
+      case 64: IPK_TC_LAUNCH(64, false, 1, mA_hi, mA_lo); break;
+      case 128: IPK_TC_LAUNCH(128, false, 1, mA_hi, mA_lo); break;
+      default: IPK_TC_LAUNCH(256, false, 1, mA_hi, mA_lo); break;
+    }
   }
-#undef IPK_TC_CASE
+#undef IPK_TC_LAUNCH
   return nsplit;
 }
 

@@ -427,7 +427,11 @@ extern "C" int ipk_fs_finalize(ipk_fs* d, void* stream) {
     fe = std::max(fe, (size_t)ub.s_in * ub.s_in * ub.Cin);
     d->blocks.push_back(ub);
   }
-  if (dc[d->nd - 1] == OUT_CONV_CIN) {
+  // Final 3x3 64 -> 3 conv.  On 128-wide frames the tensor-core engine runs it in halo mode (one 130-pixel row box per input row, the
+  // three dx taps as shifted descriptors): the contraction is ~0.2 ms of tcgen05 time for 1 024 frames, so the layer is bounded by
+  // reading its input once, where the fp32 FFMA kernel (out_conv.cu) is issue-bound at ~3x that.  IPK_OUTCONV_TC=0 keeps the FFMA kernel.
+  static const bool outconv_tc = []() { const char* e = getenv("IPK_OUTCONV_TC"); return !(e && e[0] == '0'); }();
+  if (dc[d->nd - 1] == OUT_CONV_CIN && !(outconv_tc && eng != IPK_PREC_FP32_SIMT && d->S == 128)) {
     const std::string p = "gen.out_conv.conv.";
     float* packed = d->pool.alloc<float>(OUT_CONV_PACKED_FLOATS);
     const float* bias = (const float*)fneed(d, p + "bias", 3).p;

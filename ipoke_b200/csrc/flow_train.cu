@@ -387,6 +387,94 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 
 static inline int gridn(long long n) { return (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, 148LL * 16)); }
 
+// ------------------------------------------------------------------------------------------------ small fp32 GEMM (MCF networks)
+// The 800 masked-conv flows' contractions are tiny (M = B*64 rows, N, K <= 384): on the persistent tcgen05 engine each of them paid
+// 16-50 us of fixed cost plus two operand-conversion passes for 1-2 us of math.  This kernel reads the fp32 tensors where they lie
+// (the parameters in their checkpoint layout, activations row-major), with generic strides so that one kernel serves
+//   forward  C[m][n] = sum_k A[m][k] W[n][k] (+ bias)        dgrad  C[m][k] = sum_n dY[m][n] W[n][k]
+//   wgrad    C[n][k] (+)= sum_m dY[m][n] X[m][k]             (split over the M reduction, fp32 atomics)
+// 64x64 output tile per CTA, 16-deep K slices staged in shared memory, 4x4 register tile per thread, plain FFMA: exact fp32.
+struct SgemmArgs {
+  const float* A; long long sAi, sAk;     // A(i, k) = A[i*sAi + k*sAk]
+  const float* B; long long sBj, sBk;     // B(j, k) = B[j*sBj + k*sBk]
+  float* C; long long ldc;                // C[i*ldc + j]
+  const float* bias;                      // [J] added to every row (ksplit == 1 only), or null
+  int I, J, K, kchunk, atomic;            // blockIdx.z covers k in [z*kchunk, (z+1)*kchunk); atomic: atomicAdd into C
+};
+__global__ void __launch_bounds__(256) sgemm_kernel(const SgemmArgs a) {
+  __shared__ float As[16][68], Bs[16][68];
+  const int tid = threadIdx.x;
+  const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+  const int k_begin = blockIdx.z * a.kchunk, k_end = min(a.K, k_begin + a.kchunk);
+  const int ti = tid >> 4, tj = tid & 15;          // thread computes rows ti*4..+3, cols tj*4..+3
+  // loader mapping: 1 024 elements per tile, 4 per thread; the unit-stride axis runs across consecutive threads
+  const bool a_kfast = a.sAk == 1, b_kfast = a.sBk == 1;
+  float acc[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+  for (int k0 = k_begin; k0 < k_end; k0 += 16) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = tid + e * 256;
+      {
+        const int kk = a_kfast ? (idx & 15) : (idx >> 6), ii = a_kfast ? (idx >> 4) : (idx & 63);
+        const int gi = i0 + ii, gk = k0 + kk;
+        As[kk][ii] = (gi < a.I && gk < k_end) ? a.A[gi * a.sAi + gk * a.sAk] : 0.f;
+      }
+      {
+        const int kk = b_kfast ? (idx & 15) : (idx >> 6), jj = b_kfast ? (idx >> 4) : (idx & 63);
+        const int gj = j0 + jj, gk = k0 + kk;
+        Bs[kk][jj] = (gj < a.J && gk < k_end) ? a.B[gj * a.sBj + gk * a.sBk] : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      const float4 av = *(const float4*)&As[kk][ti * 4];
+      const float4 bv = *(const float4*)&Bs[kk][tj * 4];
+      const float ar[4] = {av.x, av.y, av.z, av.w}, br[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(ar[r], br[c], acc[r][c]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int gi = i0 + ti * 4 + r;
+    if (gi >= a.I) continue;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int gj = j0 + tj * 4 + c;
+      if (gj >= a.J) continue;
+      float v = acc[r][c];
+      if (a.atomic) atomicAdd(&a.C[gi * a.ldc + gj], v);
+      else a.C[gi * a.ldc + gj] = a.bias ? v + a.bias[gj] : v;
+    }
+  }
+}
+// ksplit > 1: the reduction is split over blockIdx.z and accumulated with atomics -- C must be zeroed by the caller (zero_first does it)
+static void sgemm(const float* A, long long sAi, long long sAk, const float* B, long long sBj, long long sBk, float* C, long long ldc, const float* bias,
+                  int I, int J, int K, int ksplit, bool zero_first, cudaStream_t st) {
+  SgemmArgs a{A, sAi, sAk, B, sBj, sBk, C, ldc, bias, I, J, K, 0, 0};
+  ksplit = std::max(1, std::min(ksplit, cdiv(K, 16)));
+  a.kchunk = round_up(cdiv(K, ksplit), 16);
+  ksplit = cdiv(K, a.kchunk);
+  a.atomic = ksplit > 1 ? 1 : 0;
+  if (a.atomic) {
+    IPK_CHECK(bias == nullptr, IPK_ERR_STATE, "sgemm: bias with split-K");
+    if (zero_first) {
+      IPK_CHECK(ldc == J, IPK_ERR_STATE, "sgemm: zero_first needs a dense output");
+      IPK_CUDA(cudaMemsetAsync(C, 0, (size_t)I * J * sizeof(float), st));
+    }
+  }
+  sgemm_kernel<<<dim3(cdiv(J, 64), cdiv(I, 64), ksplit), 256, 0, st>>>(a);
+  IPK_LAUNCH_CHECK();
+}
+
 struct McfTrain {
   std::string p; int C, Cp, order, hid, K1, C2;
   TapOff taps;
@@ -422,7 +510,7 @@ struct ipk_flowtrain {
   // workspace (M = max_batch * 64 rows)
   float *tape = nullptr, *G = nullptr, *Gtmp = nullptr, *logdet = nullptr, *Ecache = nullptr;
   float *c1 = nullptr, *E = nullptr, *P = nullptr, *dP = nullptr, *a1 = nullptr, *a2 = nullptr, *da = nullptr, *col = nullptr, *dcol = nullptr, *stack = nullptr,
-        *wout = nullptr, *cond_nhwc = nullptr, *x_in = nullptr, *cond_in = nullptr, *loss_dev = nullptr, *z_dev = nullptr, *dld = nullptr, *dz_in = nullptr;
+        *wout = nullptr, *dstack = nullptr, *cond_nhwc = nullptr, *x_in = nullptr, *cond_in = nullptr, *loss_dev = nullptr, *z_dev = nullptr, *dld = nullptr, *dz_in = nullptr;
   bool use_graph = true;
   int fwd_batch = 0;                  // batch of the last ipk_flowtrain_forward whose tape is still valid
   float* slices = nullptr;            // [9][M][ldP] split-K partial sums of the NICE conv3
@@ -535,15 +623,18 @@ static void wgrad(ipk_flowtrain* f, int N, const float* X, int ldx, int Kx, int 
 namespace ipk {
 
 // ---- network forward passes (also the recomputation inside backward) ------------------------------------------------------
-// MCFBlock on the taped input x [M][C0]: leaves c1 (pre-ELU hidden), E = [ELU(c1) | ELU(cond)] and P = params in the workspace
+// MCFBlock on the taped input x [M][C0]: leaves c1 (pre-ELU hidden), E = [ELU(c1) | ELU(cond)] and P = params in the workspace.
+// Both contractions read the parameters where they lie: the shifted conv is an im2col (channel-major columns c*taps + t, the OIHW
+// order) followed by a GEMM against the raw weight tensor, the 1x1 a GEMM against the weight-normed matrix of this step.
 static void mcf_net(ipk_flowtrain* f, const McfTrain& m, const float* x, int B, cudaStream_t st) {
   const long long M = (long long)B * 64;
-  to_operand(f, x, f->C0, 0, M, m.C, m.Cp, f->opA, f->opA_lo, st);
-  conv8(m.ws, f->opA, f->opA_lo, m.Cp, B, taplist(m.taps, 1), f->c1, f->ldc1, nullptr, st);
+  const int Kc = m.taps.n * m.C;
+  im2col_taps_kernel<<<gridn(M * Kc), 256, 0, st>>>(x, f->C0, nullptr, m.C, m.taps, 1, f->stack, f->ldstack, Kc, M);
+  IPK_LAUNCH_CHECK();
+  sgemm(f->stack, f->ldstack, 1, m.v_ws, Kc, 1, f->c1, f->ldc1, nullptr, (int)M, m.hid, Kc, 1, false, st);
   elu_concat_kernel<<<gridn(M * m.K1), 256, 0, st>>>(f->c1, f->ldc1, m.hid, f->Ecache, f->hch, f->E, f->ldE, M);
   IPK_LAUNCH_CHECK();
-  to_operand(f, f->E, f->ldE, 0, M, m.K1, round_up(m.K1, 8), f->opA, f->opA_lo, st);
-  gemm(m.w1, f->opA, f->opA_lo, round_up(m.K1, 8), M, f->P, f->ldP, m.w1.bias, ACT_NONE, st);
+  sgemm(f->E, f->ldE, 1, m.weff, m.K1, 1, f->P, f->ldP, m.b1, (int)M, m.C2, m.K1, 1, false, st);
 }
 // NICEConvBlock on the z channels of x: leaves col (im2col of z), a1, a2 (post-ELU) and P in the workspace
 static void nice_net(ipk_flowtrain* f, const NiceTrain& n, const float* x, int B, cudaStream_t st) {
@@ -618,35 +709,25 @@ static void mcf_backward(ipk_flowtrain* f, McfTrain& m, int ai, const float* x, 
   IPK_LAUNCH_CHECK();
   colsum_kernel<<<m.C2, 256, 0, st>>>(f->dP, f->ldP, M, m.g_b1);
   IPK_LAUNCH_CHECK();
-  // 1x1: dW_eff = dP^T E  -> (dv, dg);  dE = dP W_eff
-  to_operand_T(f, f->dP, f->ldP, 0, M, m.C2, f->opT, f->opT_lo, f->opT_elems, st);
-  wgrad(f, m.C2, f->E, f->ldE, m.K1, M, f->wout, f->ldwout, st);
-  wn_bwd_kernel<<<m.C2, 128, 0, st>>>(f->wout, f->ldwout, 1, 0, 1, m.v1, m.g1, m.g_v1, m.g_g1, m.K1);
+  const int Kc = m.taps.n * m.C;
+  const int ks = std::max(1, M / 128);                // split of the M reduction of the weight gradients
+  // 1x1: dW_eff[o][k] = sum_m dP[m][o] E[m][k]  -> (dv, dg);  dE = dP W_eff (only the first hid columns feed back)
+  sgemm(f->dP, 1, f->ldP, f->E, 1, f->ldE, f->wout, m.K1, nullptr, m.C2, m.K1, M, ks, true, st);
+  wn_bwd_kernel<<<m.C2, 128, 0, st>>>(f->wout, m.K1, 1, 0, 1, m.v1, m.g1, m.g_v1, m.g_g1, m.K1);
   IPK_LAUNCH_CHECK();
-  const int C2p = round_up(m.C2, 8);
-  to_operand(f, f->dP, f->ldP, 0, M, m.C2, C2p, f->opA, f->opA_lo, st);
-  gemm(m.w1T, f->opA, f->opA_lo, C2p, M, f->E, f->ldE, nullptr, ACT_NONE, st);              // E <- dE (first hid columns are used)
+  sgemm(f->dP, f->ldP, 1, m.weff, 1, m.K1, f->E, f->ldE, nullptr, M, m.hid, m.C2, 1, false, st);       // E[:, :hid] <- dE
   // dc1 = dE * ELU'(c1): ELU output of c1 recomputed in place
   elu_kernel<<<gridn((long long)M * f->ldc1), 256, 0, st>>>(f->c1, f->c1, (long long)M * f->ldc1);
   IPK_LAUNCH_CHECK();
   elu_bwd_kernel<<<gridn((long long)M * m.hid), 256, 0, st>>>(f->E, f->ldE, f->c1, f->ldc1, m.hid, M);
   IPK_LAUNCH_CHECK();
-  // shifted conv: dWs[n][c][t] = sum_m dc1[m][n] x[m + delta_t][c];  dx += conv^T(dc1)
-  im2col_taps_kernel<<<gridn((long long)M * m.taps.n * m.C), 256, 0, st>>>(x, f->C0, nullptr, m.C, m.taps, 1, f->stack, f->ldstack, m.taps.n * m.C, M);
+  // shifted conv: dWs[n][c*taps + t] = sum_m dc1[m][n] x[m + delta_t][c] (straight into the OIHW gradient);  dx += conv^T(dc1)
+  im2col_taps_kernel<<<gridn((long long)M * Kc), 256, 0, st>>>(x, f->C0, nullptr, m.C, m.taps, 1, f->stack, f->ldstack, Kc, M);
   IPK_LAUNCH_CHECK();
-  to_operand_T(f, f->stack, f->ldstack, 0, M, m.taps.n * m.C, f->opT, f->opT_lo, f->opT_elems, st);
-  wgrad(f, m.taps.n * m.C, f->E, f->ldE, m.hid, M, f->wout, f->ldwout, st);                  // wout[(c*nt + t)][n]
-  relayout_kernel<<<gridn((long long)m.hid * m.C * m.taps.n), 256, 0, st>>>(f->wout, 1, f->ldwout, 0, 1, m.g_ws, m.C * m.taps.n,
-                                                                         (long long)m.hid * m.C * m.taps.n);
+  sgemm(f->E, 1, f->ldE, f->stack, 1, f->ldstack, m.g_ws, Kc, nullptr, m.hid, Kc, M, ks, true, st);
+  sgemm(f->E, f->ldE, 1, m.v_ws, 1, Kc, f->dstack, f->ldstack, nullptr, M, Kc, m.hid, 1, false, st);      // d(im2col rows)
+  col2im_taps_kernel<<<gridn((long long)M * m.C), 256, 0, st>>>(f->dstack, f->ldstack, nullptr, m.C, m.taps, f->G, f->C0, M);
   IPK_LAUNCH_CHECK();
-  to_operand(f, f->E, f->ldE, 0, M, m.hid, round_up(m.hid, 8), f->opA, f->opA_lo, st);
-  conv8(m.wsT, f->opA, f->opA_lo, round_up(m.hid, 8), B, taplist(m.taps, -1), f->dcol, f->ldcol, nullptr, st);
-  // G[:, :C] += dx_conv
-  {
-    TapOff one; one.n = 1; one.dy[0] = 0; one.dx[0] = 0;
-    col2im_taps_kernel<<<gridn((long long)M * m.C), 256, 0, st>>>(f->dcol, f->ldcol, nullptr, m.C, one, f->G, f->C0, M);
-    IPK_LAUNCH_CHECK();
-  }
 }
 
 static void nice_backward(ipk_flowtrain* f, NiceTrain& n, int ai, const float* x, int B, cudaStream_t st) {
@@ -777,11 +858,7 @@ extern "C" int ipk_flowtrain_finalize(ipk_flowtrain* f, void* stream) {
         const TrainRef& b = tneed(f, o.prefix + "net.conv1x1.conv.bias", m.C2, IPK_F32);
         m.v_ws = (const float*)ws.p; m.v1 = (const float*)v.p; m.g1 = (const float*)g.p; m.b1 = (const float*)b.p;
         m.g_ws = ws.g; m.g_v1 = v.g; m.g_g1 = g.g; m.g_b1 = b.g;
-        m.ws = conv_alloc(f->pool, eng, m.taps.n, o.C, m.hid, false);
-        m.wsT = conv_alloc(f->pool, eng, m.taps.n, m.hid, o.C, false);
-        m.w1 = conv_alloc(f->pool, eng, 1, m.K1, m.C2, true);
-        m.w1T = conv_alloc(f->pool, eng, 1, m.C2, m.K1, false);
-        m.weff = f->pool.alloc<float>((size_t)m.C2 * m.K1);
+        m.weff = f->pool.alloc<float>((size_t)m.C2 * m.K1);     // the MCF contractions run on sgemm: no packed operands
         Cmax = std::max(Cmax, o.C);
         t.a = (int)f->mcfs.size();
         f->mcfs.push_back(m);
@@ -827,11 +904,6 @@ extern "C" int ipk_flowtrain_finalize(ipk_flowtrain* f, void* stream) {
       conv_pack_job(dst, 0, s2, iota(ntaps), jobs.data() + jobs.size() - jb);
     };
     for (McfTrain& m : f->mcfs) {
-      const int kt = m.taps.n;
-      add(m.ws, m.v_ws, m.hid, m.C, kt, false);
-      add(m.wsT, m.v_ws, m.C, m.hid, kt, true);
-      add(m.w1, m.weff, m.C2, m.K1, 1, false);
-      add(m.w1T, m.weff, m.K1, m.C2, 1, true);
       wn.push_back(WnJob{m.v1, m.g1, m.weff, m.C2, m.K1});
       f->wn_maxrows = std::max(f->wn_maxrows, m.C2);
     }
@@ -870,7 +942,7 @@ extern "C" int ipk_flowtrain_finalize(ipk_flowtrain* f, void* stream) {
   auto rb = [](size_t b) { return (b + 255) / 256 * 256; };
   const size_t slot = M * f->C0;
   size_t bytes = rb((f->ops.size() + 1) * slot * 4) + 5 * rb(slot * 4) + rb(f->cfg.max_batch * 4) + rb(f->cfg.max_batch * 4) + 3 * rb(M * hch * 4) + 4096 + rb(M * f->ldc1 * 4) + rb(M * f->ldE * 4) +
-                 2 * rb(M * f->ldP * 4) + 3 * rb(M * Hd * 4) + 2 * rb(M * f->ldcol * 4) + rb(M * f->ldstack * 4) + rb(wout_rows * f->ldwout * 4) + rb(9 * M * f->ldP * 4) +
+                 2 * rb(M * f->ldP * 4) + 3 * rb(M * Hd * 4) + 2 * rb(M * f->ldcol * 4) + 2 * rb(M * f->ldstack * 4) + rb(wout_rows * f->ldwout * 4) + rb(9 * M * f->ldP * 4) +
                  2 * rb(f->opA_elems * 4) + rb(f->opT_elems * 4) + rb(f->opW_elems * 4) + (1 << 16);
   f->ws.init(bytes);
   f->tape = f->ws.alloc<float>((f->ops.size() + 1) * slot);
@@ -884,6 +956,7 @@ extern "C" int ipk_flowtrain_finalize(ipk_flowtrain* f, void* stream) {
   f->a1 = f->ws.alloc<float>(M * Hd); f->a2 = f->ws.alloc<float>(M * Hd); f->da = f->ws.alloc<float>(M * Hd);
   f->col = f->ws.alloc<float>(M * f->ldcol); f->dcol = f->ws.alloc<float>(M * f->ldcol);
   f->stack = f->ws.alloc<float>(M * f->ldstack);
+  f->dstack = f->ws.alloc<float>(M * f->ldstack);
   f->wout = f->ws.alloc<float>(wout_rows * f->ldwout);
   f->slices = f->ws.alloc<float>(9 * M * f->ldP);
   // operand scratch: fp32 rows (SIMT) or two bf16 planes (tensor cores) share one allocation of 4 bytes per element
@@ -920,7 +993,6 @@ static void train_repack_and_forward(ipk_flowtrain* f, int B, cudaStream_t st) {
     wn_apply_multi_kernel<<<dim3(f->wn_maxrows, f->n_wn_jobs), 128, 0, st>>>(f->d_wn_jobs);
     IPK_LAUNCH_CHECK();
     conv_pack_run_jobs(f->d_pack_jobs, f->n_pack_jobs, st);
-    for (McfTrain& m : f->mcfs) conv_pack_bias(m.w1, 0, m.b1, m.C2, 0.f, st);
     for (NiceTrain& n : f->nices) conv_pack_bias(n.c3, 0, n.b3, n.N3, 0.f, st);
   }
   nchw_to_nhwc(f->x_in, f->tape, B, f->C0, 64, f->C0, st);
