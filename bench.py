@@ -535,7 +535,7 @@ class TrainRun:
         _lib = self.ipk._lib
         _lib.prof_enable(True)
         self.step()
-        rep = {k: round(t, 3) for k, (c, t) in _lib.prof_report().items() if k.startswith(("train.", "enc."))}
+        rep = {k: {"n": c, "ms": round(t, 3)} for k, (c, t) in _lib.prof_report().items() if k.startswith(("train.", "enc."))}
         _lib.prof_enable(False)
         return rep
 

@@ -104,6 +104,14 @@ typedef struct ipk_cenc_config {
   int32_t max_batch;
 } ipk_cenc_config;
 
+/* I3D(num_classes, 'rgb') of the in-repo Frechet video distance (utils/metrics.py:999-1105). */
+typedef struct ipk_i3d_config {
+  int32_t num_classes;                /* 400; a multiple of 8                                                 */
+  int32_t max_batch;
+  int32_t max_frames;                 /* >= 9: the (2,7,7) average pool needs two time steps after 3 halvings */
+  int32_t precision;                  /* IPK_PREC_FP32_SPLIT (bf16x3 tcgen05, default) or IPK_PREC_BF16        */
+} ipk_i3d_config;
+
 /* Devices: a plan belongs to the CUDA device that was current when it was created (its packed weights and workspaces live there);
  * call every entry point of that plan with the same device current.  One process may hold plans on several devices: one-time setup
  * (kernel attributes, SM counts, the staging buffers of ipk_sample_host, graph-capture streams) is kept per device ordinal. */
@@ -111,6 +119,7 @@ typedef struct ipk_flow ipk_flow;
 typedef struct ipk_fs ipk_fs;
 typedef struct ipk_enc ipk_enc;
 typedef struct ipk_cenc ipk_cenc;
+typedef struct ipk_i3d ipk_i3d;
 
 int ipk_version(void);
 const char* ipk_last_error(void);
@@ -169,6 +178,19 @@ int ipk_cenc_finalize(ipk_cenc* e, void* stream);
 /* x[B,nf_in,S,S] -> out[B,nf_max,8,8] (after the bottleneck) and, if non-null, mean[B,nf_max,8,8] (before it) */
 int ipk_cenc_forward(ipk_cenc* e, const float* x, float* out, float* mean, int32_t B, void* stream);
 int ipk_cenc_destroy(ipk_cenc* e);
+
+/* ---- I3D feature extractor of the in-repo FVD: I3D.forward, utils/metrics.py:1079-1105 (Unit3Dpy :857-937 with
+ *      TF-SAME padding :814-842, MaxPool3dTFPadding :940-960, Mixed :963-997); tensors by the reference's state-dict names
+ *      ("conv3d_1a_7x7.conv3d.weight", "mixed_3b.branch_1.1.batch3d.running_var", ...).  BatchNorm is folded at finalize (eval mode). ---- */
+int ipk_i3d_create(const ipk_i3d_config* cfg, ipk_i3d** out);
+int ipk_i3d_set_tensor(ipk_i3d* m, const char* name, const void* dev_ptr, int64_t numel, int dtype);
+int ipk_i3d_finalize(ipk_i3d* m, void* stream);
+/* x[B,3,T,224,224] fp32 (the layout get_activations feeds, utils/metrics.py:726) -> logits[B,num_classes] (the second output of I3D.forward) */
+int ipk_i3d_forward(ipk_i3d* m, const float* x, float* logits, int32_t B, int32_t T, void* stream);
+int ipk_i3d_destroy(ipk_i3d* m);
+/* preprocess (utils/metrics.py:786-802) of one set of frames: videos[n_frames,3,S,S] -> out[n_frames,3,224,224], bilinear with
+ * align_corners; the (x + 1) / 2 map is applied when any resized value of the set is negative (decided on the device) */
+int ipk_i3d_preprocess(const float* videos, float* out, int64_t n_frames, int32_t S, void* stream);
 
 /* ---- second-stage training step of the flow (BASELINE configs[3]): forward_density + FlowLoss + backward
  *      models/second_stage_video.py:345-350, models/modules/INN/loss.py:13-31; optimizer: second_stage_video.py:633-660 ----

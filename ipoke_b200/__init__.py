@@ -6,6 +6,8 @@ from .cond_encoder import ConvEncoder, make_cond  # noqa: F401
 from .encoder import ResNetMotionEncoder, encode_first_stage  # noqa: F401
 from .first_stage import SpadeCondMotionDecoder, decode_first_stage  # noqa: F401
 from .flow import SupervisedMacowTransformer, FlowLoss, flow_nll  # noqa: F401
+from . import i3d  # noqa: F401
+from .i3d import I3D  # noqa: F401
 from .parallel import shard_bounds, sharded_sample, global_noise  # noqa: F401
 from .sampler import PokeMotionSampler  # noqa: F401
 

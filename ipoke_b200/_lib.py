@@ -39,11 +39,16 @@ class CencConfig(ctypes.Structure):
                 ("n_stages", ctypes.c_int32), ("max_batch", ctypes.c_int32)]
 
 
+class I3dConfig(ctypes.Structure):
+    _fields_ = [("num_classes", ctypes.c_int32), ("max_batch", ctypes.c_int32), ("max_frames", ctypes.c_int32), ("precision", ctypes.c_int32)]
+
+
 EXPORTS = [
     "ipk_version", "ipk_last_error", "ipk_launch_count", "ipk_launch_count_reset", "ipk_prof_enable", "ipk_prof_report",
     "ipk_flow_create", "ipk_flow_set_tensor", "ipk_flow_data_init", "ipk_flow_finalize", "ipk_flow_reverse", "ipk_flow_forward", "ipk_flow_destroy",
     "ipk_fs_create", "ipk_fs_set_tensor", "ipk_fs_finalize", "ipk_fs_decode", "ipk_fs_gru_step", "ipk_fs_gen", "ipk_fs_destroy",
     "ipk_cenc_create", "ipk_cenc_set_tensor", "ipk_cenc_finalize", "ipk_cenc_forward", "ipk_cenc_destroy",
+    "ipk_i3d_create", "ipk_i3d_set_tensor", "ipk_i3d_finalize", "ipk_i3d_forward", "ipk_i3d_destroy", "ipk_i3d_preprocess",
     "ipk_enc_create", "ipk_enc_set_tensor", "ipk_enc_finalize", "ipk_enc_forward", "ipk_enc_destroy",
     "ipk_sample", "ipk_sample_host", "ipk_sample_host_u8", "ipk_frames_to_u8", "ipk_test_gemm", "ipk_test_conv3x3", "ipk_test_convT3x3", "ipk_test_conv3d",
     "ipk_flowtrain_create", "ipk_flowtrain_set_tensor", "ipk_flowtrain_finalize", "ipk_flowtrain_step", "ipk_flowtrain_forward", "ipk_flowtrain_backward", "ipk_flowtrain_destroy", "ipk_adam_step",
@@ -93,6 +98,12 @@ def lib():
     L.ipk_enc_finalize.argtypes = [vp, vp]
     L.ipk_enc_forward.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp]
     L.ipk_enc_destroy.argtypes = [vp]
+    L.ipk_i3d_create.argtypes = [ctypes.POINTER(I3dConfig), ctypes.POINTER(vp)]
+    L.ipk_i3d_set_tensor.argtypes = [vp, cp, vp, i64, ctypes.c_int]
+    L.ipk_i3d_finalize.argtypes = [vp, vp]
+    L.ipk_i3d_forward.argtypes = [vp, vp, vp, i32, i32, vp]
+    L.ipk_i3d_destroy.argtypes = [vp]
+    L.ipk_i3d_preprocess.argtypes = [vp, vp, i64, i32, vp]
     L.ipk_sample.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp]
     L.ipk_sample_host.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp]
     L.ipk_sample_host_u8.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp]
@@ -113,7 +124,7 @@ def lib():
     L.ipk_adam_step.argtypes = [vp, vp, vp, vp, vp, i64, f64, f64, f64, f64, f64, i32, f32, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
-        if name.startswith(("ipk_flow_", "ipk_fs_", "ipk_enc_", "ipk_cenc_", "ipk_sample", "ipk_frames_", "ipk_test_", "ipk_flowtrain_", "ipk_adam_")):
+        if name.startswith(("ipk_flow_", "ipk_fs_", "ipk_enc_", "ipk_cenc_", "ipk_sample", "ipk_frames_", "ipk_test_", "ipk_flowtrain_", "ipk_adam_", "ipk_i3d_")):
             fn.restype = ctypes.c_int
     _lib = L
     return L

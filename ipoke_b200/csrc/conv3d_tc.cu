@@ -39,8 +39,10 @@ struct C3TArgs {
   int bw, bh, bb;                       // output box, bw * bh * bb == 128
   int tiles_x, tiles_y, tiles_b, tiles_n;
   int nkb, Npad, N, stages;
-  float* out; int cstride;
+  float* out; int cstride;              // fp32 rows (may be null when only planes are written); already offset to the first column
   double* stats;                        // [B][N][2] or null
+  __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;   // operand planes (optional), same [voxel][cstride] geometry
+  const float* scale; const float* shift; int relu;
 };
 
 template <int BN, int NSPLIT>
@@ -189,8 +191,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
 #pragma unroll 1
       for (int c = half * HALF_COLS; c < (half + 1) * HALF_COLS; c += 32) {
-        if (n0 + c >= a.Npad) break;
-        const int ncols = min(32, a.Npad - (n0 + c));
+        if (n0 + c >= a.N) break;
+        const int ncols = min(32, a.N - (n0 + c));             // N is a multiple of 4: whole 16-byte segments
         float v[32];
         {
           uint32_t rr[32];
@@ -198,6 +200,18 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = valid ? __uint_as_float(rr[j]) : 0.f;
+        }
+        if (a.scale != nullptr || a.shift != nullptr) {        // folded BatchNorm / bias, warp-uniform branch
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = min(n0 + c + j, a.N - 1);
+            const float sc = a.scale ? __ldg(a.scale + n) : 1.0f, sh = a.shift ? __ldg(a.shift + n) : 0.0f;
+            v[j] = fmaf(v[j], sc, sh);
+          }
+        }
+        if (a.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
         }
         uint8_t* stg = epi_stage + (size_t)(warp - 2) * C3T_EPI_STAGE_BYTES + lane * 128;
         const int sw = lane & 7;
@@ -211,7 +225,20 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           const int row = (lane >> 3) + 4 * i;
           if (trow[i] == ~0ull) continue;
           const uint4 dv = *(const uint4*)(rd + row * 128 + ((seg ^ (row & 7)) << 4));
-          if (seg * 4 < ncols) *(uint4*)(a.out + (size_t)trow[i] * a.cstride + n0 + c + seg * 4) = dv;
+          if (seg * 4 < ncols) {
+            const size_t o = (size_t)trow[i] * a.cstride + n0 + c + seg * 4;
+            if (a.out) *(uint4*)(a.out + o) = dv;
+            if (a.out_hi) {
+              const float f0 = __uint_as_float(dv.x), f1 = __uint_as_float(dv.y), f2 = __uint_as_float(dv.z), f3 = __uint_as_float(dv.w);
+              const __nv_bfloat162 h01 = __floats2bfloat162_rn(f0, f1), h23 = __floats2bfloat162_rn(f2, f3);
+              *(uint2*)(a.out_hi + o) = make_uint2(*(const uint32_t*)&h01, *(const uint32_t*)&h23);
+              if (a.out_lo) {
+                const float2 g01 = __bfloat1622float2(h01), g23 = __bfloat1622float2(h23);
+                const __nv_bfloat162 l01 = __floats2bfloat162_rn(f0 - g01.x, f1 - g01.y), l23 = __floats2bfloat162_rn(f2 - g23.x, f3 - g23.y);
+                *(uint2*)(a.out_lo + o) = make_uint2(*(const uint32_t*)&l01, *(const uint32_t*)&l23);
+              }
+            }
+          }
         }
         if (a.stats != nullptr) {
           // the 32 rows of this warp belong to one sample (bw*bh >= 32): lane = column, sums straight from the staging rows
@@ -321,8 +348,15 @@ void conv3d_tc_pack(ConvW& dst, const float* w_oidhw, int Cout, int CinSrc, cuda
   IPK_LAUNCH_CHECK();
 }
 
+static void out_extent(const Conv3dShape& s, int& To, int& Ho, int& Wo) {
+  To = s.To > 0 ? s.To : (s.Ti + 2 * s.pt - s.kt) / s.st + 1;
+  Ho = s.Ho > 0 ? s.Ho : (s.Hi + 2 * s.py - s.ky) / s.sy + 1;
+  Wo = s.Wo > 0 ? s.Wo : (s.Wi + 2 * s.px - s.kx) / s.sx + 1;
+}
+
 bool conv3d_tc_supported(const Conv3dShape& s) {
-  const int Ho = (s.Hi + 2 * s.py - s.ky) / s.sy + 1, Wo = (s.Wi + 2 * s.px - s.kx) / s.sx + 1;
+  int To, Ho, Wo;
+  out_extent(s, To, Ho, Wo);
   if (s.Cin % 64 != 0 || s.Cout % 64 != 0) return false;
   if (!(C3T_BM % Wo == 0 || Wo % C3T_BM == 0)) return false;
   const int bw = std::min(Wo, C3T_BM), rest = C3T_BM / bw;
@@ -332,23 +366,50 @@ bool conv3d_tc_supported(const Conv3dShape& s) {
   if ((bw - 1) * s.sx + 1 > 256 || (bh - 1) * s.sy + 1 > 256 || s.sx > 8 || s.sy > 8) return false;
   return true;
 }
+bool conv3d_tc_supported_ex(const Conv3dShape& s) {
+  return s.Cin % 8 == 0 && s.Cout % 8 == 0 && s.sx >= 1 && s.sx <= 8 && s.sy >= 1 && s.sy <= 8;
+}
 
-void conv3d_tc_run(const ConvW& w, const Conv3dShape& s, const void* in_hi, const void* in_lo, int B, float* out, double* stats, cudaStream_t st) {
-  IPK_CHECK(conv3d_tc_supported(s), IPK_ERR_UNSUPPORTED, "conv3d_tc_run: shape not supported by the tensor-core engine");
+// 128-voxel output box (bw x bh x bb, powers of two) covering [Wo][Ho][B] with the fewest out-of-range voxels; ties -> widest rows
+static void choose_box(int Wo, int Ho, int B, int sx, int sy, bool need_stats, int& bw, int& bh, int& bb) {
+  double best = 1e300;
+  bw = 0;
+  for (int w = C3T_BM; w >= 1; w >>= 1)
+    for (int h = C3T_BM / w; h >= 1; h >>= 1) {
+      const int b = C3T_BM / (w * h);
+      if ((w - 1) * sx + 1 > 256 || (h - 1) * sy + 1 > 256 || b > 256) continue;
+      if (need_stats && w * h < 32) continue;
+      const double cover = (double)cdiv(Wo, w) * w * cdiv(Ho, h) * h * cdiv(B, b) * b;
+      if (cover < best) { best = cover; bw = w; bh = h; bb = b; }
+    }
+  IPK_CHECK(bw > 0, IPK_ERR_UNSUPPORTED, "conv3d_tc: no 128-voxel box fits output %d x %d (strides %d, %d)", Wo, Ho, sx, sy);
+}
+
+void conv3d_tc_run_ex(const ConvW& w, const Conv3dShape& s, const void* in_hi, const void* in_lo, int B, const Conv3dEpi& epi, cudaStream_t st) {
+  IPK_CHECK(conv3d_tc_supported_ex(s), IPK_ERR_UNSUPPORTED, "conv3d_tc_run: shape not supported by the tensor-core engine");
   IPK_CHECK(w.w_hi != nullptr && w.ntaps == s.kt * s.ky * s.kx && w.K == s.Cin && w.N == s.Cout, IPK_ERR_STATE, "conv3d_tc_run: packed weights do not match the layer");
   const bool split = w.engine == IPK_PREC_FP32_SPLIT;
   IPK_CHECK(!split || (in_lo && w.w_lo), IPK_ERR_STATE, "conv3d_tc_run: split precision needs hi and lo operand planes");
+  IPK_CHECK(epi.out_f32 || epi.out_hi, IPK_ERR_INVALID, "conv3d_tc_run: no output");
+  IPK_CHECK(epi.cstride % 4 == 0 && epi.coff % 4 == 0 && epi.coff + s.Cout <= epi.cstride, IPK_ERR_INVALID, "conv3d_tc_run: output slice (%d + %d of %d)", epi.coff, s.Cout, epi.cstride);
   C3TArgs a;
   memset(&a, 0, sizeof(a));
   a.B = B; a.Ti = s.Ti; a.Hi = s.Hi; a.Wi = s.Wi;
-  a.To = (s.Ti + 2 * s.pt - s.kt) / s.st + 1; a.Ho = (s.Hi + 2 * s.py - s.ky) / s.sy + 1; a.Wo = (s.Wi + 2 * s.px - s.kx) / s.sx + 1;
+  out_extent(s, a.To, a.Ho, a.Wo);
   a.st = s.st; a.sy = s.sy; a.sx = s.sx; a.pt = s.pt; a.py = s.py; a.px = s.px; a.kt = s.kt; a.ky = s.ky; a.kx = s.kx;
-  a.bw = std::min(a.Wo, C3T_BM);
-  a.bh = std::min(a.Ho, C3T_BM / a.bw);
-  a.bb = C3T_BM / (a.bw * a.bh);
+  if (conv3d_tc_supported(s)) {          // the encoder's shapes keep their boxes (a warp's 32 rows inside one sample: fused statistics)
+    a.bw = std::min(a.Wo, C3T_BM);
+    a.bh = std::min(a.Ho, C3T_BM / a.bw);
+    a.bb = C3T_BM / (a.bw * a.bh);
+  } else {
+    IPK_CHECK(epi.stats == nullptr, IPK_ERR_UNSUPPORTED, "conv3d_tc_run: fused statistics need a power-of-two output geometry");
+    choose_box(a.Wo, a.Ho, B, s.sx, s.sy, false, a.bw, a.bh, a.bb);
+  }
   a.tiles_x = cdiv(a.Wo, a.bw); a.tiles_y = cdiv(a.Ho, a.bh); a.tiles_b = cdiv(B, a.bb);
   a.nkb = w.Kpad / C3T_BK; a.Npad = w.Npad; a.N = w.N;
-  a.out = out; a.cstride = s.Cout; a.stats = stats;
+  a.out = epi.out_f32 ? epi.out_f32 + epi.coff : nullptr; a.cstride = epi.cstride; a.stats = epi.stats;
+  a.out_hi = epi.out_hi ? epi.out_hi + epi.coff : nullptr; a.out_lo = epi.out_lo ? epi.out_lo + epi.coff : nullptr;
+  a.scale = epi.scale; a.shift = epi.shift; a.relu = epi.relu;
   // activation map: dims (C, W, H, T, B); element strides carry the spatial conv stride
   const cuuint64_t cs = s.stride_x > 0 ? (cuuint64_t)s.stride_x : (cuuint64_t)s.Cin * 2;
   const cuuint64_t rs = s.stride_y > 0 ? (cuuint64_t)s.stride_y : cs * s.Wi;
@@ -358,11 +419,17 @@ void conv3d_tc_run(const ConvW& w, const Conv3dShape& s, const void* in_hi, cons
   cuuint32_t es[5] = {1u, (cuuint32_t)s.sx, (cuuint32_t)s.sy, 1u, 1u};
   const CUtensorMap mA_hi = encode_map(in_hi, 5, gd, gs, bx, es);
   const CUtensorMap mA_lo = split ? encode_map(in_lo, 5, gd, gs, bx, es) : mA_hi;
-  // N tile: the widest that still gives every SM a tile
+  // N tile: the widest that still gives every SM a tile; padded columns cost MMA work, every extra N tile one more read of the A tile
   const long long tiles_m = (long long)a.tiles_b * a.To * a.tiles_y * a.tiles_x;
   int BN = 64;
-  for (int bn : {256, 128}) {
-    if (w.Npad % bn == 0 && tiles_m * (w.Npad / bn) >= sm_count3()) { BN = bn; break; }
+  {
+    double best = 1e300;
+    for (int bn : {256, 128, 64}) {
+      const int tn = cdiv(w.Npad, bn);
+      double cost = (double)tn * bn * (1.0 + 32.0 / bn);
+      if (tiles_m * tn < sm_count3()) cost *= 2.0;          // too few tiles to fill the machine
+      if (cost < best) { best = cost; BN = bn; }
+    }
   }
   a.tiles_n = cdiv(w.Npad, BN);
   cuuint64_t wd[2] = {(cuuint64_t)w.Kpad, (cuuint64_t)w.ntaps * w.Npad};
@@ -376,6 +443,13 @@ void conv3d_tc_run(const ConvW& w, const Conv3dShape& s, const void* in_hi, cons
     case 128: if (split) launch_c3t<128, 3>(mA_hi, mA_lo, mW_hi, mW_lo, a, st); else launch_c3t<128, 1>(mA_hi, mA_lo, mW_hi, mW_lo, a, st); break;
     default: if (split) launch_c3t<256, 3>(mA_hi, mA_lo, mW_hi, mW_lo, a, st); else launch_c3t<256, 1>(mA_hi, mA_lo, mW_hi, mW_lo, a, st); break;
   }
+}
+
+void conv3d_tc_run(const ConvW& w, const Conv3dShape& s, const void* in_hi, const void* in_lo, int B, float* out, double* stats, cudaStream_t st) {
+  IPK_CHECK(conv3d_tc_supported(s), IPK_ERR_UNSUPPORTED, "conv3d_tc_run: shape not supported by the tensor-core engine");
+  Conv3dEpi e;
+  e.out_f32 = out; e.cstride = s.Cout; e.stats = stats;
+  conv3d_tc_run_ex(w, s, in_hi, in_lo, B, e, st);
 }
 
 }  // namespace ipk

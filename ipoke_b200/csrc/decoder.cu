@@ -427,10 +427,10 @@ extern "C" int ipk_fs_finalize(ipk_fs* d, void* stream) {
     fe = std::max(fe, (size_t)ub.s_in * ub.s_in * ub.Cin);
     d->blocks.push_back(ub);
   }
-  // Final 3x3 64 -> 3 conv.  On 128-wide frames the tensor-core engine runs it in halo mode (one 130-pixel row box per input row, the
-  // three dx taps as shifted descriptors): the contraction is ~0.2 ms of tcgen05 time for 1 024 frames, so the layer is bounded by
-  // reading its input once, where the fp32 FFMA kernel (out_conv.cu) is issue-bound at ~3x that.  IPK_OUTCONV_TC=0 keeps the FFMA kernel.
-  static const bool outconv_tc = []() { const char* e = getenv("IPK_OUTCONV_TC"); return !(e && e[0] == '0'); }();
+  // Final 3x3 64 -> 3 conv: the fp32 FFMA halo-tile kernel (out_conv.cu).  IPK_OUTCONV_TC=1 runs it on the tensor-core engine in halo mode
+  // instead (BN = 32); measured on B200 that is SLOWER (3.48 vs 2.53 ms per 1 024 frames): one 128-pixel row per tile leaves ~4 us of
+  // TMA round-trip latency per tile that a 3-stage ring cannot hide, while the MMA work per tile is ~0.1 us.
+  static const bool outconv_tc = []() { const char* e = getenv("IPK_OUTCONV_TC"); return e && e[0] == '1'; }();
   if (dc[d->nd - 1] == OUT_CONV_CIN && !(outconv_tc && eng != IPK_PREC_FP32_SIMT && d->S == 128)) {
     const std::string p = "gen.out_conv.conv.";
     float* packed = d->pool.alloc<float>(OUT_CONV_PACKED_FLOATS);

@@ -127,12 +127,23 @@ __global__ void elu_bwd_kernel(float* __restrict__ d, int ldd, const float* __re
     d[m * ldd + c] *= hv > 0.f ? 1.0f : hv + 1.0f;
   }
 }
-// Affine.fwd on the transformed channels (macow_utils.py:49-59): one block per sample; P[m][j] = mu, P[m][nt + j] = log-scale input
+// d[m][c] *= ELU'(pre[m][c]) = pre > 0 ? 1 : exp(pre)
+__global__ void elu_bwd_pre_kernel(float* __restrict__ d, int ldd, const float* __restrict__ pre, int ldp, int C, long long M) {
+  const long long total = M * C;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(e % C);
+    const long long m = e / C;
+    const float x = pre[m * ldp + c];
+    d[m * ldd + c] *= x > 0.f ? 1.0f : expf(x);
+  }
+}
+// Affine.fwd on the transformed channels (macow_utils.py:49-59): blockIdx.x = sample, blockIdx.y = slice of its 64 * nt elements (the
+// log-det partial sums of a sample's slices meet in one atomicAdd each); P[m][j] = mu, P[m][nt + j] = log-scale input
 __global__ void affine_fwd_kernel(float* __restrict__ S, int ld, const int* __restrict__ idx, int nt, const float* __restrict__ P, int ldp,
                                   float* __restrict__ logdet) {
   const int b = blockIdx.x;
   float ldsum = 0.f;
-  for (int e = threadIdx.x; e < 64 * nt; e += blockDim.x) {
+  for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < 64 * nt; e += gridDim.y * blockDim.x) {
     const int j = e % nt;
     const size_t m = (size_t)b * 64 + e / nt;
     const float mu = P[m * ldp + j], sc = 1.0f + tanhf(0.5f * P[m * ldp + nt + j]);
@@ -148,7 +159,7 @@ __global__ void affine_fwd_kernel(float* __restrict__ S, int ld, const int* __re
   if (threadIdx.x == 0) {
     float v = 0.f;
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) v += red[i];
-    logdet[b] += v;
+    atomicAdd(&logdet[b], v);
   }
 }
 // backward of y_t = s x_t + mu with logdet = sum log s and dL/dlogdet_b = dld[b] (-1/B for FlowLoss):
@@ -401,58 +412,110 @@ struct SgemmArgs {
   const float* bias;                      // [J] added to every row (ksplit == 1 only), or null
   int I, J, K, kchunk, atomic;            // blockIdx.z covers k in [z*kchunk, (z+1)*kchunk); atomic: atomicAdd into C
 };
+// Loader: every thread fetches 4 elements of the A slice and 4 of the B slice per 16-deep step -- as ONE 16-byte load when the operand's
+// unit-stride axis allows it (k-fast rows with ld % 4 == 0, or 4 consecutive rows of an i-fast operand), else as 4 scalar loads -- into
+// registers BEFORE the FMAs of the current step, and stores them to the other shared-memory buffer afterwards (one barrier per step).
+struct SgemmFrag { float v[4]; };
+__device__ __forceinline__ SgemmFrag sgemm_fetch(const float* __restrict__ P, long long sI, long long sK, int i0, int I, int k0, int k_end, int tid, bool kfast,
+                                                 bool vec) {
+  SgemmFrag f;
+  if (kfast) {           // thread -> (row = tid / 4, 4 consecutive k)
+    const int ii = tid >> 2, kk = (tid & 3) * 4;
+    const int gi = i0 + ii, gk = k0 + kk;
+    if (vec && gi < I && gk + 3 < k_end) {
+      const float4 t = *(const float4*)(P + gi * sI + gk);
+      f.v[0] = t.x; f.v[1] = t.y; f.v[2] = t.z; f.v[3] = t.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) f.v[e] = (gi < I && gk + e < k_end) ? P[gi * sI + (gk + e) * sK] : 0.f;
+    }
+  } else {               // thread -> (k = tid / 16, 4 consecutive rows)
+    const int kk = tid >> 4, ii = (tid & 15) * 4;
+    const int gi = i0 + ii, gk = k0 + kk;
+    if (vec && gi + 3 < I && gk < k_end) {
+      const float4 t = *(const float4*)(P + gk * sK + gi);
+      f.v[0] = t.x; f.v[1] = t.y; f.v[2] = t.z; f.v[3] = t.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) f.v[e] = (gi + e < I && gk < k_end) ? P[(gi + e) * sI + gk * sK] : 0.f;
+    }
+  }
+  return f;
+}
+__device__ __forceinline__ void sgemm_stash(float (*S)[68], const SgemmFrag& f, int tid, bool kfast) {
+  if (kfast) {
+    const int ii = tid >> 2, kk = (tid & 3) * 4;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) S[kk + e][ii] = f.v[e];
+  } else {
+    const int kk = tid >> 4, ii = (tid & 15) * 4;
+    *(float4*)&S[kk][ii] = make_float4(f.v[0], f.v[1], f.v[2], f.v[3]);
+  }
+}
 __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmArgs a) {
-  __shared__ float As[16][68], Bs[16][68];
+  __shared__ __align__(16) float As[2][16][68], Bs[2][16][68];
   const int tid = threadIdx.x;
   const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
   const int k_begin = blockIdx.z * a.kchunk, k_end = min(a.K, k_begin + a.kchunk);
   const int ti = tid >> 4, tj = tid & 15;          // thread computes rows ti*4..+3, cols tj*4..+3
-  // loader mapping: 1 024 elements per tile, 4 per thread; the unit-stride axis runs across consecutive threads
   const bool a_kfast = a.sAk == 1, b_kfast = a.sBk == 1;
+  // 16-byte loads need the unit-stride run of 4 elements to start on a 16-byte boundary for every thread
+  const bool a_vec = a_kfast ? ((a.sAi & 3) == 0 && (((uintptr_t)a.A) & 15) == 0 && (k_begin & 3) == 0)
+                             : (a.sAi == 1 && (a.sAk & 3) == 0 && (((uintptr_t)a.A) & 15) == 0);
+  const bool b_vec = b_kfast ? ((a.sBj & 3) == 0 && (((uintptr_t)a.B) & 15) == 0 && (k_begin & 3) == 0)
+                             : (a.sBj == 1 && (a.sBk & 3) == 0 && (((uintptr_t)a.B) & 15) == 0);
   float acc[4][4];
 #pragma unroll
   for (int r = 0; r < 4; ++r)
 #pragma unroll
     for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+  SgemmFrag fa = sgemm_fetch(a.A, a.sAi, a.sAk, i0, a.I, k_begin, k_end, tid, a_kfast, a_vec);
+  SgemmFrag fb = sgemm_fetch(a.B, a.sBj, a.sBk, j0, a.J, k_begin, k_end, tid, b_kfast, b_vec);
+  sgemm_stash(As[0], fa, tid, a_kfast);
+  sgemm_stash(Bs[0], fb, tid, b_kfast);
+  __syncthreads();
+  int buf = 0;
   for (int k0 = k_begin; k0 < k_end; k0 += 16) {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int idx = tid + e * 256;
-      {
-        const int kk = a_kfast ? (idx & 15) : (idx >> 6), ii = a_kfast ? (idx >> 4) : (idx & 63);
-        const int gi = i0 + ii, gk = k0 + kk;
-        As[kk][ii] = (gi < a.I && gk < k_end) ? a.A[gi * a.sAi + gk * a.sAk] : 0.f;
-      }
-      {
-        const int kk = b_kfast ? (idx & 15) : (idx >> 6), jj = b_kfast ? (idx >> 4) : (idx & 63);
-        const int gj = j0 + jj, gk = k0 + kk;
-        Bs[kk][jj] = (gj < a.J && gk < k_end) ? a.B[gj * a.sBj + gk * a.sBk] : 0.f;
-      }
+    const bool more = k0 + 16 < k_end;
+    if (more) {
+      fa = sgemm_fetch(a.A, a.sAi, a.sAk, i0, a.I, k0 + 16, k_end, tid, a_kfast, a_vec);
+      fb = sgemm_fetch(a.B, a.sBj, a.sBk, j0, a.J, k0 + 16, k_end, tid, b_kfast, b_vec);
     }
-    __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < 16; ++kk) {
-      const float4 av = *(const float4*)&As[kk][ti * 4];
-      const float4 bv = *(const float4*)&Bs[kk][tj * 4];
+      const float4 av = *(const float4*)&As[buf][kk][ti * 4];
+      const float4 bv = *(const float4*)&Bs[buf][kk][tj * 4];
       const float ar[4] = {av.x, av.y, av.z, av.w}, br[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
       for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(ar[r], br[c], acc[r][c]);
     }
-    __syncthreads();
+    if (more) {
+      sgemm_stash(As[buf ^ 1], fa, tid, a_kfast);
+      sgemm_stash(Bs[buf ^ 1], fb, tid, b_kfast);
+      __syncthreads();
+      buf ^= 1;
+    }
   }
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     const int gi = i0 + ti * 4 + r;
     if (gi >= a.I) continue;
+    float* crow = a.C + gi * a.ldc + j0 + tj * 4;
+    if (!a.atomic && j0 + tj * 4 + 3 < a.J && (a.ldc & 3) == 0 && (((uintptr_t)a.C) & 15) == 0) {
+      float4 o = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+      if (a.bias) { const float* bp = a.bias + j0 + tj * 4; o.x += bp[0]; o.y += bp[1]; o.z += bp[2]; o.w += bp[3]; }     // parameter views: 4-byte aligned only
+      *(float4*)crow = o;
+      continue;
+    }
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       const int gj = j0 + tj * 4 + c;
       if (gj >= a.J) continue;
-      float v = acc[r][c];
-      if (a.atomic) atomicAdd(&a.C[gi * a.ldc + gj], v);
-      else a.C[gi * a.ldc + gj] = a.bias ? v + a.bias[gj] : v;
+      const float v = acc[r][c];
+      if (a.atomic) atomicAdd(&crow[c], v);
+      else crow[c] = a.bias ? v + a.bias[gj] : v;
     }
   }
 }
@@ -675,19 +738,21 @@ static void train_forward(ipk_flowtrain* f, int B, cudaStream_t st) {
       actnorm_fwd_kernel<<<gridn(M * op.cnt), 256, 0, st>>>(y, f->C0, op.coff, op.cnt, op.ls, op.bias, f->logdet, B);
       IPK_LAUNCH_CHECK();
     } else if (op.kind == L_MCF) {
+      ProfScope psm("train.fwd.mcf", st);
       const McfTrain& m = f->mcfs[op.a];
       float *c1s = f->c1, *Ps = f->P;
       if (f->keep_acts) { f->c1 = f->sv_mc1[op.a]; f->P = f->sv_mP[op.a]; }
       mcf_net(f, m, x, B, st);
-      affine_fwd_kernel<<<B, 256, 0, st>>>(y, f->C0, nullptr, m.C, f->P, f->ldP, f->logdet);
+      affine_fwd_kernel<<<dim3(B, cdiv(64 * m.C, 512)), 256, 0, st>>>(y, f->C0, nullptr, m.C, f->P, f->ldP, f->logdet);
       IPK_LAUNCH_CHECK();
       f->c1 = c1s; f->P = Ps;
     } else {
+      ProfScope psn("train.fwd.nice", st);
       const NiceTrain& n = f->nices[op.a];
       float *cols = f->col, *a1s = f->a1, *a2s = f->a2, *Ps = f->P;
       if (f->keep_acts) { f->col = f->sv_ncol[op.a]; f->a1 = f->sv_na1[op.a]; f->a2 = f->sv_na2[op.a]; f->P = f->sv_nP[op.a]; }
       nice_net(f, n, x, B, st);
-      affine_fwd_kernel<<<B, 256, 0, st>>>(y, f->C0, n.d_ip, n.n_p, f->P, f->ldP, f->logdet);
+      affine_fwd_kernel<<<dim3(B, cdiv(64 * n.n_p, 512)), 256, 0, st>>>(y, f->C0, n.d_ip, n.n_p, f->P, f->ldP, f->logdet);
       IPK_LAUNCH_CHECK();
       f->col = cols; f->a1 = a1s; f->a2 = a2s; f->P = Ps;
     }
@@ -716,10 +781,8 @@ static void mcf_backward(ipk_flowtrain* f, McfTrain& m, int ai, const float* x, 
   wn_bwd_kernel<<<m.C2, 128, 0, st>>>(f->wout, m.K1, 1, 0, 1, m.v1, m.g1, m.g_v1, m.g_g1, m.K1);
   IPK_LAUNCH_CHECK();
   sgemm(f->dP, f->ldP, 1, m.weff, 1, m.K1, f->E, f->ldE, nullptr, M, m.hid, m.C2, 1, false, st);       // E[:, :hid] <- dE
-  // dc1 = dE * ELU'(c1): ELU output of c1 recomputed in place
-  elu_kernel<<<gridn((long long)M * f->ldc1), 256, 0, st>>>(f->c1, f->c1, (long long)M * f->ldc1);
-  IPK_LAUNCH_CHECK();
-  elu_bwd_kernel<<<gridn((long long)M * m.hid), 256, 0, st>>>(f->E, f->ldE, f->c1, f->ldc1, m.hid, M);
+  // dc1 = dE * ELU'(c1), ELU'(x) = x > 0 ? 1 : exp(x), straight from the pre-activation
+  elu_bwd_pre_kernel<<<gridn((long long)M * m.hid), 256, 0, st>>>(f->E, f->ldE, f->c1, f->ldc1, m.hid, M);
   IPK_LAUNCH_CHECK();
   // shifted conv: dWs[n][c*taps + t] = sum_m dc1[m][n] x[m + delta_t][c] (straight into the OIHW gradient);  dx += conv^T(dc1)
   im2col_taps_kernel<<<gridn((long long)M * Kc), 256, 0, st>>>(x, f->C0, nullptr, m.C, m.taps, 1, f->stack, f->ldstack, Kc, M);
@@ -740,6 +803,7 @@ static void nice_backward(ipk_flowtrain* f, NiceTrain& n, int ai, const float* x
   colsum_kernel<<<n.N3, 256, 0, st>>>(f->dP, f->ldP, M, n.g_b3);
   IPK_LAUNCH_CHECK();
   // conv3 wgrad: rows (j, t) of the shifted stack of dP against a2
+  ProfScope* ps3 = new ProfScope("train.bwd.nice.conv3", st);
   im2col_taps_kernel<<<gridn((long long)M * 9 * n.N3), 256, 0, st>>>(f->dP, f->ldP, nullptr, n.N3, taps3x3(), -1, f->stack, f->ldstack, 9 * n.N3, M);
   IPK_LAUNCH_CHECK();
   to_operand_T(f, f->stack, f->ldstack, 0, M, 9 * n.N3, f->opT, f->opT_lo, f->opT_elems, st);
@@ -751,14 +815,18 @@ static void nice_backward(ipk_flowtrain* f, NiceTrain& n, int ai, const float* x
   conv8(n.c3T, f->opA, f->opA_lo, n.N3p, B, taplist(taps3x3(), -1), f->da, Hd, nullptr, st);
   elu_bwd_kernel<<<gridn((long long)M * Hd), 256, 0, st>>>(f->da, Hd, f->a2, Hd, Hd, M);
   IPK_LAUNCH_CHECK();
+  delete ps3;
   // conv2: dW2 = da2pre^T a1 (straight into the gradient tensor), da1 = da2pre W2
+  ProfScope* ps2 = new ProfScope("train.bwd.nice.conv2", st);
   to_operand_T(f, f->da, Hd, 0, M, Hd, f->opT, f->opT_lo, f->opT_elems, st);
   wgrad(f, Hd, f->a1, Hd, Hd, M, n.g_w2, Hd, st);
   to_operand(f, f->da, Hd, 0, M, Hd, Hd, f->opA, f->opA_lo, st);
   gemm(n.c2T, f->opA, f->opA_lo, Hd, M, f->a2, Hd, nullptr, ACT_NONE, st);       // a2 <- da1
   elu_bwd_kernel<<<gridn((long long)M * Hd), 256, 0, st>>>(f->a2, Hd, f->a1, Hd, Hd, M);
   IPK_LAUNCH_CHECK();
+  delete ps2;
   // conv1: dW1 = da1pre^T col (OIHW as it lies), dcol = da1pre W1 -> col2im onto the z channels
+  ProfScope ps1("train.bwd.nice.conv1", st);
   to_operand_T(f, f->a2, Hd, 0, M, Hd, f->opT, f->opT_lo, f->opT_elems, st);
   wgrad(f, Hd, f->col, f->ldcol, n.K1, M, f->wout, f->ldwout, st);
   relayout_kernel<<<gridn((long long)Hd * n.K1), 256, 0, st>>>(f->wout, f->ldwout, 1, 0, 1, n.g_w1, n.K1, (long long)Hd * n.K1);
@@ -785,8 +853,8 @@ static void train_backward(ipk_flowtrain* f, int B, cudaStream_t st) {
         IPK_LAUNCH_CHECK();
         std::swap(f->G, f->Gtmp);
         break;
-      case L_MCF: mcf_backward(f, f->mcfs[op.a], op.a, x, B, st); break;
-      default: nice_backward(f, f->nices[op.a], op.a, x, B, st); break;
+      case L_MCF: { ProfScope psm("train.bwd.mcf", st); mcf_backward(f, f->mcfs[op.a], op.a, x, B, st); break; }
+      default: { ProfScope psn("train.bwd.nice", st); nice_backward(f, f->nices[op.a], op.a, x, B, st); break; }
     }
   }
 }

@@ -10,7 +10,8 @@ z ~ N(0,I) (CPU generator seeded 42 + p, second_stage_video.py:289-300) go throu
     off, on `--oracle-device` (cuda for the full sweep: the checker is allowed to be fast; cpu for the small test),
 
 with identical synthetic weights.  Both video sets are reduced on the fly to the 400-d I3D logits of the reference's FVD
-chain (oracle/fvd_oracle.py, seeded I3D).  Reported:
+chain with a seeded I3D -- by default through the NATIVE I3D (ipoke_b200.i3d, itself pinned on the reference's logits by
+tests/test_gpu_i3d.py), `native_i3d=False` / `--oracle-i3d` through the oracle restatement (oracle/fvd_oracle.py).  Reported:
   fvd_ours_vs_ref        Frechet distance between the two sets on identical seeds/pokes (0 for identical videos),
   fvd_ref_split          reference(even pokes) vs reference(odd pokes): the ref-vs-ref baseline,
   fvd_ours_split         ours(even pokes) vs reference(odd pokes);  parity = |fvd_ours_split - fvd_ref_split| <= 1.0,
@@ -39,7 +40,7 @@ def _to(sd, dev):
 
 
 def run_sweep(n_pokes=1000, n_samples=5, frames=10, spatial=128, c0=64, hd=2048, batch_pokes=50, precision="fp32",
-              oracle_device="cuda", i3d_batch=50, num_steps=None, verbose=True):
+              oracle_device="cuda", i3d_batch=50, num_steps=None, verbose=True, native_i3d=True):
     import ipoke_b200 as ipk
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -55,6 +56,11 @@ def run_sweep(n_pokes=1000, n_samples=5, frames=10, spatial=128, c0=64, hd=2048,
     fsd, dsd = O.synth_flow_state_dict(fcfg, seed=0), O.synth_first_stage_state_dict(dcfg, seed=1)
     isd, psd = O.synth_cond_encoder_state_dict(icfg, seed=2), O.synth_cond_encoder_state_dict(pcfg, seed=3)
     i3d = _to(FO.synth_i3d_state_dict(seed=4), dev)
+    i3d_native = None
+    if native_i3d:
+        i3d_native = ipk.I3D(400, "rgb", ipk_max_batch=i3d_batch, ipk_max_frames=max(frames, 9))
+        i3d_native.load_state_dict(FO.synth_i3d_state_dict(seed=4), strict=True)
+        i3d_native = i3d_native.to(dev).eval()
 
     fc = dict(fcfg); fc.update(ipk_precision=precision, ipk_max_batch=B)
     dc = dict(dcfg); dc.update(ipk_precision=precision, ipk_max_batch=B, ipk_max_frames=frames)
@@ -68,6 +74,10 @@ def run_sweep(n_pokes=1000, n_samples=5, frames=10, spatial=128, c0=64, hd=2048,
     def features(videos):
         out = []
         for i in range(0, videos.shape[0], i3d_batch):
+            if i3d_native is not None:
+                v = ipk.i3d._preprocess_one(videos[i:i + i3d_batch].to(dev))
+                out.append(ipk.i3d.get_activations(v, i3d_native, batch_size=v.shape[0]))
+                continue
             v = FO.preprocess(videos[i:i + i3d_batch].to(dev))
             out.append(FO.activations(i3d, v, batch_size=v.shape[0]))
         return np.concatenate(out, 0)
@@ -110,7 +120,7 @@ def run_sweep(n_pokes=1000, n_samples=5, frames=10, spatial=128, c0=64, hd=2048,
         "fvd_ours_vs_ref": FO.fvd_from_activations(f_ours, f_ref),
         "fvd_ref_split": FO.fvd_from_activations(f_ref[even], f_ref[odd]),
         "fvd_ours_split": FO.fvd_from_activations(f_ours[even], f_ref[odd]),
-        "seconds_ours": t_ours, "seconds_oracle": t_ref, "oracle_device": str(odev),
+        "seconds_ours": t_ours, "seconds_oracle": t_ref, "oracle_device": str(odev), "i3d": "native (ipoke_b200.i3d)" if native_i3d else "oracle (torch ops)",
     }
     res["delta_fvd"] = res["fvd_ours_split"] - res["fvd_ref_split"]
     res["fvd_parity"] = bool(abs(res["delta_fvd"]) <= 1.0 and abs(res["fvd_ours_vs_ref"]) <= 1.0)
@@ -129,8 +139,9 @@ if __name__ == "__main__":
     ap.add_argument("--precision", default="fp32")
     ap.add_argument("--oracle-device", default="cuda")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--oracle-i3d", action="store_true", help="reduce the videos with the oracle's torch-op I3D instead of the native one")
     a = ap.parse_args()
-    r = run_sweep(a.pokes, a.samples, a.frames, a.spatial, a.c0, a.hd, a.batch_pokes, a.precision, a.oracle_device)
+    r = run_sweep(a.pokes, a.samples, a.frames, a.spatial, a.c0, a.hd, a.batch_pokes, a.precision, a.oracle_device, native_i3d=not a.oracle_i3d)
     print(json.dumps(r))
     if a.out:
         os.makedirs(os.path.dirname(os.path.abspath(a.out)), exist_ok=True)
