@@ -329,71 +329,88 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (n0 + c >= a.Npad) break;                  // warp-uniform
         const int ncols = min(EPI_CHUNK, a.Npad - (n0 + c));   // Npad is a multiple of 16: a 32-column chunk may be half valid
         float v[EPI_CHUNK];
-        auto load_acc = [&]() {
+        {
           uint32_t rr[EPI_CHUNK];
           if constexpr (EPI_CHUNK == 32) tmem_ld32(tacc + (uint32_t)c, rr);
           else tmem_ld16(tacc + (uint32_t)c, rr);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < EPI_CHUNK; ++j) v[j] = __uint_as_float(rr[j]);
-        };
+        }
         const int oi = (a.split_col > 0 && n0 + c >= a.split_col) ? 1 : 0;     // warp-uniform: destination of this chunk
         const TcOut& od = a.o[oi];
         const size_t colbase = (size_t)od.coff + (size_t)(n0 + c - (oi ? a.split_col : 0));
-        if (EPI_CHUNK == 32 && od.mode == OUT_F32_NHWC) {
-          // ---- fp32 rows: the raw accumulators are transposed through shared memory (lane = row on the way in, 8 lanes = one 128-byte
-          //      row segment on the way out) and the whole epilogue -- bias, activation, the fused residual branch -- runs in the
-          //      TRANSPOSED mapping: a lane then owns 4 fixed channels (its bias / mean / rstd are 3 registers-quads per chunk, not 24
-          //      broadcast loads), the residual is read with the same fully coalesced 128-byte row segments the result is written
-          //      with (the row-per-lane form touched 32 half-used sectors per load), and those loads are issued before the
-          //      accumulators arrive so that their latency hides behind the TMEM load and the transpose.
-          const int seg = lane & 7;
-          const bool seg_on = seg * 4 < ncols;
-          const int ch = n0 + c + seg * 4;                      // first of this lane's 4 output channels
-          const bool has_res = FUSED && a.res != nullptr;
-          float4 rres[8];
-          if (has_res) {
+        if (a.bias) {
+          const float4* b4 = (const float4*)(a.bias + n0 + c);
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              rres[i] = (trow[i] != ~0ull && seg_on) ? __ldg((const float4*)(a.res + (size_t)trow[i] * a.res_cstride + ch)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int j = 0; j < EPI_CHUNK / 4; ++j) {
+            if (4 * j >= ncols) break;
+            const float4 b = __ldg(b4 + j);
+            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
           }
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), mean4 = b4, rstd4 = make_float4(1.f, 1.f, 1.f, 1.f);
-          if (a.bias && seg_on) b4 = __ldg((const float4*)(a.bias + ch));
-          if (has_res && a.res_mr && seg_on) {
-            const int fw = min(__shfl_sync(0xffffffffu, f, 0), a.F - 1);      // a warp's 32 rows lie in one frame
-            const float4* mp = (const float4*)(a.res_mr + ((size_t)fw * a.N + ch) * 2);     // (mean, rstd) pairs
-            const float4 m01 = __ldg(mp), m23 = __ldg(mp + 1);
-            mean4 = make_float4(m01.x, m01.z, m23.x, m23.z);
-            rstd4 = make_float4(m01.y, m01.w, m23.y, m23.w);
-          } else if (has_res && a.res_mr) {
-            (void)__shfl_sync(0xffffffffu, f, 0);
+        }
+        act_tile<EPI_CHUNK>(v, od.act);
+        if (FUSED && EPI_CHUNK == 32 && a.res != nullptr) {
+          // residual branch of a ResBlock: + res_act((res - mean) * rstd), per-(frame, channel) statistics from res_mr
+          float rv[EPI_CHUNK];
+          if (valid) {
+            const float4* rp = (const float4*)(a.res + opix * a.res_cstride + n0 + c);
+#pragma unroll
+            for (int j = 0; j < EPI_CHUNK / 4; ++j) {
+              const float4 t4 = __ldg(rp + j);
+              rv[4 * j] = t4.x; rv[4 * j + 1] = t4.y; rv[4 * j + 2] = t4.z; rv[4 * j + 3] = t4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < EPI_CHUNK; ++j) rv[j] = 0.f;
           }
-          load_acc();          // the residual / constant loads above are in flight while the accumulators come out of TMEM
+          if (a.res_mr) {
+            const float4* mp = (const float4*)(a.res_mr + ((size_t)min(f, a.F - 1) * a.N + n0 + c) * 2);     // (mean, rstd) pairs
+#pragma unroll
+            for (int j = 0; j < EPI_CHUNK / 2; ++j) {
+              const float4 m4 = __ldg(mp + j);
+              rv[2 * j] = (rv[2 * j] - m4.x) * m4.y;
+              rv[2 * j + 1] = (rv[2 * j + 1] - m4.z) * m4.w;
+            }
+          }
+          act_tile<EPI_CHUNK>(rv, a.res_act);
+#pragma unroll
+          for (int j = 0; j < EPI_CHUNK; ++j) v[j] = valid ? v[j] + rv[j] : 0.f;      // rows outside the image contribute 0 to the stats
+        }
+        if (FUSED && a.stats != nullptr && a.res == nullptr && !valid) {
+#pragma unroll
+          for (int j = 0; j < EPI_CHUNK; ++j) v[j] = 0.f;      // rows outside the image contribute 0 to the statistics
+        }
+        if (od.mode == OUT_F32_NCHW) {
+          // frames at the ABI edge: [f][N][Ho][Wo]; consecutive lanes are consecutive x -> coalesced per channel
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < EPI_CHUNK; ++j) {
+              const int n = n0 + c + j;
+              if (n < a.N) ((float*)od.out)[(((size_t)f * a.N + n) * a.Ho + oy) * a.Wo + ox] = v[j];
+            }
+          }
+        } else if (EPI_CHUNK == 32 && od.mode == OUT_F32_NHWC) {
+          // ---- fp32 rows: transpose through shared memory: lane = row on the way in, 8 lanes = one 128-byte row segment on the
+          //      way out, so every global store instruction writes full, contiguous sectors (4 rows x 128 B).  (Measured: a win
+          //      for fp32 outputs; for the bf16 operand planes the extra instructions cost more than the scattered 32-byte
+          //      stores, so those keep the direct path below.)
           uint8_t* stg = epi_stage + (size_t)(warp - 2) * TC_EPI_STAGE_BYTES + lane * 128;
           const int sw = lane & 7;
 #pragma unroll
           for (int j = 0; j < 8; ++j) *(float4*)(stg + ((j ^ sw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           __syncwarp();
-          uint8_t* rd = epi_stage + (size_t)(warp - 2) * TC_EPI_STAGE_BYTES;
-          const bool want_stats = FUSED && a.stats != nullptr && oi == a.stats_oi;
+          const uint8_t* rd = epi_stage + (size_t)(warp - 2) * TC_EPI_STAGE_BYTES;
+          const int seg = lane & 7;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int row = (lane >> 3) + 4 * i;
-            float4* sp4 = (float4*)(rd + row * 128 + ((seg ^ (row & 7)) << 4));
-            const float4 raw = *sp4;
-            float t[4] = {raw.x + b4.x, raw.y + b4.y, raw.z + b4.z, raw.w + b4.w};
-            act_tile<4>(t, od.act);
-            if (has_res) {
-              float rv[4] = {(rres[i].x - mean4.x) * rstd4.x, (rres[i].y - mean4.y) * rstd4.y, (rres[i].z - mean4.z) * rstd4.z, (rres[i].w - mean4.w) * rstd4.w};
-              act_tile<4>(rv, a.res_act);
-              t[0] += rv[0]; t[1] += rv[1]; t[2] += rv[2]; t[3] += rv[3];
-            }
-            const bool row_ok = trow[i] != ~0ull;
-            if (want_stats) *sp4 = row_ok ? make_float4(t[0], t[1], t[2], t[3]) : make_float4(0.f, 0.f, 0.f, 0.f);      // rows outside the image count 0
-            if (row_ok && seg_on) *(float4*)((float*)od.out + zoff + (size_t)trow[i] * od.cstride + colbase + seg * 4) = make_float4(t[0], t[1], t[2], t[3]);
+            if (trow[i] == ~0ull) continue;
+            const uint4 dv = *(const uint4*)(rd + row * 128 + ((seg ^ (row & 7)) << 4));
+            const size_t o = (size_t)trow[i] * od.cstride + colbase;
+            if (seg * 4 < ncols) *(uint4*)((float*)od.out + zoff + o + seg * 4) = dv;
           }
-          if (want_stats) {
-            __syncwarp();
+          if (FUSED && a.stats != nullptr && oi == a.stats_oi) {
             // per-channel sum / sum of squares of this warp's 32 rows (one frame): lane = column, straight from the staging rows
             float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -410,28 +427,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             }
           }
           __syncwarp();       // staging rows are rewritten by the next chunk
-          continue;
-        }
-        load_acc();
-        if (a.bias) {
-          const float4* b4 = (const float4*)(a.bias + n0 + c);
-#pragma unroll
-          for (int j = 0; j < EPI_CHUNK / 4; ++j) {
-            if (4 * j >= ncols) break;
-            const float4 b = __ldg(b4 + j);
-            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-          }
-        }
-        act_tile<EPI_CHUNK>(v, od.act);
-        if (od.mode == OUT_F32_NCHW) {
-          // frames at the ABI edge: [f][N][Ho][Wo]; consecutive lanes are consecutive x -> coalesced per channel
-          if (valid) {
-#pragma unroll
-            for (int j = 0; j < EPI_CHUNK; ++j) {
-              const int n = n0 + c + j;
-              if (n < a.N) ((float*)od.out)[(((size_t)f * a.N + n) * a.Ho + oy) * a.Wo + ox] = v[j];
-            }
-          }
         } else {
           // bf16 operand planes, and narrow tiles (BN = 32): direct row-per-lane stores
           if (valid) {
