@@ -249,6 +249,12 @@ int ipk_test_convT3x3(const float* in, const float* w, const float* bias, float*
  * dims = {B,T,H,W,Cin,Cout, kt,ky,kx, st,sy,sx, pt,py,px}; precision IPK_PREC_FP32_SPLIT or IPK_PREC_BF16 */
 int ipk_test_conv3d(const float* in, const float* w, float* out, double* stats, const int32_t* dims, int32_t precision, void* stream);
 
+/* Timeline probe of the tcgen05 conv engine (profiles/tc_trace_probe.py): after ipk_tc_trace_enable(N, Kpad) every conv_tc launch whose
+ * packed weights have that N and padded K records 32 SM-clock stamps per CTA (entry, prologue, first TMA, per-tile MMA / epilogue
+ * milestones; slot 30 = global timer at entry); ipk_tc_trace_read copies [n_ctas][32] int64 of the LAST such launch to the host. */
+int ipk_tc_trace_enable(int32_t N, int32_t Kpad);
+int ipk_tc_trace_read(long long* host, int32_t n_ctas);
+
 #ifdef __cplusplus
 }
 #endif
