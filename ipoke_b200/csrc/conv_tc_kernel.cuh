@@ -444,13 +444,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         constexpr int ACT = decltype(ACT_C)::value;
         const TcOut& od = a.o[oi];
         const int act = ACT >= 0 ? ACT : od.act;
+        // the TMEM load of chunk c+1 is issued while chunk c is processed where a warp has several chunks per tile and the registers
+        // allow it (FUSED kernels: the statistics / residual state takes the registers; measured slower with the spills)
+        constexpr bool PREFETCH = HALF_COLS > EPI_CHUNK && FUSED == 0;
         uint32_t rr[EPI_CHUNK];
-        if constexpr (EPI_CHUNK == 32) tmem_ld32(tacc + (uint32_t)c_lo, rr);
-        else tmem_ld16(tacc + (uint32_t)c_lo, rr);
+        if constexpr (PREFETCH) {
+          if constexpr (EPI_CHUNK == 32) tmem_ld32(tacc + (uint32_t)c_lo, rr);
+          else tmem_ld16(tacc + (uint32_t)c_lo, rr);
+        }
 #pragma unroll 1
         for (int c = c_lo; c < c_hi; c += EPI_CHUNK) {
           const int ncols = min(EPI_CHUNK, c_hi - c);   // Npad is a multiple of 16: a 32-column chunk may be half valid
           float v[EPI_CHUNK];
+          if constexpr (!PREFETCH) {
+            if constexpr (EPI_CHUNK == 32) tmem_ld32(tacc + (uint32_t)c, rr);
+            else tmem_ld16(tacc + (uint32_t)c, rr);
+          }
           tmem_ld_wait_regs(rr);
 #pragma unroll
           for (int j = 0; j < EPI_CHUNK; ++j) v[j] = __uint_as_float(rr[j]);
@@ -470,8 +479,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             }
           }
           if (c + EPI_CHUNK < c_hi) {                  // next chunk's accumulators travel while this one is processed
-            if constexpr (EPI_CHUNK == 32) tmem_ld32(tacc + (uint32_t)(c + EPI_CHUNK), rr);
-            else tmem_ld16(tacc + (uint32_t)(c + EPI_CHUNK), rr);
+            if constexpr (PREFETCH) {
+              if constexpr (EPI_CHUNK == 32) tmem_ld32(tacc + (uint32_t)(c + EPI_CHUNK), rr);
+              else tmem_ld16(tacc + (uint32_t)(c + EPI_CHUNK), rr);
+            }
           } else if (last_range) {
             release_stage();
           }
