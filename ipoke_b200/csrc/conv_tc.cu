@@ -199,6 +199,12 @@ static int conv_tc_impl(const ConvW& w, const ConvIn& in, const ConvOut& out, co
 
   a.tiles_n = cdiv(w.Npad, BN);
   a.nsplit = nsplit;
+  a.fd_tiles_n.set(a.tiles_n);
+  a.fd_per.set(std::max(1, a.nsub) * a.tiles_n);
+  a.fd_tiles_mn.set(cdiv(a.tiles_m, CG) * a.tiles_n);
+  a.fd_txy.set(a.tiles_x * a.tiles_y);
+  a.fd_tiles_x.set(a.tiles_x);
+  a.fd_nsub.set(std::max(1, a.nsub));
   // ---- TMA stores for bf16 destinations: 32-row x 32-column boxes (one epilogue warp, one TMEM chunk) of the output viewed as
   //      (columns, x', y, frame).  Plain convs: x' = x.  Transposed-conv parity classes (ymul = xmul = 2, output 2H x 2W): the class
   //      offsets are folded into the view  [F][H][(a, x)][(b, column)]  (x' = a * W + x, column' = b * cstride + column), which is the

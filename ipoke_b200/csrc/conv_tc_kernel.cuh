@@ -16,6 +16,19 @@ constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr size_t TC_SMEM_BUDGET = 192 * 1024;      // pipeline stages
 constexpr size_t TC_EPI_STAGE_BYTES = 4096;          // per epilogue warp: 32 rows x 128 B transpose buffer (xor-swizzled)
 
+// division by a run-time constant without the ~20-instruction reciprocal sequence (the per-tile index arithmetic was 14 % of the fused
+// epilogue's samples): q = (umulhi(x, mul) + x) >> shr, exact for 0 <= x < 2^31
+struct FastDiv {
+  uint32_t mul = 0, shr = 0, d = 1;
+  __host__ void set(int div) {
+    d = (uint32_t)div;
+    shr = 0;
+    while ((1u << shr) < d) ++shr;
+    mul = (uint32_t)((((unsigned long long)1 << 32) * (((unsigned long long)1 << shr) - d)) / d + 1);
+  }
+  __device__ __forceinline__ int div(int x) const { return (int)((__umulhi((uint32_t)x, mul) + (uint32_t)x) >> shr); }
+};
+
 constexpr int TC_MAX_SUB = 4;
 struct TcSub {                    // one tap list + output phase (a parity class of a transposed conv; plain convs have one)
   int ntaps, yadd, xadd;
@@ -47,6 +60,7 @@ struct TcArgs {
   // bf16 operand planes leave through TMA stores (tma_out[i] != 0 for destination i): the warp's 32 rows x 32 columns are one box of the
   // output viewed as (columns, x', y, f); a transposed conv's parity class (a, b) is folded into the view: x' = a * W + x, column + b * cstride
   int tma_out[2], tma_xfold, tma_cfold[2];
+  FastDiv fd_tiles_n, fd_per, fd_tiles_mn, fd_txy, fd_tiles_x, fd_nsub;     // divisors of the per-tile index arithmetic (per = nsub * tiles_n)
   long long* trace;               // optional per-CTA timeline (ipk_tc_trace_enable): 32 clock stamps per CTA, null = off
   int halo_variant;               // HALO kernels: 1 = row-shifted descriptors carry the swizzle base offset, 2 = they do not
 };
@@ -91,14 +105,18 @@ __device__ __forceinline__ void tc_trace(const TcArgs& a, int slot) {
 __device__ __forceinline__ void tc_decode_tile(const TcArgs& a, int tiles_mn, int tile, int& z, int& mg, int& nt) {
   if (a.nsub > 1) {
     const int per = a.nsub * a.tiles_n;
-    mg = tile / per;
+    mg = a.fd_per.div(tile);
     const int rem = tile - mg * per;
-    z = rem / a.tiles_n;
-    nt = rem - z * a.tiles_n;
+    const int zi = a.fd_tiles_n.div(rem);
+    nt = rem - zi * a.tiles_n;
+    // the classes have 4 / 2 / 2 / 1 taps: rotate them with the M-tile group, otherwise a persistent CTA (stride = a multiple of nsub)
+    // would draw the same class every time (r02 timeline: 2x spread of the CTAs' finishing times)
+    const int zs = zi + mg;
+    z = zs - a.fd_nsub.div(zs) * a.nsub;
   } else {
-    z = tile / tiles_mn;
+    z = a.fd_tiles_mn.div(tile);
     const int rem = tile - z * tiles_mn;
-    mg = rem / a.tiles_n;
+    mg = a.fd_tiles_n.div(rem);
     nt = rem - mg * a.tiles_n;
   }
 }
@@ -220,8 +238,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         int z, mg, nt;                                                  // z: split-K slice, or sub-convolution when nsub > 1
         tc_decode_tile(a, tiles_mn, tile, z, mg, nt);
         const int mt = mg * CG + (int)crank;                            // beyond tiles_m: every box is out of bounds -> zero fill
-        const int tf = mt / txy, r2 = mt - tf * txy;
-        const int ty = r2 / a.tiles_x, tx = r2 - ty * a.tiles_x;
+        const int tf = a.fd_txy.div(mt), r2 = mt - tf * txy;
+        const int ty = a.fd_tiles_x.div(r2), tx = r2 - ty * a.tiles_x;
         const int f0 = tf * a.bf, y0 = ty * a.bh, x0 = tx * a.bw, n0 = nt * BN + (int)crank * WROWS;
         const TcSub& sb = a.sub[a.nsub > 1 ? z : 0];
         if constexpr (HALO) {
@@ -376,14 +394,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const int xl0 = r0w % a.bw, yl0 = (r0w / a.bw) % a.bh, fl0 = r0w / (a.bw * a.bh);
     int as = 0;
     uint32_t aph = 0;
+    int bias_nt = -1;                               // N tile whose bias this lane holds in b4 (one N tile: loaded once per kernel)
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
     // the accumulator stage goes back to the MMA issuer: the leader's barrier collects the epilogue warps of both CTAs of a pair
     const uint32_t tmem_empty_addr0 = CG == 2 ? mapa_u32(smem_u32(&tmem_empty_bar[0]), 0) : 0u;
     for (int tile = unit0; tile < total_tiles; tile += unit_step) {
       int z, mg, nt;
       tc_decode_tile(a, tiles_mn, tile, z, mg, nt);
       const int mt = mg * CG + (int)crank;
-      const int tf = mt / txy, r2 = mt - tf * txy;
-      const int ty = r2 / a.tiles_x, tx = r2 - ty * a.tiles_x;
+      const int tf = a.fd_txy.div(mt), r2 = mt - tf * txy;
+      const int ty = a.fd_tiles_x.div(r2), tx = r2 - ty * a.tiles_x;
       const int f = tf * a.bf + fl, y = ty * a.bh + yl, x = tx * a.bw + xl;
       const int n0 = nt * BN;
       const bool valid = (mt < a.tiles_m) && (f < a.F) && (y < a.H) && (x < a.W);
@@ -404,13 +424,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         fw = __shfl_sync(0xffffffffu, f, 0);          // frame of this warp's rows (fused residual / statistics: >= 32 pixels per frame)
       }
       // ---- requests that do not depend on the accumulator
-      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (a.bias != nullptr && lane * 4 < HALF_COLS && c_begin + lane * 4 < c_end) b4 = __ldg((const float4*)(a.bias + n0 + c_begin) + lane);
-      float4 resv[8];
+      if (nt != bias_nt) {
+        bias_nt = nt;
+        b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.bias != nullptr && lane * 4 < HALF_COLS && c_begin + lane * 4 < c_end) b4 = __ldg((const float4*)(a.bias + n0 + c_begin) + lane);
+      }
+      float4 resv[8], mr0 = make_float4(0.f, 1.f, 0.f, 1.f), mr1 = make_float4(0.f, 1.f, 0.f, 1.f);     // residual rows, their (mean, rstd) pairs
       auto load_res = [&](int c) __attribute__((always_inline)) {
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           resv[i] = trow[i] != ~0u ? __ldg((const float4*)(a.res + (size_t)trow[i] * a.res_cstride + n0 + c) + seg) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.res_mr != nullptr) {
+          const float4* mp = (const float4*)(a.res_mr + ((size_t)min(fw, a.F - 1) * a.N + n0 + c + seg * 4) * 2);
+          mr0 = __ldg(mp); mr1 = __ldg(mp + 1);
+        }
       };
       if (has_res && c_begin < c_end) load_res(c_begin);
 
@@ -439,9 +466,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       //      MODE 0: fp32 rows, transposed through shared memory (bias, activation, residual, statistics on the way out)
       //      MODE 1: bf16 planes through TMA stores        MODE 2: lane = row direct stores (NCHW frames, bf16 without TMA, narrow tiles)
       //      ACT: an Act value, or -1 = the destination's activation is applied through the run-time switch
-      auto run_range = [&](auto MODE_C, auto ACT_C, const int oi, const int c_lo, const int c_hi, const bool last_range) __attribute__((always_inline)) {
+      auto run_range = [&](auto MODE_C, auto ACT_C, auto RACT_C, const int oi, const int c_lo, const int c_hi, const bool last_range) __attribute__((always_inline)) {
         constexpr int MODE = decltype(MODE_C)::value;
         constexpr int ACT = decltype(ACT_C)::value;
+        constexpr int RACT = decltype(RACT_C)::value;       // activation of the residual branch (FUSED = 2), -1 = run-time switch
         const TcOut& od = a.o[oi];
         const int act = ACT >= 0 ? ACT : od.act;
         // the TMEM load of chunk c+1 is issued while chunk c is processed where a warp has several chunks per tile and the registers
@@ -499,13 +527,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             const int sw = lane & 7;
 #pragma unroll
             for (int j = 0; j < 8; ++j) st_shared_v4(stg_u32 + lane * 128 + ((j ^ sw) << 4), make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
-            float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (has_res && a.res_mr != nullptr) {
-              const float4* mp = (const float4*)(a.res_mr + ((size_t)min(fw, a.F - 1) * a.N + n0 + c + seg * 4) * 2);     // (mean, rstd) pairs
-              const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
-              sc = make_float4(m0.y, m0.w, m1.y, m1.w);
-              sh = make_float4(-m0.x * m0.y, -m0.z * m0.w, -m1.x * m1.y, -m1.z * m1.w);
-            }
+            const float4 sc = make_float4(mr0.y, mr0.w, mr1.y, mr1.w);
+            const float4 sh = make_float4(-mr0.x * mr0.y, -mr0.z * mr0.w, -mr1.x * mr1.y, -mr1.z * mr1.w);
             __syncwarp();
             const bool do_stats = FUSED != 0 && a.stats != nullptr && oi == a.stats_oi;
             const bool col_ok = seg * 4 < ncols;
@@ -520,7 +543,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               if (trow[i] == ~0u || !col_ok) continue;       // rows outside the image: nothing stored, nothing counted
               if (has_res) {
                 float rv[4] = {fmaf(resv[i].x, sc.x, sh.x), fmaf(resv[i].y, sc.y, sh.y), fmaf(resv[i].z, sc.z, sh.z), fmaf(resv[i].w, sc.w, sh.w)};
-                act_tile<4>(rv, a.res_act);
+                act_tile<4>(rv, RACT >= 0 ? RACT : a.res_act);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) t[k] += rv[k];
               }
@@ -628,15 +651,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       using std::integral_constant;
       auto dispatch = [&](const int oi, const int c_lo, const int c_hi, const bool last_range) __attribute__((always_inline)) {
         const TcOut& od = a.o[oi];
-        if (EPI_CHUNK == 32 && (has_res || od.mode == OUT_F32_NHWC)) {
-          if (od.act == ACT_NONE) run_range(integral_constant<int, 0>{}, integral_constant<int, ACT_NONE>{}, oi, c_lo, c_hi, last_range);
-          else run_range(integral_constant<int, 0>{}, integral_constant<int, -1>{}, oi, c_lo, c_hi, last_range);
-        } else if (!has_res && EPI_CHUNK == 32 && a.tma_out[oi]) {
-          if (od.act == ACT_ELU) run_range(integral_constant<int, 1>{}, integral_constant<int, ACT_ELU>{}, oi, c_lo, c_hi, last_range);
-          else if (od.act == ACT_RELU) run_range(integral_constant<int, 1>{}, integral_constant<int, ACT_RELU>{}, oi, c_lo, c_hi, last_range);
-          else run_range(integral_constant<int, 1>{}, integral_constant<int, -1>{}, oi, c_lo, c_hi, last_range);
-        } else if (!has_res) {
-          run_range(integral_constant<int, 2>{}, integral_constant<int, -1>{}, oi, c_lo, c_hi, last_range);
+        using IC = integral_constant<int, 0>;
+        if constexpr (has_res) {
+          // one fp32 destination with the residual branch: the ResBlocks use (no activation, ReLU on the residual)
+          if (od.act == ACT_NONE && a.res_act == ACT_RELU) run_range(IC{}, integral_constant<int, ACT_NONE>{}, integral_constant<int, ACT_RELU>{}, oi, c_lo, c_hi, last_range);
+          else run_range(IC{}, integral_constant<int, -1>{}, integral_constant<int, -1>{}, oi, c_lo, c_hi, last_range);
+        } else if (EPI_CHUNK == 32 && od.mode == OUT_F32_NHWC) {
+          if (od.act == ACT_NONE) run_range(IC{}, integral_constant<int, ACT_NONE>{}, integral_constant<int, -1>{}, oi, c_lo, c_hi, last_range);
+          else run_range(IC{}, integral_constant<int, -1>{}, integral_constant<int, -1>{}, oi, c_lo, c_hi, last_range);
+        } else if (EPI_CHUNK == 32 && a.tma_out[oi]) {
+          if (od.act == ACT_ELU) run_range(integral_constant<int, 1>{}, integral_constant<int, ACT_ELU>{}, integral_constant<int, -1>{}, oi, c_lo, c_hi, last_range);
+          else if (od.act == ACT_RELU) run_range(integral_constant<int, 1>{}, integral_constant<int, ACT_RELU>{}, integral_constant<int, -1>{}, oi, c_lo, c_hi, last_range);
+          else run_range(integral_constant<int, 1>{}, integral_constant<int, -1>{}, integral_constant<int, -1>{}, oi, c_lo, c_hi, last_range);
+        } else {
+          run_range(integral_constant<int, 2>{}, integral_constant<int, -1>{}, integral_constant<int, -1>{}, oi, c_lo, c_hi, last_range);
         }
       };
       if (c_begin >= c_end) {
