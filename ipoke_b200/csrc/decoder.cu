@@ -164,6 +164,9 @@ static void spade_maps(ipk_fs* d, const float* x0, int B, cudaStream_t st) {
 // videos start at video offset v0.
 static void decode_frames(ipk_fs* d, const float* h, int nv, int T, int v0, float* frames, cudaStream_t st) {
   const int F = nv * T, z = d->z, C0 = d->cfg.dec_channels[0];
+  // last SPADE block fused into the final conv (IPK_OUTCONV_FUSED=0: separate normalisation pass)
+  static const bool fused_out_env = []() { const char* e = getenv("IPK_OUTCONV_FUSED"); return !(e && e[0] == '0'); }();
+  const bool fused_out = fused_out_env && d->eng != IPK_PREC_FP32_SIMT;
   IPK_CHECK(F <= d->Fmax, IPK_ERR_INVALID, "decoder chunk of %d frames exceeds workspace (%d)", F, d->Fmax);
   // ---- in_block: ResBlock(z -> C0, norm='group') at 8x8 (util.py:140-192)
   {
@@ -248,6 +251,7 @@ static void decode_frames(ipk_fs* d, const float* h, int nv, int T, int v0, floa
     ProfScope pse(("dec.up.norm_spade.b" + bi).c_str(), st);
     // SPADE: GroupNorm(16, affine=False)(out) * (1 + gamma) + beta
     finalize_stats(d->sums, d->mr, F, P, ub.Cout, ub.groups, 1e-5f, st);
+    if (last && d->out_direct && fused_out) break;      // the final conv normalises its input tiles itself (out_conv.cu)
     NormApply sp; sp.x = d->bufS; sp.F = F; sp.C = ub.Cout; sp.P = P; sp.mr = d->mr; sp.spade = ub.SP + (size_t)v0 * P * 2 * ub.Cout; sp.T = T;
     if (last && d->out_direct) sp.out_f32 = (float*)d->bufA;      // the final conv reads fp32
     else to_operand(d, sp, d->bufA, d->bufA_lo);
@@ -256,7 +260,10 @@ static void decode_frames(ipk_fs* d, const float* h, int nv, int T, int v0, floa
   // ---- out_conv: 3x3 -> 3 channels + tanh, written straight into the NCHW frame tensor
   {
     ProfScope ps("dec.out_conv", st);
-    if (d->out_direct) {
+    if (d->out_direct && fused_out) {
+      const UpBlock& ub = d->blocks.back();
+      out_conv_run(d->out_direct, d->bufS, frames, F, d->S, st, d->mr, ub.SP + (size_t)v0 * d->S * d->S * 2 * ub.Cout, T);
+    } else if (d->out_direct) {
       out_conv_run(d->out_direct, (const float*)d->bufA, frames, F, d->S, st);
     } else {
       const int Cl = d->cfg.dec_channels[d->nd - 1];

@@ -73,7 +73,10 @@ constexpr int OUT_CONV_PACKED_FLOATS = 9 * 64 * 3 + 3;
 void out_conv_pack(const float* w_oihw, const float* sigma, const float* bias, float* dst, cudaStream_t st);
 OutConvPlan* out_conv_plan_create(const float* w_dev_packed, cudaStream_t st);
 void out_conv_plan_destroy(OutConvPlan* p);
-void out_conv_run(const OutConvPlan* p, const float* in_nhwc, float* out_nchw, int F, int S, cudaStream_t st);
+// mr / spade (optional, both or none): the input is normalised in the staged tile first, y = (x - mean) * rstd * spade_gamma1 + spade_beta
+// with mr [F][64][2] and spade [videos][S*S][128] = (1 + gamma | beta), video = frame / T
+void out_conv_run(const OutConvPlan* p, const float* in_nhwc, float* out_nchw, int F, int S, cudaStream_t st, const float* mr = nullptr,
+                  const float* spade = nullptr, int T = 1);
 
 // weight-norm row scale: oscale[n] = g[n] / ||v[n,:]||_2   (torch.nn.utils.weight_norm, dim=0)
 void weight_norm_scale(const float* v, const float* g, float* oscale, int N, int row, cudaStream_t st);

@@ -4,6 +4,10 @@
 // N = 3 makes this layer bandwidth-shaped: a GEMM formulation re-reads the 64-channel input once per tap for almost no
 // math.  Here a CTA stages an (8+2) x (32+2) pixel halo tile of the fp32 NHWC input in shared memory ONCE (padded rows:
 // conflict-free LDS.128) and the 1 728 folded weights live in registers, 108 per lane (one channel quad each).
+//
+// Fused SPADE (Spade.forward, util.py:494-499): when `mr` / `spade` are given the input is the last up-block's raw output and the staged
+// tile is normalised in place before the taps read it,  y = (x - mean[f,c]) * rstd[f,c] * (1 + gamma)[v,p,c] + beta[v,p,c]  (zero outside
+// the image: the conv pads the NORMALISED tensor) -- the separate norm pass wrote and this kernel re-read 4.3 GB per 1 024 frames.
 #include "elementwise.cuh"
 
 namespace ipk {
@@ -20,7 +24,7 @@ struct OutConvParams {
 // sliding 3x3 window of float4 activations; the 16 channel-quad partial sums of a pixel are combined with four xor-shuffles.
 __global__ void __launch_bounds__(256, 1)
 out_conv_kernel(const float* __restrict__ in, float* __restrict__ out, int F, int S, int tiles_x, int tiles_y,
-                const float* __restrict__ wpk) {
+                const float* __restrict__ wpk, const float* __restrict__ mr, const float* __restrict__ spade, int T) {
   extern __shared__ __align__(16) float halo[];      // 2 x [(OC_TH+2)*(OC_TW+2)][OC_PS], then out tile [3][OC_TH][OC_TW]
   constexpr int HP = (OC_TH + 2) * (OC_TW + 2), C4 = OC_CIN / 4;
   float* otile = halo + 2 * HP * OC_PS;
@@ -70,6 +74,43 @@ out_conv_kernel(const float* __restrict__ in, float* __restrict__ out, int F, in
       asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
+    if (spade != nullptr) {
+      // in-place SPADE normalisation of the staged tile: thread = (channel quad tid % 16, pixels tid / 16 + 16 k)
+      float* hw = halo + (size_t)buf * HP * OC_PS;
+      const int q = tid & 15;
+      const float4 m0 = __ldg((const float4*)(mr + ((size_t)f * OC_CIN + q * 4) * 2)), m1 = __ldg((const float4*)(mr + ((size_t)f * OC_CIN + q * 4) * 2) + 1);
+      const float* spv = spade + (size_t)(f / T) * S * S * (2 * OC_CIN) + q * 4;
+      constexpr int NB = 6;                       // independent (gamma, beta) load pairs in flight per thread
+      for (int px0 = tid >> 4; px0 < HP; px0 += 16 * NB) {
+        float4 g[NB], bt[NB];
+        bool ok[NB];
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+          const int px = px0 + 16 * k;
+          const int hy = px / (OC_TW + 2), hx = px - hy * (OC_TW + 2);
+          const int y = y0 + hy - 1, x = x0 + hx - 1;
+          ok[k] = px < HP && y >= 0 && y < S && x >= 0 && x < S;
+          if (ok[k]) {
+            const float* sp = spv + ((size_t)y * S + x) * (2 * OC_CIN);
+            g[k] = __ldg((const float4*)sp);
+            bt[k] = __ldg((const float4*)(sp + OC_CIN));
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+          if (ok[k]) {
+            float4* hp = (float4*)(hw + (px0 + 16 * k) * OC_PS + q * 4);
+            float4 v = *hp;
+            v.x = (v.x - m0.x) * m0.y * g[k].x + bt[k].x;
+            v.y = (v.y - m0.z) * m0.w * g[k].y + bt[k].y;
+            v.z = (v.z - m1.x) * m1.y * g[k].z + bt[k].z;
+            v.w = (v.w - m1.z) * m1.w * g[k].w + bt[k].w;
+            *hp = v;
+          }
+        }
+      }
+      __syncthreads();
+    }
     // ---- this half-warp: output row `warp`, columns 16*strip .. 16*strip+15 (halo coords: rows warp..warp+2, cols +0..+2)
     const float* hrow = hb + (warp * (OC_TW + 2) + strip * 16) * OC_PS + c4 * 4;
     float4 win[3][3];
@@ -139,13 +180,13 @@ OutConvPlan* out_conv_plan_create(const float* w_dev_packed, cudaStream_t st) {
 }
 void out_conv_plan_destroy(OutConvPlan* p) { delete p; }
 
-void out_conv_run(const OutConvPlan* p, const float* in_nhwc, float* out_nchw, int F, int S, cudaStream_t st) {
+void out_conv_run(const OutConvPlan* p, const float* in_nhwc, float* out_nchw, int F, int S, cudaStream_t st, const float* mr, const float* spade, int T) {
   const int tiles_x = cdiv(S, OC_TW), tiles_y = cdiv(S, OC_TH);
   const long long tiles = (long long)F * tiles_x * tiles_y;
   if (tiles == 0) return;
   const size_t smem = ((size_t)2 * (OC_TH + 2) * (OC_TW + 2) * OC_PS + 3 * OC_TH * OC_TW) * sizeof(float);
   const int grid = (int)std::min<long long>(tiles, 148LL);
-  launch_k(out_conv_kernel, dim3(grid), dim3(256), smem, st, in_nhwc, out_nchw, F, S, tiles_x, tiles_y, p->wpk);
+  launch_k(out_conv_kernel, dim3(grid), dim3(256), smem, st, in_nhwc, out_nchw, F, S, tiles_x, tiles_y, p->wpk, mr, spade, std::max(1, T));
 }
 
 // packs OIHW [3][64][3][3] (optionally divided by the spectral-norm sigma) + bias into the layout above
