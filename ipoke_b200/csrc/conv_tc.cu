@@ -40,19 +40,19 @@ static EncodeTiledFn get_encode() {
 }
 
 struct MapKey {
-  const void* p; long long d0, d1, d2, d3, s1, s2, s3; int b0, b1, b2, b3, rank, sw;
+  const void* p; long long d0, d1, d2, d3, s1, s2, s3; int b0, b1, b2, b3, rank, sw, dt;
   bool operator<(const MapKey& o) const {
-    return std::tie(p, d0, d1, d2, d3, s1, s2, s3, b0, b1, b2, b3, rank, sw) <
-           std::tie(o.p, o.d0, o.d1, o.d2, o.d3, o.s1, o.s2, o.s3, o.b0, o.b1, o.b2, o.b3, o.rank, o.sw);
+    return std::tie(p, d0, d1, d2, d3, s1, s2, s3, b0, b1, b2, b3, rank, sw, dt) <
+           std::tie(o.p, o.d0, o.d1, o.d2, o.d3, o.s1, o.s2, o.s3, o.b0, o.b1, o.b2, o.b3, o.rank, o.sw, o.dt);
   }
 };
 static std::map<MapKey, CUtensorMap> g_maps;
 static std::mutex g_maps_mu;
 
 static CUtensorMap make_map(const void* base, int rank, const long long* dims, const long long* strides_bytes, const int* box,
-                            CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+                            CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B, CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
   MapKey k{base, dims[0], dims[1], rank > 2 ? dims[2] : 1, rank > 3 ? dims[3] : 1, strides_bytes[0], rank > 2 ? strides_bytes[1] : 0,
-           rank > 3 ? strides_bytes[2] : 0, box[0], box[1], rank > 2 ? box[2] : 1, rank > 3 ? box[3] : 1, rank, (int)swz};
+           rank > 3 ? strides_bytes[2] : 0, box[0], box[1], rank > 2 ? box[2] : 1, rank > 3 ? box[3] : 1, rank, (int)swz, (int)dt};
   std::lock_guard<std::mutex> lk(g_maps_mu);
   auto it = g_maps.find(k);
   if (it != g_maps.end()) return it->second;
@@ -60,7 +60,7 @@ static CUtensorMap make_map(const void* base, int rank, const long long* dims, c
   cuuint64_t gd[4]; cuuint64_t gs[3]; cuuint32_t bx[4]; cuuint32_t es[4] = {1, 1, 1, 1};
   for (int i = 0; i < rank; ++i) { gd[i] = (cuuint64_t)dims[i]; bx[i] = (cuuint32_t)box[i]; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = (cuuint64_t)strides_bytes[i];
-  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+  CUresult r = get_encode()(&m, dt, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   IPK_CHECK(r == CUDA_SUCCESS, IPK_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): rank %d dims [%lld,%lld,%lld,%lld] box [%d,%d,%d,%d] stride1 %lld",
@@ -90,6 +90,13 @@ extern "C" int ipk_tc_trace_read(long long* host, int32_t n_ctas) {
   IPK_CATCH
 }
 namespace ipk {
+
+static int sm_count_host() { return tc_sm_count(); }
+
+// un-swizzled fp32 tiled map (out_conv.cu); out-of-bounds elements of a box read as zero
+CUtensorMap tc_make_map_f32(const float* base, int rank, const long long* dims, const long long* strides_bytes, const int* box) {
+  return make_map(base, rank, dims, strides_bytes, box, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+}
 
 static int conv_tc_impl(const ConvW& w, const ConvIn& in, const ConvOut& out, const ConvSub* subs, int nsub, int nsplit, cudaStream_t st) {
   IPK_CHECK(w.w_hi != nullptr, IPK_ERR_STATE, "conv_tc_run: layer was not packed for the tensor-core engine");
@@ -184,6 +191,11 @@ static int conv_tc_impl(const ConvW& w, const ConvIn& in, const ConvOut& out, co
     }
   }
   a.tiles_m = a.tiles_x * a.tiles_y * tiles_f;
+  // Small batches (the GUI's B = 1 call, testing/gui.py:139-148: one M tile): the launch is bound by how fast the CTAs can stream the
+  // weights, so narrower N tiles that put the layer on more SMs win over MMA efficiency -- halve the tile while the launch would leave
+  // more than half of the machine idle and the main loop is long enough to matter.
+  if (!out.res && !out.stats && !(out.second && out.second->stats))
+    while (BN > 32 && a.tiles_m <= 2 && (long long)a.tiles_m * cdiv(w.Npad, BN) * std::max(1, nsub) * nsplit * 2 <= sm_count_host() && max_taps * a.nkb >= 8) BN /= 2;
   // CTA pairs (cta_group::2): two consecutive M tiles share one N tile and each CTA stages half of its weights (IPK_TC_CTA2=0 disables,
   // =2 also pairs short main loops).
   static const int cta2_env = []() { const char* e = getenv("IPK_TC_CTA2"); return e ? atoi(e) : 1; }();

@@ -1,35 +1,51 @@
 // Final decoder convolution: 3x3, 64 -> 3 channels, + tanh, fp32 FFMA, frames written NCHW at the ABI edge
-// (SpadeCondConvDecoder.out_conv, models/modules/autoencoders/fully_conv_models.py:163-164,176).
+// (SpadeCondConvDecoder.out_conv, models/modules/autoencoders/fully_conv_models.py:163-164,176), with the last SPADE block
+// (Spade.forward, util.py:494-499) fused in front of it.
 //
-// N = 3 makes this layer bandwidth-shaped: a GEMM formulation re-reads the 64-channel input once per tap for almost no
-// math.  Here a CTA stages an (8+2) x (32+2) pixel halo tile of the fp32 NHWC input in shared memory ONCE (padded rows:
-// conflict-free LDS.128) and the 1 728 folded weights live in registers, 108 per lane (one channel quad each).
+// N = 3 makes this layer bandwidth-shaped: a GEMM formulation re-reads the 64-channel input once per tap for almost no math.  Here a
+// CTA works on 8 x 16 output pixels: the (8+2) x (16+2) halo tile of the fp32 NHWC input arrives as ONE TMA box (out-of-bounds pixels
+// zero-filled = the conv's padding; no per-thread address arithmetic), double-buffered so that tile i+1 travels while tile i is
+// computed, and the 1 728 folded weights live in registers, 108 per lane (one channel quad each).
 //
-// Fused SPADE (Spade.forward, util.py:494-499): when `mr` / `spade` are given the input is the last up-block's raw output and the staged
-// tile is normalised in place before the taps read it,  y = (x - mean[f,c]) * rstd[f,c] * (1 + gamma)[v,p,c] + beta[v,p,c]  (zero outside
-// the image: the conv pads the NORMALISED tensor) -- the separate norm pass wrote and this kernel re-read 4.3 GB per 1 024 frames.
+// Fused SPADE: when `mr` / `spade` are given the input is the last up-block's RAW output; the matching box of the (1 + gamma | beta)
+// maps lands beside the tile and the tile is normalised in place before the taps read it,
+//     y = (x - mean[f,c]) * rstd[f,c] * (1 + gamma)[v,p,c] + beta[v,p,c]
+// (zero outside the image, because the maps' box is zero-filled there too: the conv pads the NORMALISED tensor).  The separate pass
+// wrote, and this kernel re-read, a 4.3 GB normalised copy per 1 024 frames.
+#include <cuda.h>
 #include "elementwise.cuh"
+#include "tc_ptx.cuh"
 
 namespace ipk {
 
-constexpr int OC_CIN = 64, OC_TH = 8, OC_TW = 32, OC_PS = OC_CIN + 4;     // pixel stride in floats (pad 4: bank spread)
+CUtensorMap tc_make_map_f32(const float* base, int rank, const long long* dims, const long long* strides_bytes, const int* box);   // conv_tc.cu
 
-struct OutConvParams {
-  float w[9 * OC_CIN * 3];     // [tap = ky*3+kx][c][o]
-  float bias[3];
-};
+constexpr int OC_CIN = 64, OC_TH = 8, OC_TW = 16, OC_HW = OC_TW + 2, OC_HP = (OC_TH + 2) * OC_HW;     // 180 halo pixels
+constexpr int OC_X_BYTES = OC_HP * OC_CIN * 4, OC_SP_BYTES = OC_HP * 2 * OC_CIN * 4;
+constexpr size_t OC_SMEM = 2 * OC_X_BYTES + OC_SP_BYTES + 3 * OC_TH * OC_TW * 4 + 64;
 
-// 256 threads = 8 warps; warp w owns output row w of the 8 x 32 tile, each half-warp a 16-column strip; lane = (strip,
-// channel quad c4).  A lane keeps the 108 weights of its channel quad in registers for the whole (persistent) kernel and a
-// sliding 3x3 window of float4 activations; the 16 channel-quad partial sums of a pixel are combined with four xor-shuffles.
+// 256 threads = 8 warps; warp w owns output row w of the tile, each half-warp an 8-column strip; lane = (strip, channel quad c4).  A
+// lane keeps the 108 weights of its channel quad in registers for the whole (persistent) kernel and a sliding 3x3 window of float4
+// activations.  The 16 channel-quad partial sums of the strip's 8 pixels x 3 outputs are combined by a halving exchange (24 shuffles per
+// lane instead of 96): after the xor-8 / 4 / 2 steps a lane holds the three outputs of pixel c4 >> 1.
 __global__ void __launch_bounds__(256, 1)
-out_conv_kernel(const float* __restrict__ in, float* __restrict__ out, int F, int S, int tiles_x, int tiles_y,
-                const float* __restrict__ wpk, const float* __restrict__ mr, const float* __restrict__ spade, int T) {
-  extern __shared__ __align__(16) float halo[];      // 2 x [(OC_TH+2)*(OC_TW+2)][OC_PS], then out tile [3][OC_TH][OC_TW]
-  constexpr int HP = (OC_TH + 2) * (OC_TW + 2), C4 = OC_CIN / 4;
-  float* otile = halo + 2 * HP * OC_PS;
+out_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmSP, float* __restrict__ out, int F, int S,
+                int tiles_x, int tiles_y, const float* __restrict__ wpk, const float* __restrict__ mr, int has_spade, int T) {
+  extern __shared__ __align__(1024) uint8_t oc_smem[];
+  float* xb = (float*)oc_smem;                                   // [2][OC_HP][64]
+  float* spb = (float*)(oc_smem + 2 * OC_X_BYTES);               // [OC_HP][128]
+  float* otile = (float*)(oc_smem + 2 * OC_X_BYTES + OC_SP_BYTES);
+  uint64_t* full_x = (uint64_t*)(otile + 3 * OC_TH * OC_TW);     // [2]
+  uint64_t* full_sp = full_x + 2;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int c4 = lane & 15, strip = lane >> 4;
+  if (tid == 0) {
+    prefetch_tensormap(&tmX);
+    if (has_spade) prefetch_tensormap(&tmSP);
+    mbar_init(&full_x[0], 1); mbar_init(&full_x[1], 1); mbar_init(full_sp, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
   pdl_wait();
   pdl_trigger();
   float wr[9][4][3];
@@ -43,86 +59,63 @@ out_conv_kernel(const float* __restrict__ in, float* __restrict__ out, int F, in
 
   const int tpf = tiles_x * tiles_y;
   const int ntiles = F * tpf;
-  // halo tiles are double-buffered: tile i+1 is fetched with cp.async (zero-fill outside the image = conv padding) while
-  // tile i is being computed
-  auto stage = [&](int tile, float* dst) {
+  auto issue = [&](int tile, int b) {      // thread 0: the boxes of `tile` -> x buffer b (+ the SPADE maps' buffer)
     const int f = tile / tpf, r = tile - f * tpf;
     const int y0 = (r / tiles_x) * OC_TH, x0 = (r % tiles_x) * OC_TW;
-    const float* inf = in + (size_t)f * S * S * OC_CIN;
-    for (int i = tid; i < HP * C4; i += 256) {
-      const int px = i / C4, q = i - px * C4;
-      const int hy = px / (OC_TW + 2), hx = px - hy * (OC_TW + 2);
-      const int y = y0 + hy - 1, x = x0 + hx - 1;
-      const bool ok = y >= 0 && y < S && x >= 0 && x < S;
-      const float* src = ok ? inf + ((size_t)y * S + x) * OC_CIN + q * 4 : inf;
-      const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + px * OC_PS + q * 4);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(ok ? 16 : 0) : "memory");
+    mbar_expect_tx(&full_x[b], OC_X_BYTES);
+    tma_load_4d(xb + (size_t)b * OC_HP * OC_CIN, &tmX, &full_x[b], 0, x0 - 1, y0 - 1, f);
+    if (has_spade) {
+      mbar_expect_tx(full_sp, OC_SP_BYTES);
+      tma_load_4d(spb, &tmSP, full_sp, 0, x0 - 1, y0 - 1, f / T);
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  int buf = 0;
-  if (blockIdx.x < ntiles) stage(blockIdx.x, halo);
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  if (tid == 0 && (int)blockIdx.x < ntiles) issue(blockIdx.x, 0);
+  int it = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
     const int f = tile / tpf, r = tile - f * tpf;
     const int y0 = (r / tiles_x) * OC_TH, x0 = (r % tiles_x) * OC_TW;
-    const float* hb = halo + (size_t)buf * HP * OC_PS;
-    const int nxt = tile + gridDim.x;
-    if (nxt < ntiles) {
-      stage(nxt, halo + (size_t)(buf ^ 1) * HP * OC_PS);     // that buffer was released by the barrier ending the previous tile
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    float* hb = xb + (size_t)buf * OC_HP * OC_CIN;
+    float4 m0 = make_float4(0.f, 1.f, 0.f, 1.f), m1 = m0;
+    if (has_spade) {
+      const float4* mp = (const float4*)(mr + ((size_t)f * OC_CIN + (tid & 15) * 4) * 2);
+      m0 = __ldg(mp); m1 = __ldg(mp + 1);
+    }
+    mbar_wait(&full_x[buf], (uint32_t)((it >> 1) & 1));
+    if (has_spade) {
+      mbar_wait(full_sp, (uint32_t)(it & 1));
+      // in-place normalisation: thread = (channel quad tid % 16, pixels tid / 16 + 16 k)
+      const int q = tid & 15;
+#pragma unroll 4
+      for (int px = tid >> 4; px < OC_HP; px += 16) {
+        float4* hp = (float4*)(hb + px * OC_CIN + q * 4);
+        const float4 g = *(const float4*)(spb + px * (2 * OC_CIN) + q * 4), bt = *(const float4*)(spb + px * (2 * OC_CIN) + OC_CIN + q * 4);
+        float4 v = *hp;
+        v.x = (v.x - m0.x) * m0.y * g.x + bt.x;
+        v.y = (v.y - m0.z) * m0.w * g.y + bt.y;
+        v.z = (v.z - m1.x) * m1.y * g.z + bt.z;
+        v.w = (v.w - m1.z) * m1.w * g.w + bt.w;
+        *hp = v;
+      }
+      fence_proxy_async_shared();      // the maps' buffer is about to be overwritten by the next tile's box
     }
     __syncthreads();
-    if (spade != nullptr) {
-      // in-place SPADE normalisation of the staged tile: thread = (channel quad tid % 16, pixels tid / 16 + 16 k)
-      float* hw = halo + (size_t)buf * HP * OC_PS;
-      const int q = tid & 15;
-      const float4 m0 = __ldg((const float4*)(mr + ((size_t)f * OC_CIN + q * 4) * 2)), m1 = __ldg((const float4*)(mr + ((size_t)f * OC_CIN + q * 4) * 2) + 1);
-      const float* spv = spade + (size_t)(f / T) * S * S * (2 * OC_CIN) + q * 4;
-      constexpr int NB = 6;                       // independent (gamma, beta) load pairs in flight per thread
-      for (int px0 = tid >> 4; px0 < HP; px0 += 16 * NB) {
-        float4 g[NB], bt[NB];
-        bool ok[NB];
-#pragma unroll
-        for (int k = 0; k < NB; ++k) {
-          const int px = px0 + 16 * k;
-          const int hy = px / (OC_TW + 2), hx = px - hy * (OC_TW + 2);
-          const int y = y0 + hy - 1, x = x0 + hx - 1;
-          ok[k] = px < HP && y >= 0 && y < S && x >= 0 && x < S;
-          if (ok[k]) {
-            const float* sp = spv + ((size_t)y * S + x) * (2 * OC_CIN);
-            g[k] = __ldg((const float4*)sp);
-            bt[k] = __ldg((const float4*)(sp + OC_CIN));
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < NB; ++k) {
-          if (ok[k]) {
-            float4* hp = (float4*)(hw + (px0 + 16 * k) * OC_PS + q * 4);
-            float4 v = *hp;
-            v.x = (v.x - m0.x) * m0.y * g[k].x + bt[k].x;
-            v.y = (v.y - m0.z) * m0.w * g[k].y + bt[k].y;
-            v.z = (v.z - m1.x) * m1.y * g[k].z + bt[k].z;
-            v.w = (v.w - m1.z) * m1.w * g[k].w + bt[k].w;
-            *hp = v;
-          }
-        }
-      }
-      __syncthreads();
-    }
-    // ---- this half-warp: output row `warp`, columns 16*strip .. 16*strip+15 (halo coords: rows warp..warp+2, cols +0..+2)
-    const float* hrow = hb + (warp * (OC_TW + 2) + strip * 16) * OC_PS + c4 * 4;
+    // next tile's boxes: the other x buffer was released by the barrier ending the previous tile, the maps' buffer just now
+    if (tid == 0 && tile + (int)gridDim.x < ntiles) issue(tile + gridDim.x, buf ^ 1);
+
+    // ---- this half-warp: output row `warp`, columns 8*strip .. 8*strip+7 (halo coords: rows warp..warp+2, cols +0..+2)
+    const float* hrow = hb + (warp * OC_HW + strip * 8) * OC_CIN + c4 * 4;
     float4 win[3][3];
 #pragma unroll
     for (int rr = 0; rr < 3; ++rr) {
-      win[rr][0] = *(const float4*)(hrow + (rr * (OC_TW + 2) + 0) * OC_PS);
-      win[rr][1] = *(const float4*)(hrow + (rr * (OC_TW + 2) + 1) * OC_PS);
+      win[rr][0] = *(const float4*)(hrow + (rr * OC_HW + 0) * OC_CIN);
+      win[rr][1] = *(const float4*)(hrow + (rr * OC_HW + 1) * OC_CIN);
     }
+    float acc[24];       // [pixel j][output o]
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
+    for (int j = 0; j < 8; ++j) {
 #pragma unroll
-      for (int rr = 0; rr < 3; ++rr) win[rr][2] = *(const float4*)(hrow + (rr * (OC_TW + 2) + j + 2) * OC_PS);
+      for (int rr = 0; rr < 3; ++rr) win[rr][2] = *(const float4*)(hrow + (rr * OC_HW + j + 2) * OC_CIN);
       float a0 = 0.f, a1 = 0.f, a2 = 0.f;
 #pragma unroll
       for (int rr = 0; rr < 3; ++rr)
@@ -136,30 +129,46 @@ out_conv_kernel(const float* __restrict__ in, float* __restrict__ out, int F, in
             a2 = fmaf(av[k], wr[rr * 3 + cc][k][2], a2);
           }
         }
-#pragma unroll
-      for (int off = 8; off > 0; off >>= 1) {        // combine the 16 channel quads of this pixel (stays inside the half-warp)
-        a0 += __shfl_xor_sync(0xffffffffu, a0, off);
-        a1 += __shfl_xor_sync(0xffffffffu, a1, off);
-        a2 += __shfl_xor_sync(0xffffffffu, a2, off);
-      }
-      if (c4 == 0) {
-        const int col = strip * 16 + j;
-        otile[(0 * OC_TH + warp) * OC_TW + col] = a0 + b0;      // tanh is applied by the coalesced store pass
-        otile[(1 * OC_TH + warp) * OC_TW + col] = a1 + b1;
-        otile[(2 * OC_TH + warp) * OC_TW + col] = a2 + b2;
-      }
+      acc[3 * j] = a0; acc[3 * j + 1] = a1; acc[3 * j + 2] = a2;
 #pragma unroll
       for (int rr = 0; rr < 3; ++rr) { win[rr][0] = win[rr][1]; win[rr][1] = win[rr][2]; }
     }
+    // halving exchange over the 16 channel quads: keep the half of the values selected by this lane's bit, add the partner's
+    {
+      const bool h8 = (c4 & 8) != 0, h4 = (c4 & 4) != 0, h2 = (c4 & 2) != 0;
+      float s12[12], s6[6], s3[3];
+#pragma unroll
+      for (int i = 0; i < 12; ++i) {
+        const float keep = h8 ? acc[12 + i] : acc[i], send = h8 ? acc[i] : acc[12 + i];
+        s12[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const float keep = h4 ? s12[6 + i] : s12[i], send = h4 ? s12[i] : s12[6 + i];
+        s6[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const float keep = h2 ? s6[3 + i] : s6[i], send = h2 ? s6[i] : s6[3 + i];
+        s3[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) s3[i] += __shfl_xor_sync(0xffffffffu, s3[i], 1);
+      if ((c4 & 1) == 0) {
+        const int col = strip * 8 + (c4 >> 1);
+        otile[(0 * OC_TH + warp) * OC_TW + col] = s3[0] + b0;      // tanh is applied by the coalesced store pass
+        otile[(1 * OC_TH + warp) * OC_TW + col] = s3[1] + b1;
+        otile[(2 * OC_TH + warp) * OC_TW + col] = s3[2] + b2;
+      }
+    }
     __syncthreads();
-    // ---- coalesced NCHW store of the 3 x 8 x 32 tile
+    // ---- coalesced NCHW store of the 3 x 8 x 16 tile
     for (int i = tid; i < 3 * OC_TH * OC_TW; i += 256) {
       const int col = i % OC_TW, row = (i / OC_TW) % OC_TH, o = i / (OC_TW * OC_TH);
       const int y = y0 + row, x = x0 + col;
       if (y < S && x < S) out[((size_t)f * 3 + o) * S * S + (size_t)y * S + x] = tanhf(otile[i]);
     }
     __syncthreads();     // tile buffer and output tile free for reuse
-    buf ^= 1;
   }
 }
 
@@ -173,7 +182,7 @@ OutConvPlan* out_conv_plan_create(const float* w_dev_packed, cudaStream_t st) {
   static bool attr_set[IPK_MAX_DEVICES] = {false};
   const int slot = current_device_slot();
   if (!attr_set[slot]) {
-    IPK_CUDA(cudaFuncSetAttribute(out_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    IPK_CUDA(cudaFuncSetAttribute(out_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OC_SMEM));
     attr_set[slot] = true;
   }
   return p;
@@ -184,9 +193,21 @@ void out_conv_run(const OutConvPlan* p, const float* in_nhwc, float* out_nchw, i
   const int tiles_x = cdiv(S, OC_TW), tiles_y = cdiv(S, OC_TH);
   const long long tiles = (long long)F * tiles_x * tiles_y;
   if (tiles == 0) return;
-  const size_t smem = ((size_t)2 * (OC_TH + 2) * (OC_TW + 2) * OC_PS + 3 * OC_TH * OC_TW) * sizeof(float);
+  IPK_CHECK((mr == nullptr) == (spade == nullptr), IPK_ERR_INVALID, "out_conv_run: the fused SPADE needs both the statistics and the maps");
+  T = std::max(1, T);
+  long long xd[4] = {OC_CIN, S, S, F};
+  long long xs[3] = {OC_CIN * 4LL, (long long)S * OC_CIN * 4, (long long)S * S * OC_CIN * 4};
+  int xbox[4] = {OC_CIN, OC_HW, OC_TH + 2, 1};
+  const CUtensorMap mX = tc_make_map_f32(in_nhwc, 4, xd, xs, xbox);
+  CUtensorMap mSP = mX;
+  if (spade) {
+    long long sd[4] = {2 * OC_CIN, S, S, (F + T - 1) / T};
+    long long ss[3] = {2 * OC_CIN * 4LL, (long long)S * 2 * OC_CIN * 4, (long long)S * S * 2 * OC_CIN * 4};
+    int sbox[4] = {2 * OC_CIN, OC_HW, OC_TH + 2, 1};
+    mSP = tc_make_map_f32(spade, 4, sd, ss, sbox);
+  }
   const int grid = (int)std::min<long long>(tiles, 148LL);
-  launch_k(out_conv_kernel, dim3(grid), dim3(256), smem, st, in_nhwc, out_nchw, F, S, tiles_x, tiles_y, p->wpk, mr, spade, std::max(1, T));
+  launch_k(out_conv_kernel, dim3(grid), dim3(256), OC_SMEM, st, mX, mSP, out_nchw, F, S, tiles_x, tiles_y, p->wpk, mr, spade ? 1 : 0, T);
 }
 
 // packs OIHW [3][64][3][3] (optionally divided by the spectral-norm sigma) + bias into the layout above
