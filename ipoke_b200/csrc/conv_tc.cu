@@ -181,13 +181,21 @@ static int conv_tc_impl(const ConvW& w, const ConvIn& in, const ConvOut& out, co
   const __nv_bfloat16* ahi = (const __nv_bfloat16*)in.p + in.coff;
   CUtensorMap mA_hi = make_map(ahi, 4, ad, as, ab);
   CUtensorMap mA_lo = split ? make_map((const __nv_bfloat16*)in.p_lo + in.coff, 4, ad, as, ab) : mA_hi;
-  // N tile: weigh padded columns (MMA work) against A-tile re-reads (one per N tile)
-  int BN = 32;
+  // N tile: `bn` columns per tile, any multiple of 16 up to 256 (UMMA N), run by the kernel instantiation with the next larger BN
+  // (32 / 64 / 128 / 256: shared-memory and TMEM capacity).  Weigh padded columns (MMA work) against A-tile re-reads (one per N tile).
+  int BN = 32, bn_eff = 32;
   {
+    static const int flex_env = []() { const char* e = getenv("IPK_TC_FLEX_BN"); return e ? atoi(e) : 1; }();     // 0: power-of-two tiles only
     double best = 1e30;
-    for (int bn : {256, 128, 64, 32}) {
-      double cost = (double)cdiv(w.Npad, bn) * bn * (1.0 + 32.0 / bn);
-      if (cost < best) { best = cost; BN = bn; }
+    const int tn0 = cdiv(w.Npad, 256);
+    for (int tn = tn0; tn <= tn0 + 8; ++tn) {
+      int bn = round_up(cdiv(w.Npad, tn), 16);
+      if (flex_env == 0) { int p2 = 32; while (p2 < bn) p2 *= 2; bn = p2; }
+      if (bn > 256) continue;
+      if (bn < 32) bn = 32;
+      const double cost = (double)cdiv(w.Npad, bn) * bn * (1.0 + 32.0 / bn);
+      if (cost < best - 1e-9) { best = cost; bn_eff = bn; }
+      if (bn == 32) break;
     }
   }
   a.tiles_m = a.tiles_x * a.tiles_y * tiles_f;
@@ -195,7 +203,9 @@ static int conv_tc_impl(const ConvW& w, const ConvIn& in, const ConvOut& out, co
   // weights, so narrower N tiles that put the layer on more SMs win over MMA efficiency -- halve the tile while the launch would leave
   // more than half of the machine idle and the main loop is long enough to matter.
   if (!out.res && !out.stats && !(out.second && out.second->stats))
-    while (BN > 32 && a.tiles_m <= 2 && (long long)a.tiles_m * cdiv(w.Npad, BN) * std::max(1, nsub) * nsplit * 2 <= sm_count_host() && max_taps * a.nkb >= 8) BN /= 2;
+    while (bn_eff > 32 && a.tiles_m <= 2 && (long long)a.tiles_m * cdiv(w.Npad, bn_eff) * std::max(1, nsub) * nsplit * 2 <= sm_count_host() && max_taps * a.nkb >= 8)
+      bn_eff = std::max(32, round_up(bn_eff / 2, 16));
+  BN = bn_eff <= 32 ? 32 : (bn_eff <= 64 ? 64 : (bn_eff <= 128 ? 128 : 256));
   // CTA pairs (cta_group::2): two consecutive M tiles share one N tile and each CTA stages half of its weights (IPK_TC_CTA2=0 disables,
   // =2 also pairs short main loops).
   static const int cta2_env = []() { const char* e = getenv("IPK_TC_CTA2"); return e ? atoi(e) : 1; }();
@@ -205,11 +215,13 @@ static int conv_tc_impl(const ConvW& w, const ConvIn& in, const ConvOut& out, co
   const int CG = (cta2_env > 0 && a.tiles_m >= 2 && BN == 256 && (cta2_env > 1 || max_taps * a.nkb >= 8)) ? 2 : 1;
   long long wd[2] = {w.Kpad, (long long)w.ntaps * w.Npad};
   long long wsb[1] = {(long long)w.Kpad * 2};
-  int wb[2] = {TC_BK, BN / CG};
+  int wb[2] = {TC_BK, bn_eff / CG};
   CUtensorMap mW_hi = make_map(w.w_hi, 2, wd, wsb, wb);
   CUtensorMap mW_lo = split ? make_map(w.w_lo, 2, wd, wsb, wb) : mW_hi;
 
-  a.tiles_n = cdiv(w.Npad, BN);
+  a.tiles_n = cdiv(w.Npad, bn_eff);
+  a.bn = bn_eff;
+  a.half_cols = BN >= 64 ? round_up(cdiv(bn_eff, 2), 32) : 16;
   a.nsplit = nsplit;
   a.fd_tiles_n.set(a.tiles_n);
   a.fd_per.set(std::max(1, a.nsub) * a.tiles_n);
@@ -230,7 +242,7 @@ static int conv_tc_impl(const ConvW& w, const ConvIn& in, const ConvOut& out, co
     const bool folded = out.ymul == 2 && out.xmul == 2 && out.Ho == 2 * in.H && out.Wo == 2 * in.W && in.W % a.bw == 0;
     for (int i = 0; i < 2; ++i) {
       const ConvOut* o = outs[i];
-      if (!o || tma_out_env == 0 || BN < 64 || !(plain || folded)) continue;
+      if (!o || tma_out_env == 0 || BN < 64 || bn_eff % 32 != 0 || !(plain || folded)) continue;
       if (o->mode != OUT_BF16_SPLIT && o->mode != OUT_BF16) continue;
       if (ncol[i] % 32 != 0 || (i == 0 && out.second && out.split_col % 32 != 0)) continue;
       const long long cs = o->cstride;

@@ -60,6 +60,10 @@ struct TcArgs {
   // bf16 operand planes leave through TMA stores (tma_out[i] != 0 for destination i): the warp's 32 rows x 32 columns are one box of the
   // output viewed as (columns, x', y, f); a transposed conv's parity class (a, b) is folded into the view: x' = a * W + x, column + b * cstride
   int tma_out[2], tma_xfold, tma_cfold[2];
+  // effective N tile: bn columns (a multiple of 16, <= the kernel's BN) are computed per tile -- UMMA N, the W box and the epilogue follow it,
+  // so a layer with 144 or 288 output columns is one or two tiles of 144 instead of padded 256-column tiles; half_cols = columns of the
+  // first epilogue column half (a multiple of 32)
+  int bn, half_cols;
   FastDiv fd_tiles_n, fd_per, fd_tiles_mn, fd_txy, fd_tiles_x, fd_nsub;     // divisors of the per-tile index arithmetic (per = nsub * tiles_n)
   long long* trace;               // optional per-CTA timeline (ipk_tc_trace_enable): 32 clock stamps per CTA, null = off
   int halo_variant;               // HALO kernels: 1 = row-shifted descriptors carry the swizzle base offset, 2 = they do not
@@ -147,7 +151,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   constexpr int W_BYTES = WROWS * TC_BK * 2;
   constexpr int NPLANES = NSPLIT == 3 ? 2 : 1;
   constexpr int STAGE_BYTES = HALO ? NPLANES * (TC_HALO_A_BYTES + 3 * W_BYTES) : NPLANES * (A_BYTES + W_BYTES);
-  constexpr uint32_t IDESC = umma_idesc_bf16(TC_BM * CG, BN);
+  const uint32_t IDESC = umma_idesc_bf16(TC_BM * CG, a.bn);
+  const uint32_t w_tx_bytes = (uint32_t)(a.bn / CG) * TC_BK * 2;       // bytes of one W plane actually loaded per stage
   constexpr int MAX_STAGES = 8;
   constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   constexpr int EPI_CHUNK = BN >= 64 ? 32 : 16;      // columns per TMEM load
@@ -216,9 +221,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
   if (tid_ == 0) tc_trace(a, 1);
-  pdl_wait();        // prologue above overlapped the previous kernel's tail; its outputs are visible from here on
+  // Programmatic dependent launch: the prologue above overlapped the previous kernel's tail.  Each role waits for the previous grid
+  // (griddepcontrol.wait) only where it first touches global memory -- the producer right before its first TMA load, after the first
+  // tile's index arithmetic, so that the cold instruction-cache misses of that code are taken while the previous kernel still runs
+  // (r02 timeline: 3 000 cycles between the wait and the first TMA load of every launch); the MMA warp touches no global memory.
   pdl_trigger();
-  if (tid_ == 0) tc_trace(a, 2);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -240,7 +247,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int mt = mg * CG + (int)crank;                            // beyond tiles_m: every box is out of bounds -> zero fill
         const int tf = a.fd_txy.div(mt), r2 = mt - tf * txy;
         const int ty = a.fd_tiles_x.div(r2), tx = r2 - ty * a.tiles_x;
-        const int f0 = tf * a.bf, y0 = ty * a.bh, x0 = tx * a.bw, n0 = nt * BN + (int)crank * WROWS;
+        const int f0 = tf * a.bf, y0 = ty * a.bh, x0 = tx * a.bw, n0 = nt * a.bn + (int)crank * (a.bn / CG);
         const TcSub& sb = a.sub[a.nsub > 1 ? z : 0];
         if constexpr (HALO) {
           // one stage per (input row dy, k-block): the 130-pixel row box of both planes + the weights of its three dx taps
@@ -248,7 +255,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             for (int kb = 0; kb < a.nkb; ++kb) {
               mbar_wait(&empty_bar[s], ph ^ 1);
               uint8_t* st = smem + (size_t)s * STAGE_BYTES;
-              if (crank == 0) mbar_expect_tx(&full_bar[s], CG * NPLANES * (130 * 128 + 3 * W_BYTES));
+              if (crank == 0) mbar_expect_tx(&full_bar[s], CG * NPLANES * (130 * 128 + 3 * w_tx_bytes));
+              if (tile == unit0 && dyi == 0 && kb == 0) pdl_wait();
               lda(st, &tmA_hi, s, kb * TC_BK, -1, y0 + dyi - 1, f0);
               if (NSPLIT == 3) lda(st + TC_HALO_A_BYTES, &tmA_lo, s, kb * TC_BK, -1, y0 + dyi - 1, f0);
               uint8_t* wst = st + NPLANES * TC_HALO_A_BYTES;
@@ -269,8 +277,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           {
             mbar_wait(&empty_bar[s], ph ^ 1);
             uint8_t* st = smem + (size_t)s * STAGE_BYTES;
-            if (crank == 0) mbar_expect_tx(&full_bar[s], CG * STAGE_BYTES);
+            if (crank == 0) mbar_expect_tx(&full_bar[s], CG * NPLANES * (A_BYTES + w_tx_bytes));
+            if (tile == unit0 && it == it_begin) { pdl_wait(); tc_trace(a, 2); }
             lda(st, &tmA_hi, s, kb * TC_BK, x0 + dx, y0 + dy, f0);
+            if (tile == unit0 && it == it_begin) tc_trace(a, 19);
             ldw(st + NPLANES * A_BYTES, &tmW_hi, s, kb * TC_BK, wrow);
             if (NSPLIT == 3) {
               lda(st + A_BYTES, &tmA_lo, s, kb * TC_BK, x0 + dx, y0 + dy, f0);
@@ -394,6 +404,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const int xl0 = r0w % a.bw, yl0 = (r0w / a.bw) % a.bh, fl0 = r0w / (a.bw * a.bh);
     int as = 0;
     uint32_t aph = 0;
+    pdl_wait();                                     // residual rows / statistics are read, and outputs written, after the previous grid
     int bias_nt = -1;                               // N tile whose bias this lane holds in b4 (one N tile: loaded once per kernel)
     float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
     // the accumulator stage goes back to the MMA issuer: the leader's barrier collects the epilogue warps of both CTAs of a pair
@@ -405,13 +416,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const int tf = a.fd_txy.div(mt), r2 = mt - tf * txy;
       const int ty = a.fd_tiles_x.div(r2), tx = r2 - ty * a.tiles_x;
       const int f = tf * a.bf + fl, y = ty * a.bh + yl, x = tx * a.bw + xl;
-      const int n0 = nt * BN;
+      const int n0 = nt * a.bn;
       const bool valid = (mt < a.tiles_m) && (f < a.F) && (y < a.H) && (x < a.W);
       const TcSub& sb = a.sub[a.nsub > 1 ? z : 0];
       const int oy = y * a.ymul + sb.yadd, ox = x * a.xmul + sb.xadd;
       const size_t opix = ((size_t)f * a.Ho + (size_t)oy) * a.Wo + (size_t)ox;
       const size_t zoff = a.nsub > 1 ? 0 : (size_t)z * a.split_stride;
-      const int c_begin = half * HALF_COLS, c_end = min((half + 1) * HALF_COLS, a.Npad - n0);     // this warp's columns of the tile
+      const int c_begin = half * a.half_cols, c_end = min(min(c_begin + a.half_cols, a.bn), a.Npad - n0);     // this warp's columns of the tile
 
       // rows this lane stores in the transposed (coalesced) write-out: row_i = lane/8 + 4*i; their output pixels come from
       // the lanes that own them (all-ones = row outside the image)
@@ -427,14 +438,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       if (nt != bias_nt) {
         bias_nt = nt;
         b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (a.bias != nullptr && lane * 4 < HALF_COLS && c_begin + lane * 4 < c_end) b4 = __ldg((const float4*)(a.bias + n0 + c_begin) + lane);
+        if (a.bias != nullptr && lane * 4 < a.half_cols && c_begin + lane * 4 < c_end) b4 = __ldg((const float4*)(a.bias + n0 + c_begin) + lane);
       }
       float4 resv[8], mr0 = make_float4(0.f, 1.f, 0.f, 1.f), mr1 = make_float4(0.f, 1.f, 0.f, 1.f);     // residual rows, their (mean, rstd) pairs
       auto load_res = [&](int c) __attribute__((always_inline)) {
 #pragma unroll
+        const bool cok = c + seg * 4 < c_end;        // a 16-column tail chunk: the upper segments lie outside the tile
         for (int i = 0; i < 8; ++i)
-          resv[i] = trow[i] != ~0u ? __ldg((const float4*)(a.res + (size_t)trow[i] * a.res_cstride + n0 + c) + seg) : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (a.res_mr != nullptr) {
+          resv[i] = (trow[i] != ~0u && cok) ? __ldg((const float4*)(a.res + (size_t)trow[i] * a.res_cstride + n0 + c) + seg) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.res_mr != nullptr && cok) {
           const float4* mp = (const float4*)(a.res_mr + ((size_t)min(fw, a.F - 1) * a.N + n0 + c + seg * 4) * 2);
           mr0 = __ldg(mp); mr1 = __ldg(mp + 1);
         }
@@ -449,7 +461,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       // the four warps of a column half write identical values; each one reads back what it wrote itself (no cross-warp ordering needed:
       // a warp reaches this point for the tile after next only once every warp has released the accumulator stage of this one)
       const uint32_t bias_u32 = smem_u32(bias_s + as * BN + c_begin);
-      if (lane * 4 < HALF_COLS) st_shared_v4(bias_u32 + lane * 16, b4);
+      if (lane * 4 < a.half_cols) st_shared_v4(bias_u32 + lane * 16, b4);
       __syncwarp();
 
       auto release_stage = [&]() __attribute__((always_inline)) {

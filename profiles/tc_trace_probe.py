@@ -15,11 +15,11 @@ import torch
 sys.path.insert(0, ".")
 import bench  # noqa: E402
 
-SLOTS = {0: "entry", 1: "prologue done", 2: "pdl_wait passed", 3: "producer: first stage issued", 4: "producer: tile 0 issued",
+SLOTS = {0: "entry", 1: "prologue done", 2: "producer: pdl_wait passed (before first TMA)", 3: "producer: first stage issued", 4: "producer: tile 0 issued",
          5: "producer: done", 6: "mma: tile 0 first operands", 7: "mma: tile 0 committed", 8: "mma: tile 1 first operands",
          9: "mma: tile 1 committed", 10: "epi w2: tile 0 accumulator ready", 11: "epi w2: tile 0 chunk 0 done (fp32 path)",
          12: "epi w2: tile 0 done", 13: "epi w2: tile 1 accumulator ready", 14: "epi w2: tile 1 done", 15: "epi w9: tile 0 done",
-         16: "epi w9: tile 1 done", 17: "all warps joined", 26: "epi w2: last tile>1 accumulator ready", 28: "mma: last tile>1 first operands",
+         16: "epi w9: tile 1 done", 17: "all warps joined", 19: "producer: after first TMA", 26: "epi w2: last tile>1 accumulator ready", 28: "mma: last tile>1 first operands",
          29: "mma: last tile>1 committed"}
 
 

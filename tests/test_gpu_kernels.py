@@ -15,7 +15,8 @@ def _lib():
     return _lib
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (256, 256, 128), (200, 48, 72), (1000, 144, 200), (4096, 2048, 2048)])
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (256, 256, 128), (200, 48, 72), (1000, 144, 200), (4096, 2048, 2048),
+                                   (512, 288, 2048), (300, 80, 128), (64, 2048, 2048), (640, 160, 64), (256, 272, 192)])
 @pytest.mark.parametrize("prec,name,tol", PRECS)
 def test_gemm(M, N, K, prec, name, tol):
     L = _lib()
