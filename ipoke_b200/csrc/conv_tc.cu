@@ -194,6 +194,8 @@ static int conv_tc_impl(const ConvW& w, const ConvIn& in, const ConvOut& out, co
       if (bn > 256) continue;
       if (bn < 32) bn = 32;
       const double cost = (double)cdiv(w.Npad, bn) * bn * (1.0 + 32.0 / bn);
+      // (Measured, r02: counting waves of the persistent grid instead -- 9 tiles of 240 columns for the 2 048-wide NICE convs, the same two
+      //  waves as 8 x 256 -- is SLOWER: conv2 17.3 -> 22.8 ms per step; UMMA N = 240 and 120-row W boxes lose more than the 6 % they save.)
       if (cost < best - 1e-9) { best = cost; bn_eff = bn; }
       if (bn == 32) break;
     }
@@ -242,7 +244,7 @@ static int conv_tc_impl(const ConvW& w, const ConvIn& in, const ConvOut& out, co
     const bool folded = out.ymul == 2 && out.xmul == 2 && out.Ho == 2 * in.H && out.Wo == 2 * in.W && in.W % a.bw == 0;
     for (int i = 0; i < 2; ++i) {
       const ConvOut* o = outs[i];
-      if (!o || tma_out_env == 0 || BN < 64 || bn_eff % 32 != 0 || !(plain || folded)) continue;
+      if (!o || tma_out_env == 0 || BN < 64 || !(plain || folded)) continue;
       if (o->mode != OUT_BF16_SPLIT && o->mode != OUT_BF16) continue;
       if (ncol[i] % 32 != 0 || (i == 0 && out.second && out.split_col % 32 != 0)) continue;
       const long long cs = o->cstride;

@@ -672,9 +672,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           if (od.act == ACT_NONE) run_range(IC{}, integral_constant<int, ACT_NONE>{}, integral_constant<int, -1>{}, oi, c_lo, c_hi, last_range);
           else run_range(IC{}, integral_constant<int, -1>{}, integral_constant<int, -1>{}, oi, c_lo, c_hi, last_range);
         } else if (EPI_CHUNK == 32 && a.tma_out[oi]) {
-          if (od.act == ACT_ELU) run_range(integral_constant<int, 1>{}, integral_constant<int, ACT_ELU>{}, integral_constant<int, -1>{}, oi, c_lo, c_hi, last_range);
-          else if (od.act == ACT_RELU) run_range(integral_constant<int, 1>{}, integral_constant<int, ACT_RELU>{}, integral_constant<int, -1>{}, oi, c_lo, c_hi, last_range);
-          else run_range(integral_constant<int, 1>{}, integral_constant<int, -1>{}, integral_constant<int, -1>{}, oi, c_lo, c_hi, last_range);
+          // whole 32-column chunks leave as TMA boxes; a 16-column tail (N tiles of 240 columns) takes the direct stores
+          const int c_full = c_lo + ((c_hi - c_lo) & ~31);
+          const bool tail = c_full < c_hi;
+          if (c_full > c_lo) {
+            if (od.act == ACT_ELU) run_range(integral_constant<int, 1>{}, integral_constant<int, ACT_ELU>{}, integral_constant<int, -1>{}, oi, c_lo, c_full, last_range && !tail);
+            else if (od.act == ACT_RELU) run_range(integral_constant<int, 1>{}, integral_constant<int, ACT_RELU>{}, integral_constant<int, -1>{}, oi, c_lo, c_full, last_range && !tail);
+            else run_range(integral_constant<int, 1>{}, integral_constant<int, -1>{}, integral_constant<int, -1>{}, oi, c_lo, c_full, last_range && !tail);
+          }
+          if (tail) run_range(integral_constant<int, 2>{}, integral_constant<int, -1>{}, integral_constant<int, -1>{}, oi, c_full, c_hi, last_range);
         } else {
           run_range(integral_constant<int, 2>{}, integral_constant<int, -1>{}, integral_constant<int, -1>{}, oi, c_lo, c_hi, last_range);
         }
