@@ -171,9 +171,21 @@ static int build_nice(ipk_flow* f, const std::string& p, int C, int factor, bool
     conv_pack_into(n.c3, t * n.N3p, s, {t}, st);
   }
   {
-    // split-K so that one launch fills the machine about twice over (tensor-core engine only)
+    // split-K (tensor-core engine only): the slice count that minimises (waves of the persistent grid) x (k-blocks per slice), with a
+    // small charge per slice for the partial sums the next segment gathers.  The engine runs layers wider than 128 columns as
+    // cdiv(Npad, 256) N tiles on CTA pairs (74 slots), narrower ones on single CTAs (148 slots).  (The previous rule assumed 128-column
+    // tiles: the 288-column conv3 of the two widest levels got 3 slices = 96 pair-units = two waves, the second 30 % full.)
     const int mt = cdiv(f->cfg.max_batch * 64, 128);
-    const int want = std::max(1, std::min(MAX_NSPLIT - 1, (2 * 148) / std::max(1, mt * cdiv(n.c3.Npad, 128))));
+    const int nkb = n.c3.Kpad / 64;
+    const bool pairs = n.c3.Npad > 128 && mt >= 2;
+    const long long per_slice = (long long)(pairs ? cdiv(mt, 2) : mt) * cdiv(n.c3.Npad, 256);
+    const int slots = pairs ? 74 : 148;
+    int want = 1;
+    double best = 1e30;
+    for (int ns = 1; ns < MAX_NSPLIT; ++ns) {
+      const double cost = (double)cdiv((int)(per_slice * ns), slots) * cdiv(nkb, ns) + 0.25 * ns;
+      if (cost < best - 1e-9) { best = cost; want = ns; }
+    }
     n.nsplit3 = conv_split_count(n.c3, taps_1x1(), want);
   }
   n.bias3 = f->pool.alloc<float>(N3);
