@@ -159,13 +159,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   constexpr int HALF_COLS = BN / 2;                  // columns owned by one of the two epilogue warps of a lane quarter
 
   // Shared memory (all dynamic, so that its base is the CTA's 1024-byte aligned window and no alignment slack is needed):
-  //   [stages x STAGE_BYTES] operand ring | [8 x 4 KB] epilogue transpose buffers | [2 x BN] fp32 bias of the tile in each accumulator
-  //   stage | mbarriers + the TMEM base address
+  //   [stages x STAGE_BYTES] operand ring | [8 x 4 KB] epilogue transpose buffers | mbarriers + the TMEM base address
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;                                                        // SWIZZLE_128B needs 1024-byte alignment
   uint8_t* epi_stage = smem + (size_t)a.stages * STAGE_BYTES;                      // 8 x 4 KB epilogue transpose buffers
-  float* bias_s = (float*)(epi_stage + TC_EPI_WARPS * TC_EPI_STAGE_BYTES);
-  uint64_t* full_bar = (uint64_t*)(bias_s + 2 * BN);
+  uint64_t* full_bar = (uint64_t*)(epi_stage + TC_EPI_WARPS * TC_EPI_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
@@ -458,11 +456,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const int esl = tile == unit0 ? 10 : (tile == unit0 + unit_step ? 13 : 26);
       if (warp == 2 && lane == 0) tc_trace(a, esl);
       const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
-      // the four warps of a column half write identical values; each one reads back what it wrote itself (no cross-warp ordering needed:
-      // a warp reaches this point for the tile after next only once every warp has released the accumulator stage of this one)
-      const uint32_t bias_u32 = smem_u32(bias_s + as * BN + c_begin);
-      if (lane * 4 < a.half_cols) st_shared_v4(bias_u32 + lane * 16, b4);
-      __syncwarp();
 
       auto release_stage = [&]() __attribute__((always_inline)) {
         // all TMEM reads of this warp have landed: hand the accumulator stage back to the MMA warp before the stores
@@ -504,17 +497,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
           for (int j = 0; j < EPI_CHUNK; ++j) v[j] = __uint_as_float(rr[j]);
           const size_t colbase = (size_t)od.coff + (size_t)(n0 + c - (oi ? a.split_col : 0));
-          const uint32_t bias_c = bias_u32 + (uint32_t)(c - c_begin) * 4;
-          // the tile's bias is read from shared memory BEFORE the accumulator stage is released (its buffer belongs to the stage)
+          // the tile's bias lives in registers, 4 columns per lane (b4 = columns c_begin + 4 lane ..): a lane fetches what it needs by
+          // shuffles (no shared copy: the four warps of a column half would otherwise race on it, compute-sanitizer racecheck r02)
+          const int bl = (c - c_begin) >> 2;             // lane holding the chunk's first 4 columns
           float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
           if constexpr (MODE == 0) {
-            bb = ld_shared_v4(bias_c + seg * 16);        // the 4 columns this lane owns on the way out
+            // the 4 columns this lane owns on the way out
+            bb.x = __shfl_sync(0xffffffffu, b4.x, bl + seg); bb.y = __shfl_sync(0xffffffffu, b4.y, bl + seg);
+            bb.z = __shfl_sync(0xffffffffu, b4.z, bl + seg); bb.w = __shfl_sync(0xffffffffu, b4.w, bl + seg);
           } else {
-            if (a.bias != nullptr) {
+            if (a.bias != nullptr) {                     // lane = row: all columns of the chunk
 #pragma unroll
-              for (int j = 0; j < EPI_CHUNK / 4; ++j) {    // lane = row: all columns of the chunk (broadcast reads)
-                const float4 b = ld_shared_v4(bias_c + j * 16);
-                v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+              for (int j = 0; j < EPI_CHUNK / 4; ++j) {
+                v[4 * j] += __shfl_sync(0xffffffffu, b4.x, bl + j); v[4 * j + 1] += __shfl_sync(0xffffffffu, b4.y, bl + j);
+                v[4 * j + 2] += __shfl_sync(0xffffffffu, b4.z, bl + j); v[4 * j + 3] += __shfl_sync(0xffffffffu, b4.w, bl + j);
               }
             }
           }
@@ -730,9 +726,9 @@ inline void launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CU
   int stages = (int)std::min<size_t>(8, TC_SMEM_BUDGET / STAGE_BYTES);
   IPK_CHECK(stages >= 2, IPK_ERR_UNSUPPORTED, "conv_tc: pipeline needs at least two stages (stage %d bytes)", STAGE_BYTES);
   a.stages = stages;
-  // ring + epilogue transpose buffers + 2 x BN bias floats + barriers (see the kernel's layout comment); no alignment slack: the dynamic
+  // ring + epilogue transpose buffers + barriers (see the kernel's layout comment); no alignment slack: the dynamic
   // array is declared __align__(1024) and the kernel traps if its base is not
-  constexpr size_t TAIL_BYTES = TC_EPI_WARPS * TC_EPI_STAGE_BYTES + 2 * BN * sizeof(float) + 256;
+  constexpr size_t TAIL_BYTES = TC_EPI_WARPS * TC_EPI_STAGE_BYTES + 256;
   size_t smem = (size_t)stages * STAGE_BYTES + TAIL_BYTES;
   static bool attr_set[IPK_MAX_DEVICES] = {false};      // function attributes are per device
   const int slot = current_device_slot();

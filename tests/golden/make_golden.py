@@ -148,6 +148,9 @@ GRAD_CASES = {
     "flowgrad_tiny": (dict(flow_in_channels=16, flow_mid_channels=64, h_channels=16, num_steps=[2, 1, 1], factor=4), 3, 1, 11),
     "flowgrad_c32_hd128": (dict(flow_in_channels=32, flow_mid_channels=128, h_channels=128, num_steps=[2, 1, 1] + [1] * 12), 4, 3, 13),
     "flowgrad_c64_hd128": (dict(flow_in_channels=64, flow_mid_channels=128, h_channels=128, num_steps=[1] * 15), 2, 4, 14),
+    # the actual h36m_128 shape of BASELINE configs[3] (C0 = 64, Hd = 2048, shipped num_steps: 1.24 B parameters); reference only
+    # (`skip_oracle`: the oracle's second autograd graph would double the ~25 GB this case needs)
+    "flowgrad_full_c64": (dict(flow_in_channels=64, flow_mid_channels=2048, h_channels=128), 2, 5, 15, "skip_oracle"),
 }
 
 
@@ -155,7 +158,8 @@ def run_grad_case(name, spec, out_dir):
     """loss.backward() of the reference flow + FlowLoss on a seeded latent; all gradients are kept as (norm, 64 sampled entries)
     per tensor plus a handful in full, and compared with the oracle's autograd in the same run."""
     import importlib
-    kw, B, wseed, iseed = spec
+    kw, B, wseed, iseed = spec[:4]
+    skip_oracle = len(spec) > 4 and spec[4] == "skip_oracle"
     cfg = O.flow_config(**kw)
     sd = O.synth_flow_state_dict(cfg, seed=wseed)
     x, cond, _ = O.synth_inputs(B, cfg["flow_in_channels"], cfg["h_channels"], 8, seed=iseed)
@@ -167,11 +171,14 @@ def run_grad_case(name, spec, out_dir):
     out, logdet = m(x, cond, reverse=False)
     loss, _ = crit(out, logdet)
     loss.backward()
-    ref_grads = {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
-    loss_or, grads_or = O.flow_loss_and_grads(sd, cfg, x, cond)
+    ref_grads = {k: p.grad.detach() for k, p in m.named_parameters() if p.grad is not None}
     keys = O.flow_trainable_keys(sd)
     assert set(ref_grads) == set(keys), (set(keys) ^ set(ref_grads))
-    worst = max(((grads_or[k] - ref_grads[k]).abs().max().item() / (ref_grads[k].abs().max().item() + 1e-12)) for k in keys)
+    if skip_oracle:
+        loss_or, worst = loss.detach(), float("nan")
+    else:
+        loss_or, grads_or = O.flow_loss_and_grads(sd, cfg, x, cond)
+        worst = max(((grads_or[k] - ref_grads[k]).abs().max().item() / (ref_grads[k].abs().max().item() + 1e-12)) for k in keys)
     # compact summary: per tensor the L2 norm, the max-abs and NS sampled entries (flat index, value), stored as three arrays
     NS = 16
     gsel = torch.Generator().manual_seed(5)

@@ -20,8 +20,9 @@ def _trainer(cfg, sd, precision, max_batch):
 
 # stated tolerances: loss relative 1e-5; gradients relative to each tensor's own max-abs:
 # fp32_simt 2e-4, fp32 (bf16x3 tensor cores) 1e-3
-@pytest.mark.parametrize("precision,gtol", [("fp32_simt", 2e-4), ("fp32", 1e-3)])
-@pytest.mark.parametrize("name", ["flowgrad_tiny", "flowgrad_c32_hd128", "flowgrad_c64_hd128"])
+# flowgrad_full_c64 is the actual h36m_128 shape of BASELINE configs[3] (C0 = 64, Hd = 2048, 1.24 B parameters, 5 305 gradient tensors), B = 2
+@pytest.mark.parametrize("name,precision,gtol", [(n, p, t) for n in ("flowgrad_tiny", "flowgrad_c32_hd128", "flowgrad_c64_hd128")
+                                                 for p, t in (("fp32_simt", 2e-4), ("fp32", 1e-3))] + [("flowgrad_full_c64", "fp32", 1e-3)])
 def test_training_step_matches_reference_autograd(name, precision, gtol):
     fx = golden(name)
     cfg = O.flow_config(**fx["cfg_kwargs"])
