@@ -207,6 +207,10 @@ static int conv_tc_impl(const ConvW& w, const ConvIn& in, const ConvOut& out, co
   if (!out.res && !out.stats && !(out.second && out.second->stats))
     while (bn_eff > 32 && a.tiles_m <= 2 && (long long)a.tiles_m * cdiv(w.Npad, bn_eff) * std::max(1, nsub) * nsplit * 2 <= sm_count_host() && max_taps * a.nkb >= 8)
       bn_eff = std::max(32, round_up(bn_eff / 2, 16));
+  // short main loops on wide layers (NICE conv1: K <= 192, N = 2 048) are epilogue-bound: narrower tiles give the persistent grid a finer
+  // granularity (IPK_TC_SHORTK_BN, 0 = keep the cost model's tile)
+  static const int shortk_bn = []() { const char* e = getenv("IPK_TC_SHORTK_BN"); return e ? atoi(e) : 0; }();
+  if (shortk_bn >= 32 && shortk_bn <= 256 && shortk_bn % 32 == 0 && w.Npad >= 1024 && max_taps * a.nkb < 8 && nsub == 1) bn_eff = shortk_bn;
   BN = bn_eff <= 32 ? 32 : (bn_eff <= 64 ? 64 : (bn_eff <= 128 ? 128 : 256));
   // CTA pairs (cta_group::2): two consecutive M tiles share one N tile and each CTA stages half of its weights (IPK_TC_CTA2=0 disables,
   // =2 also pairs short main loops).
