@@ -383,8 +383,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     __syncwarp();
   } else {
     // ===================== epilogue: warps 2..9; TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 ============
-    // * Everything an epilogue warp needs from global memory is requested BEFORE it waits for the accumulator (the tile's bias -> shared
-    //   memory, the first chunk's residual rows -> registers), the TMEM load of chunk c+1 is in flight while chunk c is processed, and
+    // * Everything an epilogue warp needs from global memory is requested BEFORE it waits for the accumulator (the tile's bias, 4 columns
+    //   per lane, and the first chunk's residual rows -> registers), the TMEM load of chunk c+1 is in flight while chunk c is processed, and
     //   the accumulator stage goes back to the MMA warp as soon as the last TMEM load has landed (ncu, r02: the first version spent
     //   > 60 % of its time on the L2 latency of per-chunk bias / residual loads).
     // * The write-out mode and the activation are dispatched ONCE per column range of a destination, outside the chunk loop, into bodies
