@@ -605,7 +605,7 @@ def run_ours(a):
             roofline = {"kernel": "conv_tc_kernel (NICE coupling conv2: 1x1 2048->2048 implicit GEMM, M=B*64)", "bound": "tensor",
                         "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": ncu_traffic("nice_conv2", a.precision, B),
                         "launches_per_step": c // nprof, "avg_launch_ms": t / c, "peak_source": peak_src,
-                        "note": "algorithmic FLOPs (1x); fp32 mode issues 3 bf16 MMAs per product (bf16x3), so its ceiling is 1/3 of the bf16 peak; the binding resource is the L2->SM operand stream (hi + lo planes of both operands: 537 MB per launch), see DESIGN.md 7b"
+                        "note": "algorithmic FLOPs (1x); fp32 mode issues 3 bf16 MMAs per product (bf16x3), so its ceiling is 1/3 of the bf16 peak; 1.73 waves of the persistent grid (tensor pipe 76 % busy on the two-unit SMs), see DESIGN.md 7b"
                                 if a.precision == "fp32" else "algorithmic FLOPs"}
         latency = {"ms_per_sample_b1": round(run.latency_b1(), 3), "note": "B=1, T=%d, device-resident (GUI call shape, testing/gui.py:139-148)" % T}
 
