@@ -211,6 +211,8 @@ static int conv_tc_impl(const ConvW& w, const ConvIn& in, const ConvOut& out, co
   // granularity (IPK_TC_SHORTK_BN, 0 = keep the cost model's tile)
   static const int shortk_bn = []() { const char* e = getenv("IPK_TC_SHORTK_BN"); return e ? atoi(e) : 0; }();
   if (shortk_bn >= 32 && shortk_bn <= 256 && shortk_bn % 32 == 0 && w.Npad >= 1024 && max_taps * a.nkb < 8 && nsub == 1) bn_eff = shortk_bn;
+  static const int longk_bn = []() { const char* e = getenv("IPK_TC_LONGK_BN"); return e ? atoi(e) : 0; }();     // experiment: N tile of the long-K 2 048-wide layers
+  if (longk_bn >= 32 && longk_bn <= 256 && longk_bn % 16 == 0 && w.Npad >= 1024 && max_taps * a.nkb >= 8 && nsub == 1) bn_eff = longk_bn;
   BN = bn_eff <= 32 ? 32 : (bn_eff <= 64 ? 64 : (bn_eff <= 128 ? 128 : 256));
   // CTA pairs (cta_group::2): two consecutive M tiles share one N tile and each CTA stages half of its weights (IPK_TC_CTA2=0 disables,
   // =2 also pairs short main loops).
@@ -219,13 +221,44 @@ static int conv_tc_impl(const ConvW& w, const ConvIn& in, const ConvOut& out, co
   // 19.2 -> 16.9 ms per step, N = K = 2048); a loss for narrow N tiles (A traffic dominates, and the pair's lock-step epilogue hand-off
   // costs more than the halved W fetch saves) and for short main loops (NICE conv1, K <= 192: epilogue-bound).
   const int CG = (cta2_env > 0 && a.tiles_m >= 2 && BN == 256 && (cta2_env > 1 || max_taps * a.nkb >= 8)) ? 2 : 1;
+  // ---- uneven N tiles for wide layers on CTA pairs (NICE conv2 at B = 64: 16 M-tile groups x 8 tiles of 256 columns = 128 pair-units on
+  //      74 pairs, i.e. 54 pairs run two units and 20 run one).  Nine tiles per group (eight of 224 columns, one of 256) are 144 units: every
+  //      pair runs at most two, and with the wide tiles dealt out first no pair gets two of them -- the longest pair does 224 + 256 columns
+  //      instead of 512, in lock-step like the uniform schedule (a stream-K split loses the lock-step and measured slower).
+  //      The UMMA main loop was measured proportional to N (47.3 / 41.5 / 36.7 kcycles per unit at N = 256 / 224 / 192).
+  static const int nv_env = []() { const char* e = getenv("IPK_TC_NV"); return e ? atoi(e) : 1; }();
+  int nv_tiles = 0;
+  short nv_n0[TC_MAX_NV], nv_w[TC_MAX_NV];
+  if (nv_env > 0 && CG == 2 && nsub == 1 && nsplit == 1 && w.Npad % 32 == 0 && w.Npad >= 1024) {
+    const int mgs = cdiv(a.tiles_m, 2), slots = std::max(1, sm_count_host() / 2), chunks = w.Npad / 32;
+    const int tn_u = cdiv(w.Npad, bn_eff);
+    const double cost_u = (double)cdiv(mgs * tn_u, slots) * (bn_eff + 32);
+    double best = cost_u * 0.97;       // must win by 3 %
+    for (int tn = tn_u; tn <= std::min(TC_MAX_NV, tn_u + 3); ++tn) {
+      const int base = chunks / tn, rem = chunks % tn;
+      if ((base + (rem ? 1 : 0)) * 32 > 256 || base == 0) continue;
+      std::vector<double> load(slots, 0.0);
+      for (int u = 0; u < mgs * tn; ++u) load[u % slots] += ((u / mgs) < rem ? base + 1 : base) * 32 + 32;     // wide slots first, group fastest
+      const double cost = *std::max_element(load.begin(), load.end());
+      if (cost < best - 1e-9) {
+        best = cost;
+        nv_tiles = tn;
+        int off = 0;        // wide tiles take the first columns; their slots come first in the unit order too
+        for (int i = 0; i < tn; ++i) { nv_n0[i] = (short)off; nv_w[i] = (short)((i < rem ? base + 1 : base) * 32); off += nv_w[i]; }
+      }
+    }
+    if (nv_tiles > 0) bn_eff = nv_w[0];      // the widest tile: W box rows, shared-memory stage and TMEM columns follow it
+  }
   long long wd[2] = {w.Kpad, (long long)w.ntaps * w.Npad};
   long long wsb[1] = {(long long)w.Kpad * 2};
   int wb[2] = {TC_BK, bn_eff / CG};
   CUtensorMap mW_hi = make_map(w.w_hi, 2, wd, wsb, wb);
   CUtensorMap mW_lo = split ? make_map(w.w_lo, 2, wd, wsb, wb) : mW_hi;
 
-  a.tiles_n = cdiv(w.Npad, bn_eff);
+  a.tiles_n = nv_tiles > 0 ? nv_tiles : cdiv(w.Npad, bn_eff);
+  a.nv_tiles = nv_tiles;
+  for (int i = 0; i < nv_tiles; ++i) { a.nv_n0[i] = nv_n0[i]; a.nv_w[i] = nv_w[i]; }
+  a.fd_tiles_mg.set(cdiv(a.tiles_m, CG));
   a.bn = bn_eff;
   a.half_cols = BN >= 64 ? round_up(cdiv(bn_eff, 2), 32) : 16;
   a.nsplit = nsplit;

@@ -30,6 +30,7 @@ struct FastDiv {
 };
 
 constexpr int TC_MAX_SUB = 4;
+constexpr int TC_MAX_NV = 16;
 struct TcSub {                    // one tap list + output phase (a parity class of a transposed conv; plain convs have one)
   int ntaps, yadd, xadd;
   int dy[MAX_TAPS], dx[MAX_TAPS], widx[MAX_TAPS];
@@ -64,6 +65,12 @@ struct TcArgs {
   // so a layer with 144 or 288 output columns is one or two tiles of 144 instead of padded 256-column tiles; half_cols = columns of the
   // first epilogue column half (a multiple of 32)
   int bn, half_cols;
+  // uneven N tiles (nv_tiles > 0; wide layers on CTA pairs whose uniform tiling ends in a partly filled wave): tile slot i covers columns
+  // [nv_n0[i], nv_n0[i] + nv_w[i]), widths are multiples of 32 <= bn (the W box is always bn / CG rows), slots are sorted wide-first and a
+  // unit index is slot * (M-tile groups) + group, so that the round-robin persistent schedule gives no pair two wide tiles
+  int nv_tiles;
+  short nv_n0[TC_MAX_NV], nv_w[TC_MAX_NV];
+  FastDiv fd_tiles_mg;
   FastDiv fd_tiles_n, fd_per, fd_tiles_mn, fd_txy, fd_tiles_x, fd_nsub;     // divisors of the per-tile index arithmetic (per = nsub * tiles_n)
   long long* trace;               // optional per-CTA timeline (ipk_tc_trace_enable): 32 clock stamps per CTA, null = off
   int halo_variant;               // HALO kernels: 1 = row-shifted descriptors carry the swizzle base offset, 2 = they do not
@@ -117,12 +124,21 @@ __device__ __forceinline__ void tc_decode_tile(const TcArgs& a, int tiles_mn, in
     // would draw the same class every time (r02 timeline: 2x spread of the CTAs' finishing times)
     const int zs = zi + mg;
     z = zs - a.fd_nsub.div(zs) * a.nsub;
+  } else if (a.nv_tiles > 0) {
+    z = 0;
+    nt = a.fd_tiles_mg.div(tile);                 // tile slot (wide-first), M-tile group fastest
+    mg = tile - nt * a.fd_tiles_mg.d;
   } else {
     z = a.fd_tiles_mn.div(tile);
     const int rem = tile - z * tiles_mn;
     mg = a.fd_tiles_n.div(rem);
     nt = rem - mg * a.tiles_n;
   }
+}
+// first column and width of N tile `nt`
+__device__ __forceinline__ void tc_tile_cols(const TcArgs& a, int nt, int& n0, int& w) {
+  if (a.nv_tiles > 0) { n0 = a.nv_n0[nt]; w = a.nv_w[nt]; }
+  else { n0 = nt * a.bn; w = a.bn; }
 }
 
 // Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue.
@@ -151,7 +167,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   constexpr int W_BYTES = WROWS * TC_BK * 2;
   constexpr int NPLANES = NSPLIT == 3 ? 2 : 1;
   constexpr int STAGE_BYTES = HALO ? NPLANES * (TC_HALO_A_BYTES + 3 * W_BYTES) : NPLANES * (A_BYTES + W_BYTES);
-  const uint32_t IDESC = umma_idesc_bf16(TC_BM * CG, a.bn);
   const uint32_t w_tx_bytes = (uint32_t)(a.bn / CG) * TC_BK * 2;       // bytes of one W plane actually loaded per stage
   constexpr int MAX_STAGES = 8;
   constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
@@ -245,7 +260,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int mt = mg * CG + (int)crank;                            // beyond tiles_m: every box is out of bounds -> zero fill
         const int tf = a.fd_txy.div(mt), r2 = mt - tf * txy;
         const int ty = a.fd_tiles_x.div(r2), tx = r2 - ty * a.tiles_x;
-        const int f0 = tf * a.bf, y0 = ty * a.bh, x0 = tx * a.bw, n0 = nt * a.bn + (int)crank * (a.bn / CG);
+        int n0, bnw;
+        tc_tile_cols(a, nt, n0, bnw);
+        n0 += (int)crank * (bnw / CG);
+        const int f0 = tf * a.bf, y0 = ty * a.bh, x0 = tx * a.bw;
         const TcSub& sb = a.sub[a.nsub > 1 ? z : 0];
         if constexpr (HALO) {
           // one stage per (input row dy, k-block): the 130-pixel row box of both planes + the weights of its three dx taps
@@ -301,6 +319,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       uint32_t ph = 0;
       int as = 0;
       uint32_t aph = 0;
+      uint32_t IDESC = umma_idesc_bf16(TC_BM * CG, a.bn);
       auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t acc) {
         if constexpr (CG == 2) umma_bf16_2cta(d, da, db, IDESC, acc);
         else umma_bf16(d, da, db, IDESC, acc);
@@ -312,6 +331,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       for (int tile = unit0; tile < total_tiles; tile += unit_step) {
         int z, mg_, nt_;
         tc_decode_tile(a, tiles_mn, tile, z, mg_, nt_);
+        if (a.nv_tiles > 0) IDESC = umma_idesc_bf16(TC_BM * CG, a.nv_w[nt_]);
         const int it_begin = a.nsub > 1 ? 0 : z * a.iters_per_split;
         const int iters = HALO ? 3 * a.nkb : min(a.sub[a.nsub > 1 ? z : 0].ntaps * a.nkb, it_begin + a.iters_per_split) - it_begin;
         mbar_wait(&tmem_empty_bar[as], aph ^ 1);      // epilogue has drained this accumulator stage
@@ -414,13 +434,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const int tf = a.fd_txy.div(mt), r2 = mt - tf * txy;
       const int ty = a.fd_tiles_x.div(r2), tx = r2 - ty * a.tiles_x;
       const int f = tf * a.bf + fl, y = ty * a.bh + yl, x = tx * a.bw + xl;
-      const int n0 = nt * a.bn;
+      int n0, bnw;
+      tc_tile_cols(a, nt, n0, bnw);
+      const int hcols = a.nv_tiles > 0 ? (((bnw >> 1) + 31) & ~31) : a.half_cols;
       const bool valid = (mt < a.tiles_m) && (f < a.F) && (y < a.H) && (x < a.W);
       const TcSub& sb = a.sub[a.nsub > 1 ? z : 0];
       const int oy = y * a.ymul + sb.yadd, ox = x * a.xmul + sb.xadd;
       const size_t opix = ((size_t)f * a.Ho + (size_t)oy) * a.Wo + (size_t)ox;
       const size_t zoff = a.nsub > 1 ? 0 : (size_t)z * a.split_stride;
-      const int c_begin = half * a.half_cols, c_end = min(min(c_begin + a.half_cols, a.bn), a.Npad - n0);     // this warp's columns of the tile
+      const int c_begin = half * hcols, c_end = min(min(c_begin + hcols, bnw), a.Npad - n0);     // this warp's columns of the tile
 
       // rows this lane stores in the transposed (coalesced) write-out: row_i = lane/8 + 4*i; their output pixels come from
       // the lanes that own them (all-ones = row outside the image)
@@ -436,7 +458,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       if (nt != bias_nt) {
         bias_nt = nt;
         b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (a.bias != nullptr && lane * 4 < a.half_cols && c_begin + lane * 4 < c_end) b4 = __ldg((const float4*)(a.bias + n0 + c_begin) + lane);
+        if (a.bias != nullptr && lane * 4 < hcols && c_begin + lane * 4 < c_end) b4 = __ldg((const float4*)(a.bias + n0 + c_begin) + lane);
       }
       float4 resv[8], mr0 = make_float4(0.f, 1.f, 0.f, 1.f), mr1 = make_float4(0.f, 1.f, 0.f, 1.f);     // residual rows, their (mean, rstd) pairs
       auto load_res = [&](int c) __attribute__((always_inline)) {
