@@ -226,25 +226,28 @@ static int conv_tc_impl(const ConvW& w, const ConvIn& in, const ConvOut& out, co
   //      pair runs at most two, and with the wide tiles dealt out first no pair gets two of them -- the longest pair does 224 + 256 columns
   //      instead of 512, in lock-step like the uniform schedule (a stream-K split loses the lock-step and measured slower).
   //      The UMMA main loop was measured proportional to N (47.3 / 41.5 / 36.7 kcycles per unit at N = 256 / 224 / 192).
-  static const int nv_env = []() { const char* e = getenv("IPK_TC_NV"); return e ? atoi(e) : 1; }();
+  static const int nv_env = []() { const char* e = getenv("IPK_TC_NV"); return e ? atoi(e) : 2; }();     // 0 = off, 1 = widths in multiples of 32, 2 = of 16
   int nv_tiles = 0;
   short nv_n0[TC_MAX_NV], nv_w[TC_MAX_NV];
   if (nv_env > 0 && CG == 2 && nsub == 1 && nsplit == 1 && w.Npad % 32 == 0 && w.Npad >= 1024) {
-    const int mgs = cdiv(a.tiles_m, 2), slots = std::max(1, sm_count_host() / 2), chunks = w.Npad / 32;
+    // widths in multiples of 16 (default; a 16-column tail chunk takes the direct stores): 7 x 224 + 2 x 240 columns, the longest pair runs
+    // 240 + 224; measured 16.8 -> 16.5 ms per step against the multiples-of-32 plan (8 x 224 + 256)
+    const int gran = nv_env > 1 ? 16 : 32;
+    const int mgs = cdiv(a.tiles_m, 2), slots = std::max(1, sm_count_host() / 2), chunks = w.Npad / gran;
     const int tn_u = cdiv(w.Npad, bn_eff);
     const double cost_u = (double)cdiv(mgs * tn_u, slots) * (bn_eff + 32);
     double best = cost_u * 0.97;       // must win by 3 %
     for (int tn = tn_u; tn <= std::min(TC_MAX_NV, tn_u + 3); ++tn) {
       const int base = chunks / tn, rem = chunks % tn;
-      if ((base + (rem ? 1 : 0)) * 32 > 256 || base == 0) continue;
+      if ((base + (rem ? 1 : 0)) * gran > 256 || base == 0) continue;
       std::vector<double> load(slots, 0.0);
-      for (int u = 0; u < mgs * tn; ++u) load[u % slots] += ((u / mgs) < rem ? base + 1 : base) * 32 + 32;     // wide slots first, group fastest
+      for (int u = 0; u < mgs * tn; ++u) load[u % slots] += ((u / mgs) < rem ? base + 1 : base) * gran + 32;     // wide slots first, group fastest
       const double cost = *std::max_element(load.begin(), load.end());
       if (cost < best - 1e-9) {
         best = cost;
         nv_tiles = tn;
         int off = 0;        // wide tiles take the first columns; their slots come first in the unit order too
-        for (int i = 0; i < tn; ++i) { nv_n0[i] = (short)off; nv_w[i] = (short)((i < rem ? base + 1 : base) * 32); off += nv_w[i]; }
+        for (int i = 0; i < tn; ++i) { nv_n0[i] = (short)off; nv_w[i] = (short)((i < rem ? base + 1 : base) * gran); off += nv_w[i]; }
       }
     }
     if (nv_tiles > 0) bn_eff = nv_w[0];      // the widest tile: W box rows, shared-memory stage and TMEM columns follow it
