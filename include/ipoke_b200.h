@@ -249,6 +249,12 @@ int ipk_test_convT3x3(const float* in, const float* w, const float* bias, float*
  * dims = {B,T,H,W,Cin,Cout, kt,ky,kx, st,sy,sx, pt,py,px}; precision IPK_PREC_FP32_SPLIT or IPK_PREC_BF16 */
 int ipk_test_conv3d(const float* in, const float* w, float* out, double* stats, const int32_t* dims, int32_t precision, void* stream);
 
+/* Host-side tile planning of the tcgen05 conv engine (no device work: callable without a GPU): for a layer with Npad output columns,
+ * tiles_m 128-row M tiles, total_iters (tap, 64-wide k-block) iterations, nsub sub-convolutions, nsplit split-K slices, a fused
+ * (residual / statistics) epilogue or not, on a device with `sms` SMs.  out[0..4] = kernel N capacity BN, columns per tile bn, CTA-pair
+ * factor CG (1 | 2), N tiles, number of uneven tiles; out[5 + 2 i], out[6 + 2 i] = first column and width of uneven tile i. */
+int ipk_test_tc_plan(int32_t Npad, int32_t tiles_m, int32_t total_iters, int32_t nsub, int32_t nsplit, int32_t fused, int32_t sms, int32_t* out);
+
 /* Timeline probe of the tcgen05 conv engine (profiles/tc_trace_probe.py): after ipk_tc_trace_enable(N, Kpad) every conv_tc launch whose
  * packed weights have that N and padded K records 32 SM-clock stamps per CTA (entry, prologue, first TMA, per-tile MMA / epilogue
  * milestones; slot 30 = global timer at entry); ipk_tc_trace_read copies [n_ctas][32] int64 of the LAST such launch to the host. */

@@ -50,7 +50,7 @@ EXPORTS = [
     "ipk_cenc_create", "ipk_cenc_set_tensor", "ipk_cenc_finalize", "ipk_cenc_forward", "ipk_cenc_destroy",
     "ipk_i3d_create", "ipk_i3d_set_tensor", "ipk_i3d_finalize", "ipk_i3d_forward", "ipk_i3d_destroy", "ipk_i3d_preprocess",
     "ipk_enc_create", "ipk_enc_set_tensor", "ipk_enc_finalize", "ipk_enc_forward", "ipk_enc_destroy",
-    "ipk_sample", "ipk_sample_host", "ipk_sample_host_u8", "ipk_frames_to_u8", "ipk_test_gemm", "ipk_test_conv3x3", "ipk_test_convT3x3", "ipk_test_conv3d", "ipk_tc_trace_enable", "ipk_tc_trace_read",
+    "ipk_sample", "ipk_sample_host", "ipk_sample_host_u8", "ipk_frames_to_u8", "ipk_test_gemm", "ipk_test_conv3x3", "ipk_test_convT3x3", "ipk_test_conv3d", "ipk_tc_trace_enable", "ipk_tc_trace_read", "ipk_test_tc_plan",
     "ipk_flowtrain_create", "ipk_flowtrain_set_tensor", "ipk_flowtrain_finalize", "ipk_flowtrain_step", "ipk_flowtrain_forward", "ipk_flowtrain_backward", "ipk_flowtrain_destroy", "ipk_adam_step",
 ]
 

@@ -98,6 +98,96 @@ CUtensorMap tc_make_map_f32(const float* base, int rank, const long long* dims, 
   return make_map(base, rank, dims, strides_bytes, box, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
 }
 
+// ------------------------------------------------------------------------------------------------ tile planning (pure host logic)
+// N tiling of one launch: kernel instantiation BN (32 / 64 / 128 / 256: shared-memory and TMEM capacity), columns per tile `bn` (any
+// multiple of 16 up to BN: UMMA N, W box and epilogue follow it), CTA pairs (CG = 2) and, for wide layers on pairs, uneven tiles.
+// Checked on the CPU through ipk_test_tc_plan (tests/test_cabi_exports.py).
+struct TcTilePlan {
+  int BN = 32, bn = 32, CG = 1, tiles_n = 1, nv_tiles = 0;
+  short nv_n0[TC_MAX_NV] = {0}, nv_w[TC_MAX_NV] = {0};
+};
+static TcTilePlan tc_plan_tiles(int Npad, int tiles_m, int total_iters, int nsub, int nsplit, bool fused_epilogue, int sms) {
+  TcTilePlan p;
+  // weigh padded columns (MMA work) against A-tile re-reads (one per N tile)
+  int bn_eff = 32;
+  {
+    static const int flex_env = []() { const char* e = getenv("IPK_TC_FLEX_BN"); return e ? atoi(e) : 1; }();     // 0: power-of-two tiles only
+    double best = 1e30;
+    const int tn0 = cdiv(Npad, 256);
+    for (int tn = tn0; tn <= tn0 + 8; ++tn) {
+      int bn = round_up(cdiv(Npad, tn), 16);
+      if (flex_env == 0) { int p2 = 32; while (p2 < bn) p2 *= 2; bn = p2; }
+      if (bn > 256) continue;
+      if (bn < 32) bn = 32;
+      const double cost = (double)cdiv(Npad, bn) * bn * (1.0 + 32.0 / bn);
+      if (cost < best - 1e-9) { best = cost; bn_eff = bn; }
+      if (bn == 32) break;
+    }
+  }
+  // Small batches (the GUI's B = 1 call, testing/gui.py:139-148: one M tile): the launch is bound by how fast the CTAs can stream the
+  // weights, so narrower N tiles that put the layer on more SMs win over MMA efficiency -- halve the tile while the launch would leave
+  // more than half of the machine idle and the main loop is long enough to matter.
+  if (!fused_epilogue)
+    while (bn_eff > 32 && tiles_m <= 2 && (long long)tiles_m * cdiv(Npad, bn_eff) * std::max(1, nsub) * nsplit * 2 <= sms && total_iters >= 8)
+      bn_eff = std::max(32, round_up(bn_eff / 2, 16));
+  // experiment knobs: force the N tile of short-K / long-K wide layers (measured, r02: narrower tiles for NICE conv1 and UNIFORM 240- or
+  // 224-column tiles for conv2 do not win; the uneven plan below does)
+  static const int shortk_bn = []() { const char* e = getenv("IPK_TC_SHORTK_BN"); return e ? atoi(e) : 0; }();
+  if (shortk_bn >= 32 && shortk_bn <= 256 && shortk_bn % 32 == 0 && Npad >= 1024 && total_iters < 8 && nsub == 1) bn_eff = shortk_bn;
+  static const int longk_bn = []() { const char* e = getenv("IPK_TC_LONGK_BN"); return e ? atoi(e) : 0; }();
+  if (longk_bn >= 32 && longk_bn <= 256 && longk_bn % 16 == 0 && Npad >= 1024 && total_iters >= 8 && nsub == 1) bn_eff = longk_bn;
+  p.BN = bn_eff <= 32 ? 32 : (bn_eff <= 64 ? 64 : (bn_eff <= 128 ? 128 : 256));
+  // CTA pairs (cta_group::2): two consecutive M tiles share one N tile and each CTA stages half of its weights (IPK_TC_CTA2=0 disables,
+  // =2 also pairs short main loops).  Measured on B200: a win where the W tile dominates the stage bytes and the main loop is long (NICE
+  // conv2 19.2 -> 16.9 ms per step, N = K = 2048); a loss for narrow N tiles (A traffic dominates, and the pair's lock-step epilogue
+  // hand-off costs more than the halved W fetch saves) and for short main loops (NICE conv1, K <= 192: epilogue-bound).
+  static const int cta2_env = []() { const char* e = getenv("IPK_TC_CTA2"); return e ? atoi(e) : 1; }();
+  p.CG = (cta2_env > 0 && tiles_m >= 2 && p.BN == 256 && (cta2_env > 1 || total_iters >= 8)) ? 2 : 1;
+  // Uneven N tiles for wide layers on CTA pairs (NICE conv2 at B = 64: 16 M-tile groups x 8 tiles of 256 columns = 128 pair-units on 74
+  // pairs, i.e. 54 pairs run two units and 20 run one).  Nine tiles per group (seven of 224 columns and two of 240) are 144 units: every
+  // pair runs at most two, and with the wide tiles dealt out first no pair gets two of them -- the longest pair does 240 + 224 columns
+  // instead of 512, in lock-step like the uniform schedule (a stream-K split loses the lock-step and measured slower).
+  // The UMMA main loop was measured proportional to N (47.3 / 41.5 / 36.7 kcycles per unit at N = 256 / 224 / 192).
+  static const int nv_env = []() { const char* e = getenv("IPK_TC_NV"); return e ? atoi(e) : 2; }();     // 0 = off, 1 = widths in multiples of 32, 2 = of 16
+  if (nv_env > 0 && p.CG == 2 && nsub == 1 && nsplit == 1 && Npad % 32 == 0 && Npad >= 1024) {
+    // widths in multiples of 16 (default; a 16-column tail chunk takes the direct stores): measured 16.8 -> 16.5 ms per step against the
+    // multiples-of-32 plan (8 x 224 + 256)
+    const int gran = nv_env > 1 ? 16 : 32;
+    const int mgs = cdiv(tiles_m, 2), slots = std::max(1, sms / 2), chunks = Npad / gran;
+    const int tn_u = cdiv(Npad, bn_eff);
+    const double cost_u = (double)cdiv(mgs * tn_u, slots) * (bn_eff + 32);
+    double best = cost_u * 0.97;       // must win by 3 %
+    for (int tn = tn_u; tn <= std::min(TC_MAX_NV, tn_u + 3); ++tn) {
+      const int base = chunks / tn, rem = chunks % tn;
+      if ((base + (rem ? 1 : 0)) * gran > 256 || base == 0) continue;
+      std::vector<double> load(slots, 0.0);
+      for (int u = 0; u < mgs * tn; ++u) load[u % slots] += ((u / mgs) < rem ? base + 1 : base) * gran + 32;     // wide slots first, group fastest
+      const double cost = *std::max_element(load.begin(), load.end());
+      if (cost < best - 1e-9) {
+        best = cost;
+        p.nv_tiles = tn;
+        int off = 0;        // wide tiles take the first columns; their slots come first in the unit order too
+        for (int i = 0; i < tn; ++i) { p.nv_n0[i] = (short)off; p.nv_w[i] = (short)((i < rem ? base + 1 : base) * gran); off += p.nv_w[i]; }
+      }
+    }
+    if (p.nv_tiles > 0) bn_eff = p.nv_w[0];      // the widest tile: W box rows, shared-memory stage and TMEM columns follow it
+  }
+  p.bn = bn_eff;
+  p.tiles_n = p.nv_tiles > 0 ? p.nv_tiles : cdiv(Npad, bn_eff);
+  return p;
+}
+}  // namespace ipk
+// out[0..4] = BN, bn, CG, tiles_n, nv_tiles; out[5 + 2 i], out[6 + 2 i] = first column and width of uneven tile i (i < nv_tiles)
+extern "C" int ipk_test_tc_plan(int32_t Npad, int32_t tiles_m, int32_t total_iters, int32_t nsub, int32_t nsplit, int32_t fused, int32_t sms, int32_t* out) {
+  IPK_TRY
+  IPK_CHECK(out && Npad > 0 && Npad % 16 == 0 && tiles_m > 0 && total_iters > 0 && nsub >= 1 && nsplit >= 1 && sms > 0, IPK_ERR_INVALID, "ipk_test_tc_plan: bad argument");
+  const ipk::TcTilePlan p = ipk::tc_plan_tiles(Npad, tiles_m, total_iters, nsub, nsplit, fused != 0, sms);
+  out[0] = p.BN; out[1] = p.bn; out[2] = p.CG; out[3] = p.tiles_n; out[4] = p.nv_tiles;
+  for (int i = 0; i < p.nv_tiles; ++i) { out[5 + 2 * i] = p.nv_n0[i]; out[6 + 2 * i] = p.nv_w[i]; }
+  IPK_CATCH
+}
+namespace ipk {
+
 static int conv_tc_impl(const ConvW& w, const ConvIn& in, const ConvOut& out, const ConvSub* subs, int nsub, int nsplit, cudaStream_t st) {
   IPK_CHECK(w.w_hi != nullptr, IPK_ERR_STATE, "conv_tc_run: layer was not packed for the tensor-core engine");
   IPK_CHECK(nsub >= 1 && nsub <= TC_MAX_SUB, IPK_ERR_INVALID, "conv_tc_run: bad sub-convolution count %d", nsub);
@@ -181,77 +271,13 @@ static int conv_tc_impl(const ConvW& w, const ConvIn& in, const ConvOut& out, co
   const __nv_bfloat16* ahi = (const __nv_bfloat16*)in.p + in.coff;
   CUtensorMap mA_hi = make_map(ahi, 4, ad, as, ab);
   CUtensorMap mA_lo = split ? make_map((const __nv_bfloat16*)in.p_lo + in.coff, 4, ad, as, ab) : mA_hi;
-  // N tile: `bn` columns per tile, any multiple of 16 up to 256 (UMMA N), run by the kernel instantiation with the next larger BN
-  // (32 / 64 / 128 / 256: shared-memory and TMEM capacity).  Weigh padded columns (MMA work) against A-tile re-reads (one per N tile).
-  int BN = 32, bn_eff = 32;
-  {
-    static const int flex_env = []() { const char* e = getenv("IPK_TC_FLEX_BN"); return e ? atoi(e) : 1; }();     // 0: power-of-two tiles only
-    double best = 1e30;
-    const int tn0 = cdiv(w.Npad, 256);
-    for (int tn = tn0; tn <= tn0 + 8; ++tn) {
-      int bn = round_up(cdiv(w.Npad, tn), 16);
-      if (flex_env == 0) { int p2 = 32; while (p2 < bn) p2 *= 2; bn = p2; }
-      if (bn > 256) continue;
-      if (bn < 32) bn = 32;
-      const double cost = (double)cdiv(w.Npad, bn) * bn * (1.0 + 32.0 / bn);
-      // (Measured, r02: counting waves of the persistent grid instead -- 9 tiles of 240 columns for the 2 048-wide NICE convs, the same two
-      //  waves as 8 x 256 -- is SLOWER: conv2 17.3 -> 22.8 ms per step; UMMA N = 240 and 120-row W boxes lose more than the 6 % they save.)
-      if (cost < best - 1e-9) { best = cost; bn_eff = bn; }
-      if (bn == 32) break;
-    }
-  }
   a.tiles_m = a.tiles_x * a.tiles_y * tiles_f;
-  // Small batches (the GUI's B = 1 call, testing/gui.py:139-148: one M tile): the launch is bound by how fast the CTAs can stream the
-  // weights, so narrower N tiles that put the layer on more SMs win over MMA efficiency -- halve the tile while the launch would leave
-  // more than half of the machine idle and the main loop is long enough to matter.
-  if (!out.res && !out.stats && !(out.second && out.second->stats))
-    while (bn_eff > 32 && a.tiles_m <= 2 && (long long)a.tiles_m * cdiv(w.Npad, bn_eff) * std::max(1, nsub) * nsplit * 2 <= sm_count_host() && max_taps * a.nkb >= 8)
-      bn_eff = std::max(32, round_up(bn_eff / 2, 16));
-  // short main loops on wide layers (NICE conv1: K <= 192, N = 2 048) are epilogue-bound: narrower tiles give the persistent grid a finer
-  // granularity (IPK_TC_SHORTK_BN, 0 = keep the cost model's tile)
-  static const int shortk_bn = []() { const char* e = getenv("IPK_TC_SHORTK_BN"); return e ? atoi(e) : 0; }();
-  if (shortk_bn >= 32 && shortk_bn <= 256 && shortk_bn % 32 == 0 && w.Npad >= 1024 && max_taps * a.nkb < 8 && nsub == 1) bn_eff = shortk_bn;
-  static const int longk_bn = []() { const char* e = getenv("IPK_TC_LONGK_BN"); return e ? atoi(e) : 0; }();     // experiment: N tile of the long-K 2 048-wide layers
-  if (longk_bn >= 32 && longk_bn <= 256 && longk_bn % 16 == 0 && w.Npad >= 1024 && max_taps * a.nkb >= 8 && nsub == 1) bn_eff = longk_bn;
-  BN = bn_eff <= 32 ? 32 : (bn_eff <= 64 ? 64 : (bn_eff <= 128 ? 128 : 256));
-  // CTA pairs (cta_group::2): two consecutive M tiles share one N tile and each CTA stages half of its weights (IPK_TC_CTA2=0 disables,
-  // =2 also pairs short main loops).
-  static const int cta2_env = []() { const char* e = getenv("IPK_TC_CTA2"); return e ? atoi(e) : 1; }();
-  // Measured on B200 (profiles/r02_cta2_ab.md): a win where the W tile dominates the stage bytes and the main loop is long (NICE conv2
-  // 19.2 -> 16.9 ms per step, N = K = 2048); a loss for narrow N tiles (A traffic dominates, and the pair's lock-step epilogue hand-off
-  // costs more than the halved W fetch saves) and for short main loops (NICE conv1, K <= 192: epilogue-bound).
-  const int CG = (cta2_env > 0 && a.tiles_m >= 2 && BN == 256 && (cta2_env > 1 || max_taps * a.nkb >= 8)) ? 2 : 1;
-  // ---- uneven N tiles for wide layers on CTA pairs (NICE conv2 at B = 64: 16 M-tile groups x 8 tiles of 256 columns = 128 pair-units on
-  //      74 pairs, i.e. 54 pairs run two units and 20 run one).  Nine tiles per group (eight of 224 columns, one of 256) are 144 units: every
-  //      pair runs at most two, and with the wide tiles dealt out first no pair gets two of them -- the longest pair does 224 + 256 columns
-  //      instead of 512, in lock-step like the uniform schedule (a stream-K split loses the lock-step and measured slower).
-  //      The UMMA main loop was measured proportional to N (47.3 / 41.5 / 36.7 kcycles per unit at N = 256 / 224 / 192).
-  static const int nv_env = []() { const char* e = getenv("IPK_TC_NV"); return e ? atoi(e) : 2; }();     // 0 = off, 1 = widths in multiples of 32, 2 = of 16
-  int nv_tiles = 0;
-  short nv_n0[TC_MAX_NV], nv_w[TC_MAX_NV];
-  if (nv_env > 0 && CG == 2 && nsub == 1 && nsplit == 1 && w.Npad % 32 == 0 && w.Npad >= 1024) {
-    // widths in multiples of 16 (default; a 16-column tail chunk takes the direct stores): 7 x 224 + 2 x 240 columns, the longest pair runs
-    // 240 + 224; measured 16.8 -> 16.5 ms per step against the multiples-of-32 plan (8 x 224 + 256)
-    const int gran = nv_env > 1 ? 16 : 32;
-    const int mgs = cdiv(a.tiles_m, 2), slots = std::max(1, sm_count_host() / 2), chunks = w.Npad / gran;
-    const int tn_u = cdiv(w.Npad, bn_eff);
-    const double cost_u = (double)cdiv(mgs * tn_u, slots) * (bn_eff + 32);
-    double best = cost_u * 0.97;       // must win by 3 %
-    for (int tn = tn_u; tn <= std::min(TC_MAX_NV, tn_u + 3); ++tn) {
-      const int base = chunks / tn, rem = chunks % tn;
-      if ((base + (rem ? 1 : 0)) * gran > 256 || base == 0) continue;
-      std::vector<double> load(slots, 0.0);
-      for (int u = 0; u < mgs * tn; ++u) load[u % slots] += ((u / mgs) < rem ? base + 1 : base) * gran + 32;     // wide slots first, group fastest
-      const double cost = *std::max_element(load.begin(), load.end());
-      if (cost < best - 1e-9) {
-        best = cost;
-        nv_tiles = tn;
-        int off = 0;        // wide tiles take the first columns; their slots come first in the unit order too
-        for (int i = 0; i < tn; ++i) { nv_n0[i] = (short)off; nv_w[i] = (short)((i < rem ? base + 1 : base) * gran); off += nv_w[i]; }
-      }
-    }
-    if (nv_tiles > 0) bn_eff = nv_w[0];      // the widest tile: W box rows, shared-memory stage and TMEM columns follow it
-  }
+  const TcTilePlan plan = tc_plan_tiles(w.Npad, a.tiles_m, max_taps * a.nkb, nsub, nsplit, out.res || out.stats || (out.second && out.second->stats),
+                                        sm_count_host());
+  const int BN = plan.BN, CG = plan.CG, nv_tiles = plan.nv_tiles;
+  int bn_eff = plan.bn;
+  const short* nv_n0 = plan.nv_n0;
+  const short* nv_w = plan.nv_w;
   long long wd[2] = {w.Kpad, (long long)w.ntaps * w.Npad};
   long long wsb[1] = {(long long)w.Kpad * 2};
   int wb[2] = {TC_BK, bn_eff / CG};

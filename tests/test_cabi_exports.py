@@ -129,3 +129,46 @@ def test_state_dict_layout_matches_oracle_checkpoint():
         assert sorted(own.keys()) == sorted(esd.keys())
         for k in esd:
             assert own[k].shape == esd[k].shape, k
+
+
+def _tc_plan(Npad, tiles_m, iters, nsub=1, nsplit=1, fused=0, sms=148):
+    import ctypes
+    from ipoke_b200 import _lib
+    out = (ctypes.c_int32 * 40)()
+    _lib.check(_lib.lib().ipk_test_tc_plan(Npad, tiles_m, iters, nsub, nsplit, fused, sms, out), "ipk_test_tc_plan")
+    BN, bn, CG, tiles_n, nv = out[0], out[1], out[2], out[3], out[4]
+    return BN, bn, CG, tiles_n, [(out[5 + 2 * i], out[6 + 2 * i]) for i in range(nv)]
+
+
+def test_conv_engine_tile_planning_host_logic():
+    """N tiling of the tcgen05 conv engine (conv_tc.cu: tc_plan_tiles), pure host logic, for the shapes of the sampling path on 148 SMs."""
+    # invariants over a sweep of layer widths / batch sizes
+    for Npad in (16, 32, 48, 64, 80, 96, 128, 144, 160, 192, 224, 256, 288, 512, 1024, 2048):
+        for tiles_m in (1, 2, 7, 32, 2048):
+            for iters in (1, 3, 9, 32, 288):
+                BN, bn, CG, tiles_n, nv = _tc_plan(Npad, tiles_m, iters)
+                assert BN in (32, 64, 128, 256) and bn % 16 == 0 and 32 <= bn <= BN and CG in (1, 2)
+                if CG == 2:
+                    assert BN == 256 and tiles_m >= 2 and iters >= 8
+                if nv:
+                    widths = [w for _, w in nv]
+                    assert tiles_n == len(nv) and sum(widths) == Npad and max(widths) == bn == widths[0]
+                    assert widths == sorted(widths, reverse=True) and all(w % 16 == 0 for w in widths)
+                    assert [n0 for n0, _ in nv] == [sum(widths[:i]) for i in range(len(nv))]
+                else:
+                    assert tiles_n * bn >= Npad > (tiles_n - 1) * bn
+    # NICE conv2 at B = 64 (M = 4096, N = K = 2048): CTA pairs, nine uneven tiles per M-tile group, no pair runs two wide tiles
+    BN, bn, CG, tiles_n, nv = _tc_plan(2048, 32, 32)
+    assert (BN, CG, tiles_n) == (256, 2, 9) and [w for _, w in nv] == [240, 240] + [224] * 7
+    load = [0] * 74
+    for u in range(16 * 9):
+        load[u % 74] += nv[u // 16][1]
+    assert max(load) == 240 + 224 < 2 * 256
+    # NICE conv1 (K <= 192: three k-blocks): single CTAs, uniform 256-column tiles; conv3 (288 columns): two tiles of 144
+    assert _tc_plan(2048, 32, 3)[:4] == (256, 256, 1, 8)
+    assert _tc_plan(288, 32, 32)[1:4:2] == (144, 2)
+    # the GUI's B = 1 call (one M tile): narrow tiles put the weight stream on at least half of the machine
+    BN, bn, CG, tiles_n, nv = _tc_plan(2048, 1, 32)
+    assert CG == 1 and not nv and tiles_n * 2 > 148 // 2 and bn <= 64
+    # fused-epilogue launches keep the cost model's tile
+    assert _tc_plan(256, 1, 36, fused=1)[1] == 256
