@@ -9,8 +9,9 @@
 // * 128-byte swizzled K-major tiles, UMMA M=128, N=BN, K=16 (kind::f16, bf16 inputs, fp32 accumulation in TMEM).
 // * fp32 fidelity mode (NSPLIT=3): every operand is a pair of bf16 planes (hi, lo = bf16(x - hi)) and each K-step issues
 //   three MMAs  hi*hi + lo*hi + hi*lo  into the same accumulator (error-compensated "bf16x3", ~2^-16 relative).
-// * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane), warps 2..5 = epilogue
-//   (TMEM -> registers -> bias / activation / operand split -> global).
+// * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane), warps 2..9 = epilogue
+//   (TMEM -> registers -> bias / activation / residual / statistics -> TMA stores of bf16 operand planes or coalesced fp32 rows).
+// This file is the host side (tensor maps, tile planning, launch); the kernel is conv_tc_kernel.cuh, instantiated in conv_tc_bn*.cu.
 #include <cuda.h>
 #include <cstring>
 #include <map>
